@@ -1,0 +1,218 @@
+/*
+ * instantrestore_b200 — C ABI of the B200 (sm_100a) kernels behind the InstantRestore hot path.
+ *
+ * The reference (snap-research/InstantRestore) is pure Python: it has no FFI. Every entry point below
+ * replaces a chain of torch/diffusers library calls reached from the cited reference lines; the
+ * reference-side binding is the ctypes stub in INTEGRATION.md (and instantrestore_b200/_lib.py here).
+ *
+ * Conventions
+ *  - Plain pointers + sizes only; the caller owns every buffer (torch caching allocator on the Python side).
+ *    Kernels never allocate or free device memory and never synchronise; they launch on `stream`.
+ *  - Activations are fp16, channel-last ("NHWC" == token-major [B, H*W, C]); accumulation is fp32.
+ *  - Return 0 on success, a negative IR_ERR_* otherwise; ir_last_error_string() describes the last failure
+ *    on the calling thread. Nothing throws across the ABI.
+ *  - All entry points are re-entrant and CUDA-graph capturable (TMA descriptors travel as kernel parameters).
+ *  - Device pointers must be 16-byte aligned; row strides are in ELEMENTS and must be multiples of 8.
+ */
+#ifndef INSTANTRESTORE_B200_H_
+#define INSTANTRESTORE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IR_OK 0
+#define IR_ERR_SHAPE (-1)       /* unsupported / inconsistent shape */
+#define IR_ERR_ALIGN (-2)       /* misaligned pointer or stride */
+#define IR_ERR_ARCH (-3)        /* device is not sm_100 */
+#define IR_ERR_CUDA (-4)        /* CUDA runtime / driver error */
+#define IR_ERR_ARG (-5)         /* NULL or invalid argument */
+
+#define IR_ACT_NONE 0
+#define IR_ACT_GEGLU 1          /* out[:, j] = v[:, j] * gelu_erf(g[:, j]); weights interleaved, see ir_conv_gemm */
+#define IR_ACT_SILU 2
+
+typedef void* ir_stream_t;      /* cudaStream_t */
+
+const char* ir_last_error_string(void);
+int ir_version(void);
+/* 0 when the current device is a B200-class (sm_100) GPU, IR_ERR_ARCH / IR_ERR_CUDA otherwise. */
+int ir_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * ir_conv_gemm — im2col-free implicit GEMM on tcgen05 tensor cores (TMA-staged, TMEM accumulators).
+ * Replaces nn.Conv2d 3x3 / 3x3 stride-2 / 1x1 and nn.Linear as reached from
+ *   reference face_replace/models/unet_2d_condition/block.py:1061,1106,2239,2282,2397,2414 (ResnetBlock2D,
+ *   Downsample2D, Upsample2D convs), unet.py:289,612 (conv_in/conv_out) and the q/k/v/out/proj/ff Linears
+ *   called from face_replace/models/attn_processors.py:222,229-230,267.
+ *
+ *   out[m, n] = epilogue( sum_{tap, c} A[pixel(m) + tap, c] * W[n, tap * c_in + c] )
+ *
+ * A: fp16 [batch, h_in, w_in, >= c_in] (pixel stride a_row_stride elements). ksize 1 (stride 1) or 3
+ *    (stride 1 or 2, zero padding 1). A linear layer is ksize=1 with batch=1, h_in=1, w_in=tokens.
+ * W: fp16 [c_out, ksize*ksize*c_in], K contiguous, tap-major then channel.  c_in % 64 == 0.
+ * Epilogue: + bias[n] (fp32, optional); round to fp16; + residual[m, n] (fp16, optional);
+ *    act: IR_ACT_GEGLU expects W rows interleaved in blocks of 64 (64 value rows, then their 64 gate rows)
+ *    and writes c_out/2 columns; IR_ACT_SILU applies x*sigmoid(x).
+ * out: fp16 [M, c_out or c_out/2] with row stride out_row_stride.
+ */
+typedef struct {
+  const void* a;
+  int batch, h_in, w_in, c_in;
+  int a_row_stride;
+  int ksize, stride;
+  const void* w;
+  int c_out;
+  const float* bias;
+  const void* residual;
+  int res_row_stride;
+  int act;
+  void* out;
+  int out_row_stride;
+  int tile_n; /* 0 = auto; else 64, 128, 160 or 256 */
+} ir_conv_gemm_params;
+int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ir_shared_attn_fwd — fused shared-image attention: softmax(Q K^T * scale) V with K/V streamed from
+ * [own tokens (optional)] ++ [n_ref reference images], online softmax, AdaIN on reference values applied
+ * as a per-(batch, ref, channel) affine  V' = adain_scale * V + adain_shift  inside the kernel.
+ * Replaces reference face_replace/models/attn_processors.py:232-264 (SharedAttnProcessor.forward: head split,
+ * adain(), torch.cat, get_attention_scores (baddbmm + softmax), torch.bmm, batch_to_head_dim) and the same
+ * lines of AttnProcessor.forward (:76-82).  head_dim is 64.
+ *
+ * q:      fp16 [batch, s_q, *]   head h occupies columns q_col_off + 64*h .. +63 (row stride q_row_stride)
+ * k_own/v_own: fp16 [batch or 1, s_own, *] (NULL: no own chunk); s_own need not be a multiple of the KV tile
+ *         (tail keys are masked). own_shared != 0: the same K/V serves every batch entry (constant caption).
+ * k_ref/v_ref: fp16 [batch, n_ref, s_ref, *], head h at columns ref_col_off + 64*h (NULL when n_ref == 0).
+ *         Padded reference slots are expected to be ZERO-FILLED by the caller (reference quirk,
+ *         pix2pix_turbo.py:269-273): they still receive softmax mass.
+ * adain_scale/shift: fp32 [batch, n_ref, heads*64] or NULL.
+ * out:    fp16 [batch, s_q, heads*64] (row stride out_row_stride).
+ * chunk_mass: optional fp32 [batch, heads, n_chunks] — attention probability mass per KV chunk averaged over
+ *         queries (what gradio_demo.py:118-133 derives from the dense matrix). NULL to skip.
+ */
+typedef struct {
+  const void* q;
+  int q_row_stride, q_col_off;
+  const void* k_own;
+  const void* v_own;
+  int own_row_stride, k_own_col_off, v_own_col_off;
+  int s_own;
+  int own_shared;
+  const void* k_ref;
+  const void* v_ref;
+  int ref_row_stride, ref_col_off;
+  int n_ref, s_ref;
+  const float* adain_scale;
+  const float* adain_shift;
+  int batch, heads, s_q;
+  float scale;
+  void* out;
+  int out_row_stride;
+  float* chunk_mass;
+} ir_shared_attn_params;
+int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ir_groupnorm — GroupNorm(+optional SiLU) on channel-last fp16, statistics in fp32 (two passes, centred).
+ * Replaces diffusers ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm and
+ * unet.py:1167-1169 (conv_norm_out + conv_act).
+ * x: fp16 [batch, hw, channels] (row stride x_row_stride); gamma/beta fp32 [channels];
+ * out fp16 [batch, hw, channels]; workspace: ir_groupnorm_workspace_bytes(batch, groups) bytes of device memory
+ * (per-(batch, group) mean / rstd), caller-owned.
+ */
+typedef struct {
+  const void* x;
+  int x_row_stride;
+  int batch, hw, channels, groups;
+  float eps;
+  const float* gamma;
+  const float* beta;
+  int silu;
+  void* out;
+  int out_row_stride;
+  void* workspace;
+} ir_groupnorm_params;
+size_t ir_groupnorm_workspace_bytes(int batch, int groups);
+int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream);
+
+/* ir_layernorm — LayerNorm over the last dim of fp16 [rows, channels]; fp32 statistics.
+ * Replaces diffusers BasicTransformerBlock.norm1/2/3 (reached from block.py:2355-2362). */
+typedef struct {
+  const void* x;
+  int x_row_stride;
+  int rows, channels;
+  float eps;
+  const float* gamma;
+  const float* beta;
+  void* out;
+  int out_row_stride;
+} ir_layernorm_params;
+int ir_layernorm(const ir_layernorm_params* p, ir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ir_adain_coeffs — AdaIN statistics folded to an affine (attn_processors.py:7-18, 244-245):
+ *   style_mean/std over tokens of the own V;  content mean/std over tokens of each reference V;
+ *   scale = style_std / content_std,  shift = style_mean - content_mean * scale
+ *   (std unbiased, +1e-5 added to the std as in the reference).
+ * v_own: fp16 [batch, s_own, *] columns v_col_off .. +channels; v_ref: fp16 [batch, n_ref, s_ref, *].
+ * scale/shift: fp32 [batch, n_ref, channels].
+ * workspace: ir_adain_workspace_bytes(batch, n_ref, channels) bytes (per-chunk mean / std), caller-owned.
+ */
+typedef struct {
+  const void* v_own;
+  int own_row_stride, v_col_off, s_own;
+  const void* v_ref;
+  int ref_row_stride, ref_col_off, n_ref, s_ref;
+  int batch, channels;
+  float eps;
+  float* scale;
+  float* shift;
+  void* workspace;
+} ir_adain_coeffs_params;
+size_t ir_adain_workspace_bytes(int batch, int n_ref, int channels);
+int ir_adain_coeffs(const ir_adain_coeffs_params* p, ir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ir_concat_freeu — builds the up-block resnet input cat([hidden, skip], channels) and applies FreeU
+ * (block.py:2314-2325, 2442-2453, 3495-3520): hidden[:, :C_h/2] *= b and
+ * skip <- fourier_filter(skip, threshold=1, scale=s) evaluated in closed form (4 DFT coefficients per plane).
+ * backbone_scale == 1 and skip_scale == 1 give a plain concat.
+ * hidden fp16 [batch, hw, c_hidden]; skip fp16 [batch, hw, c_skip]; out fp16 [batch, hw, c_hidden + c_skip].
+ * (The reference scales `hidden` in place; that tensor has no other reader, so only `out` carries the result.)
+ */
+typedef struct {
+  const void* hidden;
+  const void* skip;
+  int batch, h, w, c_hidden, c_skip;
+  float backbone_scale;
+  float skip_scale;
+  void* out;
+} ir_concat_freeu_params;
+int ir_concat_freeu(const ir_concat_freeu_params* p, ir_stream_t stream);
+
+/* ir_upsample_nearest2x — F.interpolate(scale_factor=2, mode="nearest") on channel-last fp16
+ * (diffusers Upsample2D, reached from block.py:2366,2476). x [batch,h,w,c] -> out [batch,2h,2w,c]. */
+int ir_upsample_nearest2x(const void* x, void* out, int batch, int h, int w, int c, ir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ir_latent_in — scheduler add_noise + layout change (pix2pix_turbo.py:250-251, 310-311):
+ *   out[b, hw, c] = fp16( a * x[b, c, hw] + s * noise[b, c, hw] ), channels zero-padded to c_pad.
+ * x, noise: fp32 NCHW [batch, c, hw] (noise may be NULL). out: fp16 [batch, hw, c_pad].
+ * ir_latent_out — DDPM pred_original_sample + layout change (pix2pix_turbo.py:277,331):
+ *   out[b, c, hw] = (xt[b, c, hw] - s * eps[b, hw, c]) * inv_a     (fp32 NCHW)
+ * eps: fp16 [batch, hw, c] channel-last (row stride eps_row_stride); xt: fp32 NCHW.
+ */
+int ir_latent_in(const float* x, const float* noise, float a, float s, void* out, int batch, int c, int hw,
+                 int c_pad, ir_stream_t stream);
+int ir_latent_out(const void* eps, int eps_row_stride, const float* xt, float s, float inv_a, float* out, int batch,
+                  int c, int hw, ir_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSTANTRESTORE_B200_H_ */

@@ -1,0 +1,284 @@
+"""ctypes binding of include/instantrestore_b200.h (the C ABI of the sm_100a kernels).
+
+There is no CPU fallback: if the shared library is missing, loading raises. PyTorch is used only for device memory
+and the current CUDA stream; every function below takes tensors, checks dtype/contiguity, and forwards raw pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libinstantrestore_b200.so"
+
+IR_ACT_NONE, IR_ACT_GEGLU, IR_ACT_SILU = 0, 1, 2
+
+EXPORTED_SYMBOLS = [
+    "ir_last_error_string", "ir_version", "ir_check_device", "ir_conv_gemm", "ir_shared_attn_fwd",
+    "ir_groupnorm", "ir_groupnorm_workspace_bytes", "ir_layernorm", "ir_adain_coeffs", "ir_adain_workspace_bytes",
+    "ir_concat_freeu", "ir_upsample_nearest2x", "ir_latent_in", "ir_latent_out",
+]
+
+
+class ConvGemmParams(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("batch", C.c_int), ("h_in", C.c_int), ("w_in", C.c_int), ("c_in", C.c_int),
+        ("a_row_stride", C.c_int), ("ksize", C.c_int), ("stride", C.c_int),
+        ("w", C.c_void_p), ("c_out", C.c_int), ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("res_row_stride", C.c_int), ("act", C.c_int), ("out", C.c_void_p), ("out_row_stride", C.c_int),
+        ("tile_n", C.c_int),
+    ]
+
+
+class SharedAttnParams(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("q_row_stride", C.c_int), ("q_col_off", C.c_int),
+        ("k_own", C.c_void_p), ("v_own", C.c_void_p),
+        ("own_row_stride", C.c_int), ("k_own_col_off", C.c_int), ("v_own_col_off", C.c_int),
+        ("s_own", C.c_int), ("own_shared", C.c_int),
+        ("k_ref", C.c_void_p), ("v_ref", C.c_void_p),
+        ("ref_row_stride", C.c_int), ("ref_col_off", C.c_int), ("n_ref", C.c_int), ("s_ref", C.c_int),
+        ("adain_scale", C.c_void_p), ("adain_shift", C.c_void_p),
+        ("batch", C.c_int), ("heads", C.c_int), ("s_q", C.c_int), ("scale", C.c_float),
+        ("out", C.c_void_p), ("out_row_stride", C.c_int), ("chunk_mass", C.c_void_p),
+    ]
+
+
+class GroupNormParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_row_stride", C.c_int), ("batch", C.c_int), ("hw", C.c_int), ("channels", C.c_int),
+        ("groups", C.c_int), ("eps", C.c_float), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("silu", C.c_int),
+        ("out", C.c_void_p), ("out_row_stride", C.c_int), ("workspace", C.c_void_p),
+    ]
+
+
+class LayerNormParams(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_row_stride", C.c_int), ("rows", C.c_int), ("channels", C.c_int), ("eps", C.c_float),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("out", C.c_void_p), ("out_row_stride", C.c_int),
+    ]
+
+
+class AdainCoeffsParams(C.Structure):
+    _fields_ = [
+        ("v_own", C.c_void_p), ("own_row_stride", C.c_int), ("v_col_off", C.c_int), ("s_own", C.c_int),
+        ("v_ref", C.c_void_p), ("ref_row_stride", C.c_int), ("ref_col_off", C.c_int), ("n_ref", C.c_int),
+        ("s_ref", C.c_int), ("batch", C.c_int), ("channels", C.c_int), ("eps", C.c_float),
+        ("scale", C.c_void_p), ("shift", C.c_void_p), ("workspace", C.c_void_p),
+    ]
+
+
+class ConcatFreeuParams(C.Structure):
+    _fields_ = [
+        ("hidden", C.c_void_p), ("skip", C.c_void_p), ("batch", C.c_int), ("h", C.c_int), ("w", C.c_int),
+        ("c_hidden", C.c_int), ("c_skip", C.c_int), ("backbone_scale", C.c_float), ("skip_scale", C.c_float),
+        ("out", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the C-ABI library. Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m instantrestore_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU/PyTorch fallback for the product path."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    lib.ir_last_error_string.restype = C.c_char_p
+    lib.ir_groupnorm_workspace_bytes.restype = C.c_size_t
+    lib.ir_adain_workspace_bytes.restype = C.c_size_t
+    lib.ir_conv_gemm.argtypes = [C.POINTER(ConvGemmParams), C.c_void_p]
+    lib.ir_shared_attn_fwd.argtypes = [C.POINTER(SharedAttnParams), C.c_void_p]
+    lib.ir_groupnorm.argtypes = [C.POINTER(GroupNormParams), C.c_void_p]
+    lib.ir_layernorm.argtypes = [C.POINTER(LayerNormParams), C.c_void_p]
+    lib.ir_adain_coeffs.argtypes = [C.POINTER(AdainCoeffsParams), C.c_void_p]
+    lib.ir_concat_freeu.argtypes = [C.POINTER(ConcatFreeuParams), C.c_void_p]
+    lib.ir_upsample_nearest2x.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.ir_latent_in.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p]
+    lib.ir_latent_out.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_int, C.c_void_p]
+    lib.ir_debug_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_uint] * 6 + [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {load().ir_last_error_string().decode()}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _h(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float16 or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA fp16 tensor, got {t.dtype} on {t.device}")
+    if t.stride(-1) != 1:
+        raise ValueError(f"{name}: innermost dimension must be contiguous")
+    return t
+
+
+def _f(t: torch.Tensor | None, name: str) -> torch.Tensor | None:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise TypeError(f"{name}: expected a contiguous CUDA fp32 tensor")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------- wrappers
+def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: int, c_in: int, ksize: int = 1,
+              stride: int = 1, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
+              act: int = IR_ACT_NONE, out: torch.Tensor | None = None, tile_n: int = 0,
+              a_row_stride: int | None = None) -> torch.Tensor:
+    """a: fp16 channel-last [batch*h_in*w_in, >=c_in]; w: fp16 [c_out, ksize*ksize*c_in]."""
+    _h(a, "a"); _h(w, "w"); _f(bias, "bias")
+    c_out = w.shape[0]
+    assert w.shape[1] == ksize * ksize * c_in and w.is_contiguous(), (w.shape, ksize, c_in)
+    m = batch * (h_in // stride) * (w_in // stride)
+    n_out = c_out // 2 if act == IR_ACT_GEGLU else c_out
+    if out is None:
+        out = torch.empty((m, n_out), dtype=torch.float16, device=a.device)
+    p = ConvGemmParams(
+        a=ptr(a), batch=batch, h_in=h_in, w_in=w_in, c_in=c_in,
+        a_row_stride=a_row_stride if a_row_stride is not None else a.stride(-2),
+        ksize=ksize, stride=stride, w=ptr(w), c_out=c_out, bias=ptr(bias),
+        residual=ptr(residual), res_row_stride=residual.stride(-2) if residual is not None else 0,
+        act=act, out=ptr(out), out_row_stride=out.stride(-2), tile_n=tile_n)
+    check(load().ir_conv_gemm(C.byref(p), stream_ptr()), "ir_conv_gemm")
+    return out
+
+
+def shared_attn(q: torch.Tensor, *, heads: int, scale: float, batch: int, s_q: int,
+                k_own: torch.Tensor | None = None, v_own: torch.Tensor | None = None, s_own: int = 0,
+                own_shared: bool = False, q_col_off: int = 0, k_own_col_off: int = 0, v_own_col_off: int = 0,
+                k_ref: torch.Tensor | None = None, v_ref: torch.Tensor | None = None, n_ref: int = 0, s_ref: int = 0,
+                ref_col_off: int = 0, adain_scale: torch.Tensor | None = None, adain_shift: torch.Tensor | None = None,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+    """q: fp16 [batch*s_q, row]; k_own/v_own: fp16 [(batch|1)*s_own, row]; k_ref/v_ref: fp16 [batch*n_ref*s_ref, row]."""
+    _h(q, "q")
+    if out is None:
+        out = torch.empty((batch * s_q, heads * 64), dtype=torch.float16, device=q.device)
+    p = SharedAttnParams(
+        q=ptr(q), q_row_stride=q.stride(-2), q_col_off=q_col_off,
+        k_own=ptr(k_own), v_own=ptr(v_own), own_row_stride=k_own.stride(-2) if k_own is not None else 0,
+        k_own_col_off=k_own_col_off, v_own_col_off=v_own_col_off, s_own=s_own, own_shared=int(own_shared),
+        k_ref=ptr(k_ref), v_ref=ptr(v_ref), ref_row_stride=k_ref.stride(-2) if k_ref is not None else 0,
+        ref_col_off=ref_col_off, n_ref=n_ref, s_ref=s_ref,
+        adain_scale=ptr(_f(adain_scale, "adain_scale")), adain_shift=ptr(_f(adain_shift, "adain_shift")),
+        batch=batch, heads=heads, s_q=s_q, scale=scale, out=ptr(out), out_row_stride=out.stride(-2), chunk_mass=None)
+    if k_own is not None:
+        _h(k_own, "k_own"); _h(v_own, "v_own")
+        assert k_own.stride(-2) == v_own.stride(-2)
+    if k_ref is not None:
+        _h(k_ref, "k_ref"); _h(v_ref, "v_ref")
+        assert k_ref.stride(-2) == v_ref.stride(-2)
+    check(load().ir_shared_attn_fwd(C.byref(p), stream_ptr()), "ir_shared_attn_fwd")
+    return out
+
+
+def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch: int, hw: int, groups: int = 32,
+              eps: float = 1e-5, silu: bool = False, out: torch.Tensor | None = None,
+              workspace: torch.Tensor | None = None) -> torch.Tensor:
+    _h(x, "x"); _f(gamma, "gamma"); _f(beta, "beta")
+    channels = x.shape[-1]
+    if out is None:
+        out = torch.empty((batch * hw, channels), dtype=torch.float16, device=x.device)
+    if workspace is None:
+        workspace = torch.empty(batch * groups * 2, dtype=torch.float32, device=x.device)
+    p = GroupNormParams(x=ptr(x), x_row_stride=x.stride(-2), batch=batch, hw=hw, channels=channels, groups=groups,
+                        eps=eps, gamma=ptr(gamma), beta=ptr(beta), silu=int(silu), out=ptr(out),
+                        out_row_stride=out.stride(-2), workspace=ptr(workspace))
+    check(load().ir_groupnorm(C.byref(p), stream_ptr()), "ir_groupnorm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-5,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    _h(x, "x"); _f(gamma, "gamma"); _f(beta, "beta")
+    rows, channels = x.shape[-2], x.shape[-1]
+    if out is None:
+        out = torch.empty((rows, channels), dtype=torch.float16, device=x.device)
+    p = LayerNormParams(x=ptr(x), x_row_stride=x.stride(-2), rows=rows, channels=channels, eps=eps, gamma=ptr(gamma),
+                        beta=ptr(beta), out=ptr(out), out_row_stride=out.stride(-2))
+    check(load().ir_layernorm(C.byref(p), stream_ptr()), "ir_layernorm")
+    return out
+
+
+def adain_coeffs(v_own: torch.Tensor, v_ref: torch.Tensor, *, batch: int, s_own: int, n_ref: int, s_ref: int,
+                 channels: int, v_col_off: int = 0, ref_col_off: int = 0, eps: float = 1e-5,
+                 scale: torch.Tensor | None = None, shift: torch.Tensor | None = None,
+                 workspace: torch.Tensor | None = None):
+    _h(v_own, "v_own"); _h(v_ref, "v_ref")
+    dev = v_own.device
+    if scale is None:
+        scale = torch.empty((batch, n_ref, channels), dtype=torch.float32, device=dev)
+    if shift is None:
+        shift = torch.empty((batch, n_ref, channels), dtype=torch.float32, device=dev)
+    if workspace is None:
+        workspace = torch.empty(batch * (1 + n_ref) * channels * 2, dtype=torch.float32, device=dev)
+    p = AdainCoeffsParams(v_own=ptr(v_own), own_row_stride=v_own.stride(-2), v_col_off=v_col_off, s_own=s_own,
+                          v_ref=ptr(v_ref), ref_row_stride=v_ref.stride(-2), ref_col_off=ref_col_off, n_ref=n_ref,
+                          s_ref=s_ref, batch=batch, channels=channels, eps=eps, scale=ptr(scale), shift=ptr(shift),
+                          workspace=ptr(workspace))
+    check(load().ir_adain_coeffs(C.byref(p), stream_ptr()), "ir_adain_coeffs")
+    return scale, shift
+
+
+def concat_freeu(hidden: torch.Tensor, skip: torch.Tensor, *, batch: int, h: int, w: int, backbone_scale: float = 1.0,
+                 skip_scale: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
+    _h(hidden, "hidden"); _h(skip, "skip")
+    assert hidden.is_contiguous() and skip.is_contiguous()
+    ch, cs = hidden.shape[-1], skip.shape[-1]
+    if out is None:
+        out = torch.empty((batch * h * w, ch + cs), dtype=torch.float16, device=hidden.device)
+    p = ConcatFreeuParams(hidden=ptr(hidden), skip=ptr(skip), batch=batch, h=h, w=w, c_hidden=ch, c_skip=cs,
+                          backbone_scale=backbone_scale, skip_scale=skip_scale, out=ptr(out))
+    check(load().ir_concat_freeu(C.byref(p), stream_ptr()), "ir_concat_freeu")
+    return out
+
+
+def upsample_nearest2x(x: torch.Tensor, *, batch: int, h: int, w: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    _h(x, "x")
+    assert x.is_contiguous()
+    c = x.shape[-1]
+    if out is None:
+        out = torch.empty((batch * 4 * h * w, c), dtype=torch.float16, device=x.device)
+    check(load().ir_upsample_nearest2x(ptr(x), ptr(out), batch, h, w, c, stream_ptr()), "ir_upsample_nearest2x")
+    return out
+
+
+def latent_in(x: torch.Tensor, noise: torch.Tensor | None, a: float, s: float, *, c_pad: int = 64,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """x, noise: fp32 NCHW -> fp16 channel-last [B*HW, c_pad] = a*x + s*noise (zero-padded channels)."""
+    _f(x, "x"); _f(noise, "noise")
+    b, c, hh, ww = x.shape
+    if out is None:
+        out = torch.empty((b * hh * ww, c_pad), dtype=torch.float16, device=x.device)
+    check(load().ir_latent_in(ptr(x), ptr(noise), a, s, ptr(out), b, c, hh * ww, c_pad, stream_ptr()), "ir_latent_in")
+    return out
+
+
+def latent_out(eps: torch.Tensor, xt: torch.Tensor, s: float, inv_a: float, *, out: torch.Tensor | None = None) -> torch.Tensor:
+    """eps: fp16 channel-last [B*HW, >=C]; xt: fp32 NCHW -> fp32 NCHW (xt - s*eps) * inv_a."""
+    _h(eps, "eps"); _f(xt, "xt")
+    b, c, hh, ww = xt.shape
+    if out is None:
+        out = torch.empty_like(xt)
+    check(load().ir_latent_out(ptr(eps), eps.stride(-2), ptr(xt), s, inv_a, ptr(out), b, c, hh * ww, stream_ptr()),
+          "ir_latent_out")
+    return out

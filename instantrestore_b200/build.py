@@ -1,0 +1,71 @@
+"""Builds the sm_100a C-ABI library in-tree: instantrestore_b200/libinstantrestore_b200.so.
+
+nvcc cross-compiles without a GPU. Objects are cached under instantrestore_b200/csrc/_obj keyed on source mtime.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libinstantrestore_b200.so"
+SOURCES = ["ir_host.cu", "ir_gemm.cu", "ir_attn.cu", "ir_norm.cu", "ir_misc.cu", "ir_debug.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found; the CUDA extension cannot be built")
+
+
+def _stale(target: Path, deps: list[Path]) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> Path:
+    nvcc = _nvcc()
+    obj_dir = CSRC / "_obj"
+    obj_dir.mkdir(exist_ok=True)
+    headers = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "instantrestore_b200.h"]
+
+    def compile_one(src_name: str) -> Path:
+        src = CSRC / src_name
+        obj = obj_dir / (src.stem + ".o")
+        if force or _stale(obj, [src] + headers):
+            cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            (obj_dir / (src.stem + ".ptxas.log")).write_text(r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src_name}:\n{r.stderr}")
+            if verbose:
+                sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    if force or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,380 @@
+// ir_conv_gemm — im2col-free implicit GEMM on tcgen05 (sm_100a).
+//
+// One CTA computes a 128 (pixels/tokens) x BN (output channels) tile:
+//   warp 0 (one elected lane): TMA producer. Per K step it loads a 128x64 fp16 activation box straight from the
+//       channel-last tensor — for a 3x3 tap the box is shifted by (dy, dx) and TMA's out-of-bounds zero fill IS the
+//       convolution padding; a stride-2 conv reads one of four phase-strided tensor maps — plus a BNx64 weight box.
+//       Both land in 128-byte-swizzled shared memory, exactly the K-major layout tcgen05.mma consumes.
+//   warp 1 (one elected lane): issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage, accumulating in TMEM, and
+//       releases the stage with tcgen05.commit.
+//   all 4 warps: epilogue — tcgen05.ld the accumulator (thread == row), + bias, fp16 round, + residual,
+//       optional GEGLU / SiLU, 16-byte stores.
+// Two CTAs are resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's epilogue overlaps the
+// other's main loop.
+//
+// Roofline: tensor-core bound for C_in*taps >= ~600 (AI = 2*128*BN*K / ((128+BN)*K*2 B)); algorithmic FLOPs per
+// launch = 2 * M * c_out * taps * c_in.
+#include "ir_host.h"
+#include "ir_ptx.cuh"
+
+namespace ir {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+
+struct GemmKParams {
+  CUtensorMap tma_a[4];
+  CUtensorMap tma_b;
+  int M, N, n_out;
+  int kc_per_tap, taps;
+  int tiles_w, tiles_h;
+  int bw, bh, bn;
+  int8_t tap_map[9], tap_dx[9], tap_dy[9];
+  const float* bias;
+  const __half* residual;
+  int res_stride;
+  __half* out;
+  int out_stride;
+  int act;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ GemmKParams p) {
+  constexpr int B_BYTES = BN * kBK * 2;
+  constexpr int STAGE_BYTES = kABytes + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t IDESC = umma_idesc_f16(kBM, BN, 0, 0);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a[0]);
+    tma_prefetch_desc(&p.tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int mt = blockIdx.x;
+  const int nt = blockIdx.y;
+  const int num_k = p.taps * p.kc_per_tap;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int w0 = (mt % p.tiles_w) * p.bw;
+      const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+      const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+      int tap = 0, kc = 0;
+      for (int ks = 0; ks < num_k; ++ks) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (ks / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_4d(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], &full_bar[s], kc * kBK, w0 + p.tap_dx[tap],
+                    h0 + p.tap_dy[tap], n0);
+        tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], ks * kBK, nt * BN);
+        if (++kc == p.kc_per_tap) {
+          kc = 0;
+          ++tap;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int ks = 0; ks < num_k; ++ks) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (ks / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + s * kABytes);
+        const uint32_t b_base = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t adesc = umma_smem_desc(a_base + k * 32, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc(b_base + k * 32, 16, 1024);
+          umma_f16_ss(tmem_base, adesc, bdesc, IDESC, (ks | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ epilogue (all 128 threads, thread == row)
+  mbar_wait(accum_bar, 0);
+  tc_fence_after();
+
+  const int row = warp * 32 + lane;
+  const long grow = static_cast<long>(mt) * kBM + row;
+  const bool row_ok = grow < p.M;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+
+  if (p.act == IR_ACT_GEGLU) {
+    // tile columns come in blocks of 128: [64 value | 64 gate]
+    if constexpr (BN % 128 == 0) {
+#pragma unroll 1
+      for (int blk = 0; blk < BN / 128; ++blk) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t rv[32], rg[32];
+          tmem_ld32(taddr + blk * 128 + half * 32, rv);
+          tmem_ld32(taddr + blk * 128 + 64 + half * 32, rg);
+          tmem_ld_wait();
+          const int wcol = nt * BN + blk * 128 + half * 32;           // weight-row index of the value columns
+          const int ocol = (nt * BN + blk * 128) / 2 + half * 32;     // output column
+          if (row_ok) {
+            uint32_t packed[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float v0 = __uint_as_float(rv[i]), v1 = __uint_as_float(rv[i + 1]);
+              float g0 = __uint_as_float(rg[i]), g1 = __uint_as_float(rg[i + 1]);
+              if (p.bias) {
+                v0 += __ldg(p.bias + wcol + i);
+                v1 += __ldg(p.bias + wcol + i + 1);
+                g0 += __ldg(p.bias + wcol + 64 + i);
+                g1 += __ldg(p.bias + wcol + 64 + i + 1);
+              }
+              v0 = round_h(v0); v1 = round_h(v1); g0 = round_h(g0); g1 = round_h(g1);
+              packed[i / 2] = pack_half2(v0 * round_h(gelu_erf(g0)), v1 * round_h(gelu_erf(g1)));
+            }
+            uint4* dst = reinterpret_cast<uint4*>(p.out + grow * p.out_stride + ocol);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+      const int gcol = nt * BN + c0;
+      if (row_ok && gcol < p.N) {
+        const bool full = (gcol + 32 <= p.N);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (full || gcol + i < p.N) v[i] += __ldg(p.bias + gcol + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = round_h(v[i]);
+        if (p.residual) {
+          const __half* rp = p.residual + grow * p.res_stride + gcol;
+          if (full) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h2[j]);
+                v[q * 8 + 2 * j] += f.x;
+                v[q * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (gcol + i < p.N) v[i] += __half2float(rp[i]);
+          }
+        }
+        if (p.act == IR_ACT_SILU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = silu(v[i]);
+        }
+        __half* op = p.out + grow * p.out_stride + gcol;
+        if (full) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u = make_uint4(pack_half2(v[q * 8], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
+                                 pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+            reinterpret_cast<uint4*>(op)[q] = u;
+          }
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (gcol + i < p.N) op[i] = __float2half_rn(v[i]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES>
+static int launch(const GemmKParams& kp, int m_tiles, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 1024 + 256;
+  static bool attr_done = false;  // benign race: idempotent
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm<%d>): %s", BN, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  dim3 grid(m_tiles, (kp.N + BN - 1) / BN);
+  conv_gemm_kernel<BN, STAGES><<<grid, 128, smem, stream>>>(kp);
+  IR_CUDA_LAUNCH_CHECK("conv_gemm launch");
+  return 0;
+}
+
+static int pow2_floor(int x) {
+  int p = 1;
+  while (p * 2 <= x) p *= 2;
+  return p;
+}
+
+}  // namespace ir
+
+extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
+  using namespace ir;
+  if (!p || !p->a || !p->w || !p->out) return set_error(IR_ERR_ARG, "ir_conv_gemm: NULL argument");
+  if (int rc = check_arch()) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (p->c_in <= 0 || p->c_in % 64 != 0) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: c_in=%d must be a positive multiple of 64", p->c_in);
+  if (!((p->ksize == 1 && p->stride == 1) || (p->ksize == 3 && (p->stride == 1 || p->stride == 2))))
+    return set_error(IR_ERR_SHAPE, "ir_conv_gemm: unsupported ksize=%d stride=%d", p->ksize, p->stride);
+  if (p->a_row_stride < p->c_in || p->a_row_stride % 8 != 0) return set_error(IR_ERR_ALIGN, "ir_conv_gemm: a_row_stride=%d", p->a_row_stride);
+  if (p->batch <= 0 || p->h_in <= 0 || p->w_in <= 0 || p->c_out <= 0) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: non-positive dims");
+  const bool geglu = p->act == IR_ACT_GEGLU;
+  const int n_out = geglu ? p->c_out / 2 : p->c_out;
+  if (p->out_row_stride < n_out) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: out_row_stride=%d < %d", p->out_row_stride, n_out);
+  if (p->c_out % 8 == 0 && (p->out_row_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(p->out) & 15)))
+    return set_error(IR_ERR_ALIGN, "ir_conv_gemm: out pointer/stride not 16-byte aligned");
+  if (p->residual && p->c_out % 8 == 0 && (p->res_row_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(p->residual) & 15)))
+    return set_error(IR_ERR_ALIGN, "ir_conv_gemm: residual pointer/stride not 16-byte aligned");
+  if (geglu && (p->c_out % 128 != 0 || p->residual)) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: GEGLU needs c_out %% 128 == 0 and no residual");
+
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const int taps = p->ksize * p->ksize;
+  const int h_out = p->h_in / p->stride, w_out = p->w_in / p->stride;
+  if (p->stride == 2 && ((p->h_in | p->w_in) & 1)) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: stride 2 needs even h, w");
+  const long M = static_cast<long>(p->batch) * h_out * w_out;
+  if (M > 0x7fffffffL) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: M too large");
+  kp.M = static_cast<int>(M);
+  kp.N = p->c_out;
+  kp.n_out = n_out;
+  kp.kc_per_tap = p->c_in / 64;
+  kp.taps = taps;
+  kp.bias = p->bias;
+  kp.residual = static_cast<const __half*>(p->residual);
+  kp.res_stride = p->res_row_stride;
+  kp.out = static_cast<__half*>(p->out);
+  kp.out_stride = p->out_row_stride;
+  kp.act = p->act;
+
+  const uint64_t rs = static_cast<uint64_t>(p->a_row_stride) * 2;  // pixel stride in bytes
+  int m_tiles;
+  if (p->ksize == 1) {
+    // flattened token-major GEMM: dims (c_in, M, 1, 1)
+    kp.bw = 128; kp.bh = 1; kp.bn = 1;
+    kp.tiles_w = (kp.M + 127) / 128; kp.tiles_h = 1;
+    m_tiles = kp.tiles_w;
+    uint64_t dims[4] = {static_cast<uint64_t>(p->c_in), static_cast<uint64_t>(kp.M), 1, 1};
+    uint64_t str[3] = {rs, rs * kp.M, rs * kp.M};
+    uint32_t box[4] = {64, 128, 1, 1};
+    if (int rc = make_tmap_f16(&kp.tma_a[0], p->a, 4, dims, str, box)) return rc;
+  } else {
+    if ((w_out & (w_out - 1)) || (h_out & (h_out - 1)))
+      return set_error(IR_ERR_SHAPE, "ir_conv_gemm: 3x3 conv needs power-of-two output h,w (got %dx%d)", h_out, w_out);
+    kp.bw = w_out < 128 ? w_out : 128;
+    kp.bh = (128 / kp.bw) < h_out ? (128 / kp.bw) : h_out;
+    kp.bn = 128 / (kp.bw * kp.bh);
+    kp.tiles_w = w_out / kp.bw;
+    kp.tiles_h = h_out / kp.bh;
+    m_tiles = kp.tiles_w * kp.tiles_h * ((p->batch + kp.bn - 1) / kp.bn);
+    uint32_t box[4] = {64, static_cast<uint32_t>(kp.bw), static_cast<uint32_t>(kp.bh), static_cast<uint32_t>(kp.bn)};
+    if (p->stride == 1) {
+      uint64_t dims[4] = {static_cast<uint64_t>(p->c_in), static_cast<uint64_t>(p->w_in), static_cast<uint64_t>(p->h_in),
+                          static_cast<uint64_t>(p->batch)};
+      uint64_t str[3] = {rs, rs * p->w_in, rs * p->w_in * p->h_in};
+      if (int rc = make_tmap_f16(&kp.tma_a[0], p->a, 4, dims, str, box)) return rc;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          kp.tap_map[ky * 3 + kx] = 0;
+          kp.tap_dx[ky * 3 + kx] = static_cast<int8_t>(kx - 1);
+          kp.tap_dy[ky * 3 + kx] = static_cast<int8_t>(ky - 1);
+        }
+    } else {
+      // input row 2i + ky - 1: ky=0 -> odd phase, offset -1; ky=1 -> even phase; ky=2 -> odd phase, offset 0
+      uint64_t dims[4] = {static_cast<uint64_t>(p->c_in), static_cast<uint64_t>(w_out), static_cast<uint64_t>(h_out),
+                          static_cast<uint64_t>(p->batch)};
+      uint64_t str[3] = {rs * 2, rs * p->w_in * 2, rs * p->w_in * p->h_in};
+      for (int pr = 0; pr < 2; ++pr)
+        for (int pc = 0; pc < 2; ++pc) {
+          const char* base = static_cast<const char*>(p->a) + (static_cast<uint64_t>(pr) * p->w_in + pc) * rs;
+          if (int rc = make_tmap_f16(&kp.tma_a[pr * 2 + pc], base, 4, dims, str, box)) return rc;
+        }
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const int pr = (ky == 1) ? 0 : 1, pc = (kx == 1) ? 0 : 1;
+          kp.tap_map[ky * 3 + kx] = static_cast<int8_t>(pr * 2 + pc);
+          kp.tap_dx[ky * 3 + kx] = static_cast<int8_t>(kx == 0 ? -1 : 0);
+          kp.tap_dy[ky * 3 + kx] = static_cast<int8_t>(ky == 0 ? -1 : 0);
+        }
+    }
+  }
+
+  // tile-N selection: exact divisors first, fewest wasted columns
+  int bn_tile = p->tile_n;
+  if (bn_tile == 0) {
+    if (geglu) bn_tile = (p->c_out % 256 == 0 && static_cast<long>(m_tiles) * (p->c_out / 256) >= 296) ? 256 : 128;
+    else if (p->c_out <= 64) bn_tile = 64;
+    else if (p->c_out % 128 == 0) bn_tile = 128;
+    else if (p->c_out % 160 == 0) bn_tile = 160;
+    else if (p->c_out % 64 == 0) bn_tile = 64;
+    else bn_tile = 128;
+  }
+  if (geglu && bn_tile % 128 != 0) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: GEGLU needs tile_n 128 or 256");
+  (void)pow2_floor;
+
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(taps) * p->c_in, static_cast<uint64_t>(p->c_out)};
+    uint64_t str[1] = {static_cast<uint64_t>(taps) * p->c_in * 2};
+    uint32_t box[2] = {64, static_cast<uint32_t>(bn_tile)};
+    if (int rc = make_tmap_f16(&kp.tma_b, p->w, 2, dims, str, box)) return rc;
+  }
+
+  switch (bn_tile) {
+    case 64: return launch<64, 4>(kp, m_tiles, stream);
+    case 128: return launch<128, 3>(kp, m_tiles, stream);
+    case 160: return launch<160, 3>(kp, m_tiles, stream);
+    case 256: return launch<256, 4>(kp, m_tiles, stream);
+    default: return set_error(IR_ERR_SHAPE, "ir_conv_gemm: tile_n=%d unsupported", bn_tile);
+  }
+}

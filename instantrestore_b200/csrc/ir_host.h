@@ -1,0 +1,28 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/instantrestore_b200.h"
+
+namespace ir {
+
+// Records a message retrievable through ir_last_error_string() and returns `code`.
+int set_error(int code, const char* fmt, ...);
+
+// Checks the device behind the current context is sm_100 (B200). Cached.
+int check_arch();
+
+// Encodes a tiled fp16 tensor map (rank 2..5) with 128-byte swizzle and zero OOB fill.
+// dims/box are innermost-first; strides_bytes[i] is the byte stride of dimension i+1.
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+#define IR_CUDA_LAUNCH_CHECK(what)                                                      \
+  do {                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) return ir::set_error(IR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e__)); \
+  } while (0)
+
+}  // namespace ir
