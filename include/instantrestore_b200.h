@@ -204,13 +204,13 @@ int ir_upsample_nearest2x(const void* x, void* out, int batch, int h, int w, int
  *   out[b, hw, c] = fp16( a * x[b, c, hw] + s * noise[b, c, hw] ), channels zero-padded to c_pad.
  * x, noise: fp32 NCHW [batch, c, hw] (noise may be NULL). out: fp16 [batch, hw, c_pad].
  * ir_latent_out — DDPM pred_original_sample + layout change (pix2pix_turbo.py:277,331):
- *   out[b, c, hw] = (xt[b, c, hw] - s * eps[b, hw, c]) * inv_a     (fp32 NCHW)
- * eps: fp16 [batch, hw, c] channel-last (row stride eps_row_stride); xt: fp32 NCHW.
+ *   xt = a * x + s * noise;  out[b, c, hw] = (xt[b, c, hw] - s * eps[b, hw, c]) / a     (fp32 NCHW)
+ * eps: fp16 [batch, hw, c] channel-last (row stride eps_row_stride); x, noise: fp32 NCHW (noise may be NULL).
  */
 int ir_latent_in(const float* x, const float* noise, float a, float s, void* out, int batch, int c, int hw,
                  int c_pad, ir_stream_t stream);
-int ir_latent_out(const void* eps, int eps_row_stride, const float* xt, float s, float inv_a, float* out, int batch,
-                  int c, int hw, ir_stream_t stream);
+int ir_latent_out(const void* eps, int eps_row_stride, const float* x, const float* noise, float a, float s, float* out,
+                  int batch, int c, int hw, ir_stream_t stream);
 
 #ifdef __cplusplus
 }

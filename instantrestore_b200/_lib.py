@@ -104,8 +104,8 @@ def load() -> C.CDLL:
     lib.ir_upsample_nearest2x.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.ir_latent_in.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p]
-    lib.ir_latent_out.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int,
-                                  C.c_int, C.c_void_p]
+    lib.ir_latent_out.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int,
+                                  C.c_int, C.c_int, C.c_void_p]
     lib.ir_debug_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_uint] * 6 + [C.c_void_p]
     _lib = lib
     return lib
@@ -273,12 +273,13 @@ def latent_in(x: torch.Tensor, noise: torch.Tensor | None, a: float, s: float, *
     return out
 
 
-def latent_out(eps: torch.Tensor, xt: torch.Tensor, s: float, inv_a: float, *, out: torch.Tensor | None = None) -> torch.Tensor:
-    """eps: fp16 channel-last [B*HW, >=C]; xt: fp32 NCHW -> fp32 NCHW (xt - s*eps) * inv_a."""
-    _h(eps, "eps"); _f(xt, "xt")
-    b, c, hh, ww = xt.shape
+def latent_out(eps: torch.Tensor, x: torch.Tensor, noise: torch.Tensor | None, a: float, s: float, *,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+    """eps: fp16 channel-last [B*HW, >=C]; x, noise: fp32 NCHW -> fp32 NCHW ((a*x + s*noise) - s*eps) / a."""
+    _h(eps, "eps"); _f(x, "x"); _f(noise, "noise")
+    b, c, hh, ww = x.shape
     if out is None:
-        out = torch.empty_like(xt)
-    check(load().ir_latent_out(ptr(eps), eps.stride(-2), ptr(xt), s, inv_a, ptr(out), b, c, hh * ww, stream_ptr()),
-          "ir_latent_out")
+        out = torch.empty_like(x)
+    check(load().ir_latent_out(ptr(eps), eps.stride(-2), ptr(x), ptr(noise), a, s, ptr(out), b, c, hh * ww,
+                               stream_ptr()), "ir_latent_out")
     return out

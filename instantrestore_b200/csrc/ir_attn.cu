@@ -320,6 +320,9 @@ extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t st
   if (p->batch <= 0 || p->heads <= 0 || p->s_q <= 0) return set_error(IR_ERR_SHAPE, "ir_shared_attn_fwd: non-positive dims");
   if ((p->adain_scale == nullptr) != (p->adain_shift == nullptr)) return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: adain scale/shift mismatch");
   if (p->chunk_mass) return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: chunk_mass output not implemented yet");
+  if (p->q_row_stride < p->q_col_off + p->heads * kD || (has_own && p->own_row_stride < p->heads * kD) ||
+      (p->n_ref && p->ref_row_stride < p->ref_col_off + p->heads * kD))
+    return set_error(IR_ERR_SHAPE, "ir_shared_attn_fwd: row stride smaller than heads*64 columns");
   if (p->q_row_stride % 8 || p->out_row_stride % 8 || (has_own && p->own_row_stride % 8) || (p->n_ref && p->ref_row_stride % 8))
     return set_error(IR_ERR_ALIGN, "ir_shared_attn_fwd: row strides must be multiples of 8 elements");
   if ((p->q_col_off | p->k_own_col_off | p->v_own_col_off | p->ref_col_off) % 8)
@@ -330,21 +333,22 @@ extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t st
   memset(&kp, 0, sizeof(kp));
   uint32_t box3[3] = {64, 128, 1};
   {
-    uint64_t dims[3] = {static_cast<uint64_t>(p->q_row_stride), static_cast<uint64_t>(p->s_q), static_cast<uint64_t>(p->batch)};
+    uint64_t dims[3] = {static_cast<uint64_t>(p->q_col_off + p->heads * kD), static_cast<uint64_t>(p->s_q), static_cast<uint64_t>(p->batch)};
     uint64_t str[2] = {static_cast<uint64_t>(p->q_row_stride) * 2, static_cast<uint64_t>(p->q_row_stride) * 2 * p->s_q};
     if (int rc = make_tmap_f16(&kp.tma_q, p->q, 3, dims, str, box3)) return rc;
   }
   if (has_own) {
     const int nb = p->own_shared ? 1 : p->batch;
-    uint64_t dims[3] = {static_cast<uint64_t>(p->own_row_stride), static_cast<uint64_t>(p->s_own), static_cast<uint64_t>(nb)};
+    uint64_t dims[3] = {static_cast<uint64_t>(p->k_own_col_off + p->heads * kD), static_cast<uint64_t>(p->s_own), static_cast<uint64_t>(nb)};
     uint64_t str[2] = {static_cast<uint64_t>(p->own_row_stride) * 2, static_cast<uint64_t>(p->own_row_stride) * 2 * p->s_own};
     if (int rc = make_tmap_f16(&kp.tma_k_own, p->k_own, 3, dims, str, box3)) return rc;
+    dims[0] = static_cast<uint64_t>(p->v_own_col_off + p->heads * kD);
     if (int rc = make_tmap_f16(&kp.tma_v_own, p->v_own, 3, dims, str, box3)) return rc;
   }
   if (p->n_ref > 0) {
     uint32_t box4[4] = {64, 128, 1, 1};
     const uint64_t rs = static_cast<uint64_t>(p->ref_row_stride) * 2;
-    uint64_t dims[4] = {static_cast<uint64_t>(p->ref_row_stride), static_cast<uint64_t>(p->s_ref), static_cast<uint64_t>(p->n_ref),
+    uint64_t dims[4] = {static_cast<uint64_t>(p->ref_col_off + p->heads * kD), static_cast<uint64_t>(p->s_ref), static_cast<uint64_t>(p->n_ref),
                         static_cast<uint64_t>(p->batch)};
     uint64_t str[3] = {rs, rs * p->s_ref, rs * p->s_ref * p->n_ref};
     if (int rc = make_tmap_f16(&kp.tma_k_ref, p->k_ref, 4, dims, str, box4)) return rc;

@@ -210,8 +210,9 @@ __global__ void latent_in_kernel(const float* __restrict__ x, const float* __res
   out[i] = __float2half_rn(v);
 }
 
-__global__ void latent_out_kernel(const __half* __restrict__ eps, int eps_stride, const float* __restrict__ xt, float s,
-                                  float inv_a, float* __restrict__ out, int c, int hw, long total) {
+__global__ void latent_out_kernel(const __half* __restrict__ eps, int eps_stride, const float* __restrict__ x,
+                                  const float* __restrict__ noise, float a, float s, float* __restrict__ out, int c,
+                                  int hw, long total) {
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;  // NCHW index
   if (i >= total) return;
   const int p = static_cast<int>(i % hw);
@@ -219,7 +220,8 @@ __global__ void latent_out_kernel(const __half* __restrict__ eps, int eps_stride
   const int ch = static_cast<int>(bc % c);
   const long b = bc / c;
   const float e = __half2float(eps[(b * hw + p) * eps_stride + ch]);
-  out[i] = (xt[i] - s * e) * inv_a;
+  const float xt = a * x[i] + (noise ? s * noise[i] : 0.f);
+  out[i] = (xt - s * e) / a;
 }
 
 static inline int grid_for(long total, int block, int cap = 148 * 16) {
@@ -305,14 +307,14 @@ extern "C" int ir_latent_in(const float* x, const float* noise, float a, float s
   return 0;
 }
 
-extern "C" int ir_latent_out(const void* eps, int eps_row_stride, const float* xt, float s, float inv_a, float* out,
-                             int batch, int c, int hw, ir_stream_t stream_) {
+extern "C" int ir_latent_out(const void* eps, int eps_row_stride, const float* x, const float* noise, float a, float s,
+                             float* out, int batch, int c, int hw, ir_stream_t stream_) {
   using namespace ir;
-  if (!eps || !xt || !out) return set_error(IR_ERR_ARG, "ir_latent_out: NULL argument");
+  if (!eps || !x || !out || a == 0.f) return set_error(IR_ERR_ARG, "ir_latent_out: NULL argument");
   if (int rc = check_arch()) return rc;
   const long total = static_cast<long>(batch) * c * hw;
   latent_out_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __half*>(eps), eps_row_stride, xt, s, inv_a, out, c, hw, total);
+      static_cast<const __half*>(eps), eps_row_stride, x, noise, a, s, out, c, hw, total);
   IR_CUDA_LAUNCH_CHECK("latent_out launch");
   return 0;
 }

@@ -1,0 +1,123 @@
+"""RestoreEngine — the single-step restoration forward of the reference (face_replace/models/pix2pix_turbo.py:
+get_conditioning_keys_values :242-279 and forward :281-343) at the latent boundary, on the B200 kernels.
+
+    reference latents --add_noise(t=1)--> reference UNet  --(9 x K,V, used in place)--+
+    degraded latent   --add_noise(t=249)-> main UNet (shared attention + AdaIN) <-----+--> pred_original_sample
+
+The reference-UNet's fused QKV projection outputs ARE the (B, N, S, C) key/value tensors of the reference
+(batch index b*N + r), so nothing is gathered, reshaped or concatenated between the two passes; padded reference slots
+(valid_indices < N) are zero-filled in place exactly as pix2pix_turbo.py:269-273 does. The whole step (two UNet
+passes, ~1000 kernel launches) is captured once per (batch, n_ref) into a CUDA graph and replayed.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .unet_engine import RefKV, UNetEngine, UNetSpec
+from .weights import StateDictView
+
+
+@dataclass
+class ModelFlags:
+    """ModelConfig fields read at inference (reference face_replace/configs/train_config.py:118-147)."""
+    use_shared_attention: bool = True
+    use_adain: bool = False
+    train_input: bool = True
+    condition_on_face_embeds: bool = False
+    lora_rank_unet: int = 32
+
+
+def ddpm_coeffs(t: int, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012):
+    """sqrt(alpha_bar_t), sqrt(1 - alpha_bar_t) of the sd-turbo scaled-linear schedule (reference models/model.py:4-12)."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+    ac = torch.cumprod(1.0 - betas, dim=0)[int(t)]
+    return float(ac ** 0.5), float((1.0 - ac) ** 0.5)
+
+
+class RestoreEngine:
+    def __init__(self, unet_sd: Dict[str, torch.Tensor], original_unet_sd: Dict[str, torch.Tensor],
+                 caption_enc: torch.Tensor, flags: ModelFlags, spec: Optional[UNetSpec] = None, device="cuda:0",
+                 noise_timestep: int = 249, ref_timestep: int = 1, use_cuda_graph: bool = True):
+        L.load()
+        rc = L.load().ir_check_device() if torch.cuda.is_available() else -3
+        if rc != 0:
+            raise RuntimeError("instantrestore_b200 needs a B200 (sm_100) GPU: " + L.load().ir_last_error_string().decode())
+        self.spec = spec or UNetSpec()
+        self.flags = flags
+        self.dev = torch.device(device)
+        if flags.condition_on_face_embeds:
+            raise NotImplementedError("condition_on_face_embeds=True (FaceIDAttnProcessor) is not on the released path")
+        self.main = UNetEngine(StateDictView(unet_sd), self.spec, noise_timestep, caption_enc, self.dev,
+                               use_adain=flags.use_adain, train_input=flags.train_input,
+                               consume_refs=flags.use_shared_attention)
+        self.ref = (UNetEngine(StateDictView(original_unet_sd), self.spec, ref_timestep, caption_enc, self.dev, capture_kv=True)
+                    if flags.use_shared_attention else None)
+        self.a_main, self.s_main = ddpm_coeffs(noise_timestep)
+        self.a_ref, self.s_ref = ddpm_coeffs(ref_timestep)
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs: Dict[Tuple, dict] = {}
+
+    # ------------------------------------------------------------------------------------------ eager step
+    def _step(self, enc, refs, noise_main, noise_ref, valid: Optional[Sequence[int]]):
+        B, _, H, W = enc.shape
+        ref_kv = None
+        if self.ref is not None and refs is not None:
+            N = refs.shape[1]
+            rin = L.latent_in(refs.reshape(B * N, *refs.shape[2:]), noise_ref, self.a_ref, self.s_ref)
+            self.ref.forward(rin, B * N, H, W)
+            ref_kv = []
+            for cap in self.ref.captured:
+                if valid is not None:
+                    rows = cap.buf.view(B, N, cap.s_ref, -1)
+                    for b, nv in enumerate(valid):
+                        if nv < N:
+                            rows[b, nv:, :, cap.k_off:].zero_()     # K and V columns of the padded slots
+                ref_kv.append(RefKV(buf=cap.buf, k_off=cap.k_off, v_off=cap.v_off, n_ref=N, s_ref=cap.s_ref))
+        x = L.latent_in(enc, noise_main, self.a_main, self.s_main)
+        eps = self.main.forward(x, B, H, W, ref_kv=ref_kv)
+        return L.latent_out(eps, enc, noise_main, self.a_main, self.s_main)
+
+    # ------------------------------------------------------------------------------------------ public
+    @torch.no_grad()
+    def forward_latents(self, enc_control: torch.Tensor, ref_latents: Optional[torch.Tensor], noise_main: torch.Tensor,
+                        noise_ref: Optional[torch.Tensor], valid_indices: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """enc_control (B,4,h,w), ref_latents (B,N,4,h,w), noise_main (B,4,h,w), noise_ref (B*N,4,h,w): fp32 CUDA
+        tensors. Returns the predicted clean latent x0 (B,4,h,w) fp32 (before the /scaling_factor of the VAE decode)."""
+        valid = None
+        if valid_indices is not None and ref_latents is not None:
+            valid = [int(v) for v in valid_indices]
+            if all(v >= ref_latents.shape[1] for v in valid):
+                valid = None
+        if not self.use_cuda_graph:
+            return self._step(enc_control, ref_latents, noise_main, noise_ref, valid)
+        key = (tuple(enc_control.shape), None if ref_latents is None else tuple(ref_latents.shape), tuple(valid) if valid else None)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(enc_control, ref_latents, noise_main, noise_ref, valid)
+            self._graphs[key] = g
+        g["enc"].copy_(enc_control, non_blocking=True)
+        g["noise_main"].copy_(noise_main, non_blocking=True)
+        if ref_latents is not None:
+            g["refs"].copy_(ref_latents, non_blocking=True)
+            g["noise_ref"].copy_(noise_ref, non_blocking=True)
+        g["graph"].replay()
+        return g["out"]
+
+    def _capture(self, enc, refs, noise_main, noise_ref, valid):
+        st = dict(enc=enc.clone(), noise_main=noise_main.clone(), refs=None if refs is None else refs.clone(),
+                  noise_ref=None if noise_ref is None else noise_ref.clone())
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self._step(st["enc"], st["refs"], st["noise_main"], st["noise_ref"], valid)   # warm-up: allocator, func attrs
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["out"] = self._step(st["enc"], st["refs"], st["noise_main"], st["noise_ref"], valid)
+        st["graph"] = graph
+        return st

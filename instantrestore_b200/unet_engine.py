@@ -1,0 +1,267 @@
+"""B200 execution of the reference UNet forward (reference unet_2d_condition/unet.py:804-1179 and the live blocks of
+block.py) on the C-ABI kernels. Activations stay channel-last fp16 end to end ([B*H*W, C] is both "NHWC" for the
+convolutions and the token matrix of the transformer blocks, so the reference's permute/reshape pairs vanish).
+
+Folded once per checkpoint (results unchanged): LoRA merged into base weights; the timestep is a
+constant of the pipeline (249 main / 1 reference, reference test.py:62, pix2pix_turbo.py:247) so
+time_embedding(...) and every time_emb_proj(silu(emb)) vector become part of conv1's bias; the caption embedding is
+a constant (pix2pix_turbo.py:100-106) so the cross-attention K/V projections are precomputed.
+
+No CPU fallback: everything here calls instantrestore_b200._lib, which raises if the CUDA library is missing.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .weights import StateDictView, conv_weight_khwc, geglu_interleave_index
+
+
+@dataclass
+class UNetSpec:
+    """Geometry of the SD-Turbo UNet (reference unet.py:182-199 defaults + sd-turbo config);
+    attention_head_dim holds head COUNTS (unet.py:239-245), head_dim is 64 everywhere."""
+    in_channels: int = 4
+    out_channels: int = 4
+    block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280)
+    layers_per_block: int = 2
+    attention_head_dim: Tuple[int, ...] = (5, 10, 20, 20)
+    cross_attention_dim: int = 1024
+    norm_num_groups: int = 32
+    norm_eps: float = 1e-5
+    down_has_attn: Tuple[bool, ...] = (True, True, True, False)
+    up_has_attn: Tuple[bool, ...] = (False, True, True, True)
+
+
+@dataclass
+class RefKV:
+    """Keys/values of the reference images for one shared-attention layer: a [B*N*S, row] fp16 buffer holding K at
+    column k_off and V at column v_off (the reference-UNet's fused QKV projection output is used in place)."""
+    buf: torch.Tensor
+    k_off: int
+    v_off: int
+    n_ref: int
+    s_ref: int
+
+
+class _Lin:
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], dev):
+        self.w = w.to(torch.float16).contiguous().to(dev)
+        self.b = None if b is None else b.to(torch.float32).contiguous().to(dev)
+        self.c_out, self.c_in = self.w.shape
+
+
+class _Conv:
+    def __init__(self, w4: torch.Tensor, b: Optional[torch.Tensor], dev, stride: int = 1, c_in_pad: int = 0):
+        self.ksize = w4.shape[-1]
+        self.stride = stride
+        self.c_in = max(w4.shape[1], c_in_pad)
+        self.c_out = w4.shape[0]
+        self.w = conv_weight_khwc(w4, c_in_pad).to(dev)
+        self.b = None if b is None else b.to(torch.float32).contiguous().to(dev)
+
+
+class _Norm:
+    def __init__(self, v: StateDictView, name: str, dev):
+        self.g = v.param(f"{name}.weight").contiguous().to(dev)
+        self.b = v.param(f"{name}.bias").contiguous().to(dev)
+
+
+def timestep_embedding(t: int, dim: int) -> torch.Tensor:
+    """diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): [cos | sin] of t * exp(-ln(1e4) i / (dim/2))."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    arg = float(t) * freqs
+    return torch.cat([torch.cos(arg), torch.sin(arg)])[None]
+
+
+class UNetEngine:
+    def __init__(self, sd: StateDictView, spec: UNetSpec, timestep: int, caption_enc: torch.Tensor, device,
+                 *, use_adain: bool = False, train_input: bool = True, consume_refs: bool = False,
+                 capture_kv: bool = False, freeu: Optional[Tuple[float, float, float, float]] = (0.9, 0.2, 1.4, 1.6)):
+        L.load()
+        self.spec, self.dev = spec, torch.device(device)
+        self.use_adain, self.train_input = use_adain, train_input
+        self.consume_refs, self.capture_kv = consume_refs, capture_kv
+        self.freeu = freeu
+        self.captured: List[RefKV] = []
+        dev = self.dev
+        boc = spec.block_out_channels
+        cap = caption_enc.detach().to(torch.float32).cpu()
+        if cap.ndim == 3:
+            cap = cap[0]
+        self.n_ctx = cap.shape[0]
+
+        # constant time embedding -> per-resnet bias vectors
+        te = sd.sub("time_embedding")
+        emb = timestep_embedding(timestep, boc[0])
+        emb = torch.nn.functional.silu(emb @ te.weight("linear_1").T + te.bias("linear_1"))
+        emb = emb @ te.weight("linear_2").T + te.bias("linear_2")
+        self._silu_emb = torch.nn.functional.silu(emb)[0]
+
+        self.conv_in = _Conv(sd.weight("conv_in"), sd.bias("conv_in"), dev, c_in_pad=64)
+        self.down = []
+        for i, ch in enumerate(boc):
+            blk = sd.sub(f"down_blocks.{i}")
+            layers = []
+            for j in range(spec.layers_per_block):
+                res = self._load_resnet(blk.sub(f"resnets.{j}"))
+                tr = self._load_transformer(blk.sub(f"attentions.{j}"), ch, spec.attention_head_dim[i], cap) if spec.down_has_attn[i] else None
+                layers.append((res, tr))
+            ds = None
+            if i != len(boc) - 1:
+                d = blk.sub("downsamplers.0")
+                ds = _Conv(d.weight("conv"), d.bias("conv"), dev, stride=2)
+            self.down.append((layers, ds))
+        mid = sd.sub("mid_block")
+        self.mid = (self._load_resnet(mid.sub("resnets.0")),
+                    self._load_transformer(mid.sub("attentions.0"), boc[-1], spec.attention_head_dim[-1], cap),
+                    self._load_resnet(mid.sub("resnets.1")))
+        self.up = []
+        rboc = list(reversed(boc))
+        rheads = list(reversed(spec.attention_head_dim))
+        for i, ch in enumerate(rboc):
+            blk = sd.sub(f"up_blocks.{i}")
+            layers = []
+            for j in range(spec.layers_per_block + 1):
+                res = self._load_resnet(blk.sub(f"resnets.{j}"))
+                tr = self._load_transformer(blk.sub(f"attentions.{j}"), ch, rheads[i], cap) if spec.up_has_attn[i] else None
+                layers.append((res, tr))
+            us = None
+            if i != len(boc) - 1:
+                u = blk.sub("upsamplers.0")
+                us = _Conv(u.weight("conv"), u.bias("conv"), dev)
+            self.up.append((layers, us))
+        self.norm_out = _Norm(sd, "conv_norm_out", dev)
+        self.conv_out = _Conv(sd.weight("conv_out"), sd.bias("conv_out"), dev)
+
+    # ------------------------------------------------------------------------------------------ loading
+    def _load_resnet(self, v: StateDictView):
+        dev = self.dev
+        tvec = self._silu_emb @ v.weight("time_emb_proj").T + v.bias("time_emb_proj")
+        conv1 = _Conv(v.weight("conv1"), v.bias("conv1") + tvec, dev)
+        conv2 = _Conv(v.weight("conv2"), v.bias("conv2"), dev)
+        sc = None
+        if v.has("conv_shortcut.weight"):
+            w = v.weight("conv_shortcut")
+            sc = _Lin(w[:, :, 0, 0], v.bias("conv_shortcut"), dev)
+        return dict(norm1=_Norm(v, "norm1", dev), conv1=conv1, norm2=_Norm(v, "norm2", dev), conv2=conv2, shortcut=sc)
+
+    def _load_transformer(self, v: StateDictView, ch: int, heads: int, cap: torch.Tensor):
+        dev = self.dev
+        b = v.sub("transformer_blocks.0")
+        a1, a2, ff = b.sub("attn1"), b.sub("attn2"), b.sub("ff")
+        wqkv = torch.cat([a1.weight("to_q"), a1.weight("to_k"), a1.weight("to_v")], 0)
+        k2 = (cap @ a2.weight("to_k").T).to(torch.float16).contiguous().to(dev)      # [n_ctx, C], constant
+        v2 = (cap @ a2.weight("to_v").T).to(torch.float16).contiguous().to(dev)
+        idx = geglu_interleave_index(ff.weight("net.0.proj").shape[0])
+        return dict(
+            heads=heads, ch=ch,
+            norm=_Norm(v, "norm", dev), proj_in=_Lin(v.weight("proj_in"), v.bias("proj_in"), dev),
+            ln1=_Norm(b, "norm1", dev), qkv=_Lin(wqkv, None, dev), out1=_Lin(a1.weight("to_out.0"), a1.bias("to_out.0"), dev),
+            ln2=_Norm(b, "norm2", dev), q2=_Lin(a2.weight("to_q"), None, dev), k2=k2, v2=v2,
+            out2=_Lin(a2.weight("to_out.0"), a2.bias("to_out.0"), dev),
+            ln3=_Norm(b, "norm3", dev),
+            ff1=_Lin(ff.weight("net.0.proj")[idx], ff.bias("net.0.proj")[idx], dev),
+            ff2=_Lin(ff.weight("net.2"), ff.bias("net.2"), dev),
+            proj_out=_Lin(v.weight("proj_out"), v.bias("proj_out"), dev),
+        )
+
+    # ------------------------------------------------------------------------------------------ ops
+    def _lin(self, x, lin: _Lin, residual=None, act=L.IR_ACT_NONE):
+        return L.conv_gemm(x, lin.w, batch=1, h_in=1, w_in=x.shape[0], c_in=lin.c_in, bias=lin.b, residual=residual, act=act)
+
+    def _conv(self, x, cv: _Conv, B, H, W, residual=None):
+        return L.conv_gemm(x, cv.w, batch=B, h_in=H, w_in=W, c_in=cv.c_in, ksize=cv.ksize, stride=cv.stride, bias=cv.b,
+                           residual=residual)
+
+    def _gn(self, x, n: _Norm, B, HW, eps, silu):
+        return L.groupnorm(x, n.g, n.b, batch=B, hw=HW, groups=self.spec.norm_num_groups, eps=eps, silu=silu)
+
+    def _resnet(self, x, p, B, H, W):
+        t = self._gn(x, p["norm1"], B, H * W, self.spec.norm_eps, True)
+        h = self._conv(t, p["conv1"], B, H, W)
+        t = self._gn(h, p["norm2"], B, H * W, self.spec.norm_eps, True)
+        skip = x if p["shortcut"] is None else self._lin(x, p["shortcut"])
+        return self._conv(t, p["conv2"], B, H, W, residual=skip)
+
+    def _transformer(self, x, p, B, S, ref: Optional[RefKV] = None, capture: bool = False):
+        C, heads = p["ch"], p["heads"]
+        scale = 0.125  # head_dim ** -0.5, head_dim == 64
+        t = self._gn(x, p["norm"], B, S, 1e-6, False)
+        h = self._lin(t, p["proj_in"])
+        # --- attn1: self attention, shared with the reference images in the up blocks
+        n = L.layernorm(h, p["ln1"].g, p["ln1"].b)
+        qkv = self._lin(n, p["qkv"])                                   # [B*S, 3C]: q | k | v
+        if capture:
+            self.captured.append(RefKV(buf=qkv, k_off=C, v_off=2 * C, n_ref=0, s_ref=S))
+        kw = {}
+        own = True
+        if self.consume_refs and ref is not None:
+            kw.update(k_ref=ref.buf[:, ref.k_off:], v_ref=ref.buf[:, ref.v_off:], n_ref=ref.n_ref, s_ref=ref.s_ref)
+            if self.use_adain:
+                sc, sh = L.adain_coeffs(qkv[:, 2 * C:], ref.buf[:, ref.v_off:], batch=B, s_own=S, n_ref=ref.n_ref,
+                                        s_ref=ref.s_ref, channels=C)
+                kw.update(adain_scale=sc, adain_shift=sh)
+            own = self.train_input
+        if own:
+            kw.update(k_own=qkv[:, C:], v_own=qkv[:, 2 * C:], s_own=S)
+        a = L.shared_attn(qkv, heads=heads, scale=scale, batch=B, s_q=S, **kw)
+        h = self._lin(a, p["out1"], residual=h)
+        # --- attn2: cross attention against the constant caption K/V
+        n = L.layernorm(h, p["ln2"].g, p["ln2"].b)
+        q = self._lin(n, p["q2"])
+        a = L.shared_attn(q, heads=heads, scale=scale, batch=B, s_q=S, k_own=p["k2"], v_own=p["v2"], s_own=self.n_ctx,
+                          own_shared=True)
+        h = self._lin(a, p["out2"], residual=h)
+        # --- feed-forward (GEGLU fused into the first GEMM's epilogue)
+        n = L.layernorm(h, p["ln3"].g, p["ln3"].b)
+        g = self._lin(n, p["ff1"], act=L.IR_ACT_GEGLU)
+        h = self._lin(g, p["ff2"], residual=h)
+        return self._lin(h, p["proj_out"], residual=x)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, B: int, H: int, W: int, ref_kv: Optional[Sequence[RefKV]] = None) -> torch.Tensor:
+        """x: fp16 channel-last latent [B*H*W, 64] (4 real channels). Returns the model output [B*H*W, 4] fp16."""
+        self.captured = []
+        shared_idx = 0
+        h = self._conv(x, self.conv_in, B, H, W)
+        skips = [(h, H, W)]
+        for layers, ds in self.down:
+            for res, tr in layers:
+                h = self._resnet(h, res, B, H, W)
+                if tr is not None:
+                    h = self._transformer(h, tr, B, H * W)
+                skips.append((h, H, W))
+            if ds is not None:
+                h = self._conv(h, ds, B, H, W)
+                H, W = H // 2, W // 2
+                skips.append((h, H, W))
+        r0, tr, r1 = self.mid
+        h = self._resnet(h, r0, B, H, W)
+        h = self._transformer(h, tr, B, H * W)
+        h = self._resnet(h, r1, B, H, W)
+        for i, (layers, us) in enumerate(self.up):
+            bscale, sscale = 1.0, 1.0
+            if self.freeu is not None and i < 2:
+                s1, s2, b1, b2 = self.freeu
+                bscale, sscale = (b1, s1) if i == 0 else (b2, s2)
+            for res, tr in layers:
+                skip, sh, sw = skips.pop()
+                assert (sh, sw) == (H, W)
+                cat = L.concat_freeu(h, skip, batch=B, h=H, w=W, backbone_scale=bscale, skip_scale=sscale)
+                h = self._resnet(cat, res, B, H, W)
+                if tr is not None:
+                    ref = ref_kv[shared_idx] if (self.consume_refs and ref_kv is not None) else None
+                    shared_idx += 1
+                    h = self._transformer(h, tr, B, H * W, ref, capture=self.capture_kv)
+            if us is not None:
+                h = L.upsample_nearest2x(h, batch=B, h=H, w=W)
+                H, W = 2 * H, 2 * W
+                h = self._conv(h, us, B, H, W)
+        t = self._gn(h, self.norm_out, B, H * W, self.spec.norm_eps, True)
+        return self._conv(t, self.conv_out, B, H, W)

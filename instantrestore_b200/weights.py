@@ -1,0 +1,89 @@
+"""Checkpoint -> device weight packing for the UNet engine.
+
+Accepts the reference state_dict layout: diffusers module paths, optionally peft-wrapped leaves
+(`<mod>.base_layer.weight|bias`, `<mod>.lora_A.<adapter>.weight`, `<mod>.lora_B.<adapter>.weight`; reference
+pix2pix_turbo.py:171-179) which are merged at load time as W' = W + (alpha/r) * B.A with alpha = r // 2.
+Everything input-independent is folded here, once: conv weights go to [C_out, ky, kx, C_in] fp16 (the K-major B
+operand the implicit-GEMM kernel TMA-loads), q/k/v of every self-attention are stacked into one [3C, C] GEMM, GEGLU
+rows are interleaved in blocks of 64 so value and gate land in the same accumulator tile, conv_in channels are
+zero-padded to 64.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+LORA_ADAPTERS = ("default", "vae_skip")
+
+
+class StateDictView:
+    """Prefix-scoped accessor that merges LoRA on the fly. All math in fp32 on the CPU."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str = "", lora_alpha_over_r: Optional[float] = None):
+        self.sd = sd
+        self.prefix = prefix
+        self.lora_scale = lora_alpha_over_r
+
+    def sub(self, name: str) -> "StateDictView":
+        return StateDictView(self.sd, f"{self.prefix}{name}.", self.lora_scale)
+
+    def has(self, name: str) -> bool:
+        k = self.prefix + name
+        return k in self.sd or (self.prefix + name.replace(".weight", ".base_layer.weight").replace(".bias", ".base_layer.bias")) in self.sd
+
+    def _raw(self, key: str) -> Optional[torch.Tensor]:
+        t = self.sd.get(self.prefix + key)
+        return None if t is None else t.detach().to(torch.float32).cpu()
+
+    def weight(self, mod: str) -> torch.Tensor:
+        """Merged fp32 weight of a Linear/Conv2d leaf."""
+        w = self._raw(f"{mod}.weight")
+        if w is not None:
+            return w
+        w = self._raw(f"{mod}.base_layer.weight")
+        if w is None:
+            raise KeyError(f"missing weight for {self.prefix}{mod}")
+        for ad in LORA_ADAPTERS:
+            a = self._raw(f"{mod}.lora_A.{ad}.weight")
+            b = self._raw(f"{mod}.lora_B.{ad}.weight")
+            if a is None or b is None:
+                continue
+            r = a.shape[0]
+            scale = self.lora_scale if self.lora_scale is not None else (r // 2) / r
+            if w.ndim == 2:
+                w = w + scale * (b @ a)
+            else:
+                w = w + scale * torch.einsum("or,rikl->oikl", b[:, :, 0, 0], a)
+        return w
+
+    def bias(self, mod: str) -> Optional[torch.Tensor]:
+        b = self._raw(f"{mod}.bias")
+        if b is None:
+            b = self._raw(f"{mod}.base_layer.bias")
+        return b
+
+    def param(self, name: str) -> torch.Tensor:
+        t = self._raw(name)
+        if t is None:
+            raise KeyError(f"missing parameter {self.prefix}{name}")
+        return t
+
+
+def conv_weight_khwc(w: torch.Tensor, c_in_pad: int = 0) -> torch.Tensor:
+    """[C_out, C_in, kh, kw] -> [C_out, kh*kw*C_in(_pad)] fp16, tap-major then channel."""
+    co, ci, kh, kw = w.shape
+    w = w.permute(0, 2, 3, 1)
+    if c_in_pad and c_in_pad > ci:
+        w = torch.nn.functional.pad(w, (0, c_in_pad - ci))
+    return w.reshape(co, -1).contiguous().to(torch.float16)
+
+
+def geglu_interleave_index(n_total: int) -> torch.Tensor:
+    """Row permutation for the GEGLU projection: per 128-row block, 64 value rows then their 64 gate rows."""
+    half = n_total // 2
+    assert half % 64 == 0, "GEGLU inner width must be a multiple of 64"
+    idx = []
+    for blk in range(half // 64):
+        idx += list(range(blk * 64, blk * 64 + 64)) + list(range(half + blk * 64, half + blk * 64 + 64))
+    return torch.tensor(idx, dtype=torch.long)

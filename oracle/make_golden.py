@@ -1,0 +1,148 @@
+"""Generates tests/golden/*.npz by running the REFERENCE'S OWN code (face_replace/models/unet_2d_condition/unet.py,
+block.py and face_replace/models/attn_processors.py, imported from /root/reference) on top of oracle/shim.
+Runs only in the build container (the GPU box has no /root/reference); the vectors it writes are committed.
+
+    python -m oracle.make_golden            # all cases
+    python -m oracle.make_golden --no-full  # skip the full-width SD-Turbo case (about a minute of CPU)
+
+Each file stores the seeds/config needed to rebuild the inputs from oracle/synth.py plus the reference outputs
+(fp32). Inputs are NOT stored (they are regenerated from the seeds), outputs are small (<= 64 KB each).
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+GOLDEN = ROOT / "tests" / "golden"
+REFERENCE = Path("/root/reference")
+
+ATTN_CASES = [  # name, heads, S, n_ref, use_adain, train_input, zeroed_slots
+    ("attn_plain", 2, 64, 0, False, True, 0),
+    ("attn_refs_only", 2, 64, 2, False, False, 0),
+    ("attn_own_plus_refs", 2, 64, 2, False, True, 0),
+    ("attn_adain_refs_only", 2, 64, 3, True, False, 0),
+    ("attn_adain_own_plus_refs", 1, 128, 2, True, True, 0),
+    ("attn_adain_padded_slot", 2, 64, 3, True, False, 1),
+]
+UNET_CASES = [  # name, batch, n_ref, use_adain, train_input, lora_rank, valid
+    ("unet_tiny_base", 1, 2, False, True, 0, None),
+    ("unet_tiny_final", 2, 2, True, False, 4, None),
+    ("unet_tiny_padded", 2, 3, True, False, 4, [3, 1]),
+]
+
+
+def import_reference():
+    if not REFERENCE.exists():
+        raise RuntimeError("/root/reference is not mounted: golden vectors can only be regenerated in the build container")
+    sys.path.insert(0, str(ROOT / "oracle" / "shim"))
+    sys.path.insert(0, str(REFERENCE))
+    from face_replace.models import attn_processors as ref_ap
+    from face_replace.models.unet_2d_condition import block as ref_block
+    from face_replace.models.unet_2d_condition.unet import UNet2DConditionModel as RefUNet
+    return ref_ap, ref_block, RefUNet
+
+
+def attn_inputs(heads, s, n_ref, zeroed, seed=7):
+    """Inputs of one processor call: hidden states, an Attention module, reference keys/values (B, N, S, C)."""
+    from oracle.diffusers024 import Attention
+    from oracle.synth import seeded_init_
+    g = torch.Generator().manual_seed(seed)
+    c = heads * 64
+    attn = seeded_init_(Attention(query_dim=c, heads=heads, dim_head=64), seed).eval().requires_grad_(False)
+    hidden = torch.randn(2, s, c, generator=g)
+    rk = torch.randn(2, max(n_ref, 1), s, c, generator=g)
+    rv = torch.randn(2, max(n_ref, 1), s, c, generator=g) * 1.5 + 0.25
+    if zeroed:
+        rk[1, -zeroed:] = 0
+        rv[1, -zeroed:] = 0
+    return attn, hidden, rk, rv
+
+
+def build_pipeline(RefUNet, ref_ap, cfg, flags, lora_rank, seed=0):
+    """Reference UNet classes + reference processors, weights copied from the seeded oracle models."""
+    from oracle import synth
+    from oracle.pipeline import LatentRestorePipeline
+    kw = dict(sample_size=cfg.sample_size, block_out_channels=cfg.block_out_channels,
+              attention_head_dim=cfg.attention_head_dim, cross_attention_dim=cfg.cross_attention_dim,
+              use_linear_projection=True)
+    ref_unet, ref_orig = RefUNet(**kw), RefUNet(**kw)
+    o_unet = synth.make_unet(cfg, seed=seed, lora_rank=lora_rank)
+    o_orig = synth.make_unet(cfg, seed=seed)
+    if lora_rank:
+        from oracle.diffusers024 import add_lora
+        add_lora(ref_unet, synth.UNET_LORA_TARGETS, r=lora_rank, alpha=lora_rank // 2)
+    ref_unet.load_state_dict(o_unet.state_dict(), strict=True)
+    ref_orig.load_state_dict(o_orig.state_dict(), strict=True)
+    for m in (ref_unet, ref_orig):
+        m.enable_freeu(0.9, 0.2, 1.4, 1.6)
+        m.eval().requires_grad_(False)
+    cap = synth.caption_embedding(cfg.cross_attention_dim)
+    return LatentRestorePipeline(ref_unet, ref_orig, cap, flags, processors=ref_ap)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--no-full", action="store_true")
+    args = ap.parse_args()
+    ref_ap, ref_block, RefUNet = import_reference()
+    from oracle import synth
+    from oracle.unet import UNetConfig
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    torch.manual_seed(0)
+
+    # 1) the operator: SharedAttnProcessor.forward / AttnProcessor.forward of the reference
+    for name, heads, s, n_ref, use_adain, train_input, zeroed in ATTN_CASES:
+        attn, hidden, rk, rv = attn_inputs(heads, s, n_ref, zeroed)
+        proc = ref_ap.SharedAttnProcessor(self_attn_idx=0 if n_ref else None, save_self_attentions=True,
+                                          use_adain=use_adain, train_input=train_input)
+        with torch.no_grad():
+            out = proc(attn, hidden, ref_keys=[rk] if n_ref else None, ref_values=[rv] if n_ref else None)
+        mass = proc.attention_probs.sum(dim=2)  # (B, H, S_k): column mass, used for the per-chunk read-out
+        np.savez_compressed(GOLDEN / f"{name}.npz", out=out.numpy(), probs_colsum=mass.numpy(),
+                            meta=np.array([heads, s, n_ref, int(use_adain), int(train_input), zeroed]))
+        print(name, tuple(out.shape), float(out.abs().max()))
+    # the KV-capturing processor of the reference-image UNet
+    attn, hidden, _, _ = attn_inputs(2, 64, 0, 0)
+    cap_proc = ref_ap.AttnProcessor()
+    with torch.no_grad():
+        out = cap_proc(attn, hidden)
+    np.savez_compressed(GOLDEN / "attn_kv_capture.npz", out=out.numpy(), keys=cap_proc.keys.numpy(), values=cap_proc.values.numpy())
+
+    # 2) FreeU (reference block.py:3495-3520 on top of the restated fourier_filter)
+    g = torch.Generator().manual_seed(11)
+    for idx, (h, c) in enumerate([(8, 64), (16, 32)]):
+        hs = torch.randn(2, c, h, h, generator=g)
+        res = torch.randn(2, c, h, h, generator=g)
+        hs2, res2 = ref_block.apply_freeu(idx, hs.clone(), res.clone(), s1=0.9, s2=0.2, b1=1.4, b2=1.6)
+        np.savez_compressed(GOLDEN / f"freeu_stage{idx}.npz", hidden=hs2.numpy(), skip=res2.numpy())
+
+    # 3) whole pipeline at the latent boundary on the reduced-width UNet
+    tiny = UNetConfig.tiny()
+    for name, batch, n_ref, use_adain, train_input, lora_rank, valid in UNET_CASES:
+        flags = synth.ModelFlags(use_adain=use_adain, train_input=train_input)
+        pipe = build_pipeline(RefUNet, ref_ap, tiny, flags, lora_rank)
+        enc, refs, nm, nr = synth.latents(batch, n_ref, tiny.sample_size)
+        out = pipe.forward_latents(enc, refs, nm, nr, valid_indices=valid)
+        np.savez_compressed(GOLDEN / f"{name}.npz", x0=out.numpy(),
+                            meta=np.array([batch, n_ref, int(use_adain), int(train_input), lora_rank]),
+                            valid=np.array(valid if valid is not None else [n_ref] * batch))
+        print(name, tuple(out.shape), float(out.std()))
+
+    # 4) full-width SD-Turbo geometry, released "final model" flags (AdaIN on, refs-only KV), B=1, N=4
+    if not args.no_full:
+        full = UNetConfig()
+        flags = synth.ModelFlags(use_adain=True, train_input=False)
+        pipe = build_pipeline(RefUNet, ref_ap, full, flags, lora_rank=0)
+        enc, refs, nm, nr = synth.latents(1, 4, full.sample_size)
+        out = pipe.forward_latents(enc, refs, nm, nr)
+        np.savez_compressed(GOLDEN / "unet_full_final_n4.npz", x0=out.numpy(), meta=np.array([1, 4, 1, 0, 0]))
+        print("unet_full_final_n4", tuple(out.shape), float(out.std()))
+
+
+if __name__ == "__main__":
+    main()

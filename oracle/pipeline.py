@@ -1,0 +1,71 @@
+"""ORACLE (test infrastructure): CPU restatement of the reference single-step pipeline at the latent boundary.
+
+Follows reference face_replace/models/pix2pix_turbo.py: get_conditioning_keys_values :242-279 (noise the reference
+latents to t=1, run the frozen UNet, gather the 9 captured key/value pairs as (B, N, S, C), ZERO the padded slots)
+and forward :281-343 (noise the degraded latent to t=noise_timestep, run the LoRA-tuned UNet with
+cross_attention_kwargs={'ref_keys','ref_values'}, take the scheduler's pred_original_sample). The four stochastic
+draws of the reference (two VAE posterior samples, two randn_like) are injected as arguments so the path is
+deterministic; the VAE on either side of this boundary is a later row of SURVEY.md 8f.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import attn_processors as _oracle_processors
+from .diffusers024 import DDPMScheduler1Step
+from .synth import ModelFlags
+from .unet import UNet2DConditionModel
+
+
+class LatentRestorePipeline:
+    def __init__(self, unet: UNet2DConditionModel, original_unet: UNet2DConditionModel, caption_enc: torch.Tensor,
+                 flags: ModelFlags, save_self_attentions: bool = False, noise_timestep: int = 249,
+                 processors=_oracle_processors):
+        """`processors`: module providing AttnProcessor / register_attention_processor(_kv_unet); the oracle's by
+        default, the reference's own face_replace.models.attn_processors when generating golden vectors."""
+        self.unet, self.original_unet = unet, original_unet
+        self.caption_enc = caption_enc
+        self.flags = flags
+        self.sched = DDPMScheduler1Step()
+        self.noise_timestep = noise_timestep          # reference test.py:62 sets noise_timesteps = [249]
+        self._kv_proc_type = processors.AttnProcessor
+        processors.register_attention_processor_kv_unet(original_unet)                              # pix2pix_turbo.py:97
+        processors.register_attention_processor(unet, cfg=flags, save_self_attentions=save_self_attentions)  # :98
+
+    @torch.no_grad()
+    def conditioning_keys_values(self, ref_latents: torch.Tensor, noise: torch.Tensor, valid_indices) -> Tuple[List, List]:
+        b, n = ref_latents.shape[:2]
+        enc = ref_latents.reshape(b * n, *ref_latents.shape[2:])
+        t = torch.tensor([1])
+        noisy = self.sched.add_noise(enc, noise, t.long().repeat(enc.shape[0]))
+        cap = self.caption_enc.repeat(enc.shape[0], 1, 1)
+        self.original_unet(noisy, t, encoder_hidden_states=cap)
+        procs = [p for p in self.original_unet.attn_processors.values() if type(p) is self._kv_proc_type]
+        keys = [p.keys.reshape(-1, n, p.keys.shape[1], p.keys.shape[2]) for p in procs]
+        values = [p.values.reshape(-1, n, p.values.shape[1], p.values.shape[2]) for p in procs]
+        for k, v in zip(keys, values):
+            for i in range(k.shape[0]):
+                idx = int(valid_indices[i])
+                k[i, idx:] = 0
+                v[i, idx:] = 0
+        for p in procs:
+            p.reset()
+        return keys, values
+
+    @torch.no_grad()
+    def forward_latents(self, enc_control: torch.Tensor, ref_latents: Optional[torch.Tensor], noise_main: torch.Tensor,
+                        noise_ref: Optional[torch.Tensor], valid_indices=None) -> torch.Tensor:
+        keys = values = None
+        if ref_latents is not None and self.flags.use_shared_attention:
+            if valid_indices is None:
+                valid_indices = [ref_latents.shape[1]] * ref_latents.shape[0]
+            keys, values = self.conditioning_keys_values(ref_latents, noise_ref, valid_indices)
+        t = torch.tensor([self.noise_timestep])
+        noisy = self.sched.add_noise(enc_control, noise_main, t.long().repeat(enc_control.shape[0]))
+        cap = self.caption_enc.repeat(noisy.shape[0], 1, 1)
+        pred = self.unet(noisy, t, encoder_hidden_states=cap,
+                         cross_attention_kwargs={"ref_keys": keys, "ref_values": values})
+        pred = getattr(pred, "sample", pred)
+        return self.sched.pred_original_sample(pred, self.noise_timestep, noisy)
