@@ -41,6 +41,8 @@ const char* ir_last_error_string(void);
 int ir_version(void);
 /* 0 when the current device is a B200-class (sm_100) GPU, IR_ERR_ARCH / IR_ERR_CUDA otherwise. */
 int ir_check_device(void);
+/* Number of kernel launches issued (or captured into a CUDA graph) through this library since load. */
+unsigned long long ir_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * ir_conv_gemm — im2col-free implicit GEMM on tcgen05 tensor cores (TMA-staged, TMEM accumulators).

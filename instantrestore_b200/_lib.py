@@ -16,7 +16,7 @@ LIB_PATH = _PKG / "libinstantrestore_b200.so"
 IR_ACT_NONE, IR_ACT_GEGLU, IR_ACT_SILU = 0, 1, 2
 
 EXPORTED_SYMBOLS = [
-    "ir_last_error_string", "ir_version", "ir_check_device", "ir_conv_gemm", "ir_shared_attn_fwd",
+    "ir_last_error_string", "ir_version", "ir_check_device", "ir_launch_count", "ir_conv_gemm", "ir_shared_attn_fwd",
     "ir_groupnorm", "ir_groupnorm_workspace_bytes", "ir_layernorm", "ir_adain_coeffs", "ir_adain_workspace_bytes",
     "ir_concat_freeu", "ir_upsample_nearest2x", "ir_latent_in", "ir_latent_out",
 ]
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
         )
     lib = C.CDLL(str(LIB_PATH))
     lib.ir_last_error_string.restype = C.c_char_p
+    lib.ir_launch_count.restype = C.c_ulonglong
     lib.ir_groupnorm_workspace_bytes.restype = C.c_size_t
     lib.ir_adain_workspace_bytes.restype = C.c_size_t
     lib.ir_conv_gemm.argtypes = [C.POINTER(ConvGemmParams), C.c_void_p]
@@ -114,6 +115,50 @@ def load() -> C.CDLL:
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"{what} failed ({rc}): {load().ir_last_error_string().decode()}")
+
+
+def launch_count() -> int:
+    return int(load().ir_launch_count())
+
+
+class Trace:
+    """Per-call device timing for the roofline report: while active, every C-ABI call is bracketed by CUDA events
+    recorded on the launching stream, together with its algorithmic work (flops, bytes). Not usable under graph
+    capture; bench.py runs one eager instrumented step with it."""
+    active: "Trace | None" = None
+
+    def __init__(self):
+        self.records = []   # (op, tag, flops, bytes, start_event, end_event)
+
+    def __enter__(self):
+        Trace.active = self
+        return self
+
+    def __exit__(self, *exc):
+        Trace.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        rows = {}
+        for op, tag, flops, nbytes, e0, e1 in self.records:
+            r = rows.setdefault((op, tag), dict(op=op, shape=tag, calls=0, ms=0.0, flops=0.0, bytes=0.0))
+            r["calls"] += 1
+            r["ms"] += e0.elapsed_time(e1)
+            r["flops"] += flops
+            r["bytes"] += nbytes
+        return sorted(rows.values(), key=lambda r: -r["ms"])
+
+
+def _run(op: str, tag: str, flops: float, nbytes: float, fn, *args) -> None:
+    tr = Trace.active
+    if tr is None:
+        check(fn(*args), op)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(*args), op)
+    e1.record()
+    tr.records.append((op, tag, flops, nbytes, e0, e1))
 
 
 def stream_ptr() -> int:
@@ -159,7 +204,10 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
         ksize=ksize, stride=stride, w=ptr(w), c_out=c_out, bias=ptr(bias),
         residual=ptr(residual), res_row_stride=residual.stride(-2) if residual is not None else 0,
         act=act, out=ptr(out), out_row_stride=out.stride(-2), tile_n=tile_n)
-    check(load().ir_conv_gemm(C.byref(p), stream_ptr()), "ir_conv_gemm")
+    k_tot = ksize * ksize * c_in
+    _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks{ksize}s{stride}", 2.0 * m * k_tot * c_out,
+         2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out),
+         load().ir_conv_gemm, C.byref(p), stream_ptr())
     return out
 
 
@@ -187,7 +235,9 @@ def shared_attn(q: torch.Tensor, *, heads: int, scale: float, batch: int, s_q: i
     if k_ref is not None:
         _h(k_ref, "k_ref"); _h(v_ref, "v_ref")
         assert k_ref.stride(-2) == v_ref.stride(-2)
-    check(load().ir_shared_attn_fwd(C.byref(p), stream_ptr()), "ir_shared_attn_fwd")
+    s_kv = (s_own if k_own is not None else 0) + n_ref * s_ref
+    _run("ir_shared_attn_fwd", f"b{batch}_h{heads}_sq{s_q}_skv{s_kv}", 4.0 * batch * heads * s_q * s_kv * 64,
+         2.0 * batch * heads * 64 * (2 * s_q + 2 * s_kv), load().ir_shared_attn_fwd, C.byref(p), stream_ptr())
     return out
 
 
@@ -203,7 +253,8 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch
     p = GroupNormParams(x=ptr(x), x_row_stride=x.stride(-2), batch=batch, hw=hw, channels=channels, groups=groups,
                         eps=eps, gamma=ptr(gamma), beta=ptr(beta), silu=int(silu), out=ptr(out),
                         out_row_stride=out.stride(-2), workspace=ptr(workspace))
-    check(load().ir_groupnorm(C.byref(p), stream_ptr()), "ir_groupnorm")
+    _run("ir_groupnorm", f"b{batch}_hw{hw}_c{channels}", 0.0, 4.0 * batch * hw * channels, load().ir_groupnorm,
+         C.byref(p), stream_ptr())
     return out
 
 
@@ -215,7 +266,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
         out = torch.empty((rows, channels), dtype=torch.float16, device=x.device)
     p = LayerNormParams(x=ptr(x), x_row_stride=x.stride(-2), rows=rows, channels=channels, eps=eps, gamma=ptr(gamma),
                         beta=ptr(beta), out=ptr(out), out_row_stride=out.stride(-2))
-    check(load().ir_layernorm(C.byref(p), stream_ptr()), "ir_layernorm")
+    _run("ir_layernorm", f"r{rows}_c{channels}", 0.0, 4.0 * rows * channels, load().ir_layernorm, C.byref(p),
+         stream_ptr())
     return out
 
 
@@ -235,7 +287,8 @@ def adain_coeffs(v_own: torch.Tensor, v_ref: torch.Tensor, *, batch: int, s_own:
                           v_ref=ptr(v_ref), ref_row_stride=v_ref.stride(-2), ref_col_off=ref_col_off, n_ref=n_ref,
                           s_ref=s_ref, batch=batch, channels=channels, eps=eps, scale=ptr(scale), shift=ptr(shift),
                           workspace=ptr(workspace))
-    check(load().ir_adain_coeffs(C.byref(p), stream_ptr()), "ir_adain_coeffs")
+    _run("ir_adain_coeffs", f"b{batch}_n{n_ref}_s{s_ref}_c{channels}", 0.0,
+         2.0 * batch * channels * (s_own + n_ref * s_ref), load().ir_adain_coeffs, C.byref(p), stream_ptr())
     return scale, shift
 
 
@@ -248,7 +301,8 @@ def concat_freeu(hidden: torch.Tensor, skip: torch.Tensor, *, batch: int, h: int
         out = torch.empty((batch * h * w, ch + cs), dtype=torch.float16, device=hidden.device)
     p = ConcatFreeuParams(hidden=ptr(hidden), skip=ptr(skip), batch=batch, h=h, w=w, c_hidden=ch, c_skip=cs,
                           backbone_scale=backbone_scale, skip_scale=skip_scale, out=ptr(out))
-    check(load().ir_concat_freeu(C.byref(p), stream_ptr()), "ir_concat_freeu")
+    _run("ir_concat_freeu", f"b{batch}_hw{h * w}_c{ch}+{cs}", 0.0, 4.0 * batch * h * w * (ch + cs),
+         load().ir_concat_freeu, C.byref(p), stream_ptr())
     return out
 
 
@@ -258,7 +312,8 @@ def upsample_nearest2x(x: torch.Tensor, *, batch: int, h: int, w: int, out: torc
     c = x.shape[-1]
     if out is None:
         out = torch.empty((batch * 4 * h * w, c), dtype=torch.float16, device=x.device)
-    check(load().ir_upsample_nearest2x(ptr(x), ptr(out), batch, h, w, c, stream_ptr()), "ir_upsample_nearest2x")
+    _run("ir_upsample_nearest2x", f"b{batch}_hw{h * w}_c{c}", 0.0, 10.0 * batch * h * w * c,
+         load().ir_upsample_nearest2x, ptr(x), ptr(out), batch, h, w, c, stream_ptr())
     return out
 
 

@@ -6,11 +6,15 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace ir {
 
 static thread_local char g_err[512] = "ok";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -90,5 +94,6 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 }  // namespace ir
 
 extern "C" const char* ir_last_error_string(void) { return ir::g_err; }
-extern "C" int ir_version(void) { return 100; }
+extern "C" int ir_version(void) { return 101; }
+extern "C" unsigned long long ir_launch_count(void) { return ir::g_launches.load(std::memory_order_relaxed); }
 extern "C" int ir_check_device(void) { return ir::check_arch(); }

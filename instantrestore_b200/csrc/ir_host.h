@@ -19,8 +19,12 @@ int check_arch();
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
 
+// Counts kernel launches issued (or captured into a CUDA graph) through the C ABI; read by ir_launch_count().
+void count_launch();
+
 #define IR_CUDA_LAUNCH_CHECK(what)                                                      \
   do {                                                                                  \
+    ir::count_launch();                                                                 \
     cudaError_t e__ = cudaGetLastError();                                               \
     if (e__ != cudaSuccess) return ir::set_error(IR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e__)); \
   } while (0)

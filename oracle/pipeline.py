@@ -38,9 +38,9 @@ class LatentRestorePipeline:
     def conditioning_keys_values(self, ref_latents: torch.Tensor, noise: torch.Tensor, valid_indices) -> Tuple[List, List]:
         b, n = ref_latents.shape[:2]
         enc = ref_latents.reshape(b * n, *ref_latents.shape[2:])
-        t = torch.tensor([1])
+        t = torch.tensor([1], device=enc.device)
         noisy = self.sched.add_noise(enc, noise, t.long().repeat(enc.shape[0]))
-        cap = self.caption_enc.repeat(enc.shape[0], 1, 1)
+        cap = self.caption_enc.to(enc.device).repeat(enc.shape[0], 1, 1)
         self.original_unet(noisy, t, encoder_hidden_states=cap)
         procs = [p for p in self.original_unet.attn_processors.values() if type(p) is self._kv_proc_type]
         keys = [p.keys.reshape(-1, n, p.keys.shape[1], p.keys.shape[2]) for p in procs]
@@ -62,9 +62,9 @@ class LatentRestorePipeline:
             if valid_indices is None:
                 valid_indices = [ref_latents.shape[1]] * ref_latents.shape[0]
             keys, values = self.conditioning_keys_values(ref_latents, noise_ref, valid_indices)
-        t = torch.tensor([self.noise_timestep])
+        t = torch.tensor([self.noise_timestep], device=enc_control.device)
         noisy = self.sched.add_noise(enc_control, noise_main, t.long().repeat(enc_control.shape[0]))
-        cap = self.caption_enc.repeat(noisy.shape[0], 1, 1)
+        cap = self.caption_enc.to(noisy.device).repeat(noisy.shape[0], 1, 1)
         pred = self.unet(noisy, t, encoder_hidden_states=cap,
                          cross_attention_kwargs={"ref_keys": keys, "ref_values": values})
         pred = getattr(pred, "sample", pred)

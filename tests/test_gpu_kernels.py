@@ -1,0 +1,270 @@
+"""GPU parity, kernel level: every C-ABI entry point against plain fp32 torch math on the same fp16 inputs.
+Tolerance (floating point path, north_star: 1e-3 relative fp16): relative L2 error <= 1e-3 for fp16 outputs
+(one fp16 rounding of the result is 2.8e-4 RMS), 1e-5 for fp32 outputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def L():
+    from instantrestore_b200 import _lib
+    _lib.load()
+    assert _lib.load().ir_check_device() == 0, _lib.load().ir_last_error_string()
+    return _lib
+
+
+def _gen(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM / conv
+@pytest.mark.parametrize("M,K,N,tile_n,use_bias,use_res", [
+    (4096, 320, 320, 0, True, True), (4096, 320, 320, 64, True, False), (77, 1024, 640, 0, False, False),
+    (256, 1280, 1280, 0, True, True), (1024, 640, 640, 128, True, True), (1024, 640, 640, 256, True, True),
+    (64, 1280, 1280, 0, True, False), (300, 64, 72, 0, True, True), (4096, 320, 4, 0, True, False),
+    (1, 320, 1280, 0, True, False), (4096, 1280, 320, 0, True, True), (129, 64, 64, 0, False, False),
+])
+def test_linear(L, M, K, N, tile_n, use_bias, use_res):
+    g = _gen(1)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    bias = torch.randn(N, device="cuda", generator=g) if use_bias else None
+    r = torch.randn(M, N, device="cuda", generator=g).half() if use_res else None
+    out = L.conv_gemm(a, w, batch=1, h_in=1, w_in=M, c_in=K, bias=bias, residual=r, tile_n=tile_n)
+    ref = a.float() @ w.float().T
+    if bias is not None:
+        ref = ref + bias
+    if r is not None:
+        ref = ref.half().float() + r.float()
+    assert rel_l2(out, ref) <= TOL
+
+
+@pytest.mark.parametrize("M,K,N,tile_n", [(1024, 640, 5120, 0), (256, 64, 256, 128), (4096, 320, 2560, 256), (77, 128, 1024, 0)])
+def test_geglu_epilogue(L, M, K, N, tile_n):
+    from instantrestore_b200.weights import geglu_interleave_index
+    g = _gen(2)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    h = (a.float() @ w.float().T + bias)
+    ref = h[:, : N // 2] * F.gelu(h[:, N // 2:])
+    idx = geglu_interleave_index(N).cuda()
+    out = L.conv_gemm(a, w[idx].contiguous(), batch=1, h_in=1, w_in=M, c_in=K, bias=bias[idx].contiguous(),
+                      act=L.IR_ACT_GEGLU, tile_n=tile_n)
+    assert out.shape == (M, N // 2)
+    assert rel_l2(out, ref) <= 2 * TOL     # two fp16 roundings (projection, gelu) before the product, as autocast does
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co,stride,tile_n", [
+    (1, 64, 64, 64, 64, 1, 0), (2, 16, 16, 128, 192, 1, 0), (3, 8, 8, 64, 128, 1, 0), (1, 4, 4, 64, 64, 1, 0),
+    (5, 4, 4, 128, 64, 1, 0), (1, 64, 64, 320, 320, 1, 0), (1, 64, 64, 320, 320, 1, 64), (2, 32, 32, 640, 640, 1, 0),
+    (1, 64, 64, 64, 64, 2, 0), (2, 32, 32, 128, 128, 2, 0), (3, 8, 8, 64, 64, 2, 0), (1, 16, 16, 1280, 1280, 1, 0),
+    (1, 8, 8, 2560, 1280, 1, 0), (1, 64, 64, 320, 4, 1, 0), (3, 16, 16, 1920, 1280, 1, 0),
+])
+def test_conv3x3(L, B, H, W, Ci, Co, stride, tile_n):
+    g = _gen(3)
+    x = torch.randn(B, Ci, H, W, device="cuda", generator=g).half()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Ci)).half()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    ref = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
+    a = x.permute(0, 2, 3, 1).contiguous().reshape(-1, Ci)
+    wk = w.permute(0, 2, 3, 1).contiguous().reshape(Co, 9 * Ci)
+    out = L.conv_gemm(a, wk, batch=B, h_in=H, w_in=W, c_in=Ci, ksize=3, stride=stride, bias=bias, tile_n=tile_n)
+    assert rel_l2(out, ref) <= TOL
+
+
+def test_conv_rejects_bad_shapes(L):
+    a = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
+    w = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="c_in"):
+        L.conv_gemm(a, w, batch=1, h_in=1, w_in=64, c_in=60)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k_chunks, v_chunks, heads, scale):
+    B, S, C = q.shape
+    k, v = torch.cat(k_chunks, 1), torch.cat(v_chunks, 1)
+    qh = q.float().reshape(B, S, heads, 64).transpose(1, 2)
+    kh = k.float().reshape(B, -1, heads, 64).transpose(1, 2)
+    vh = v.float().reshape(B, -1, heads, 64).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1)
+    return (p @ vh).transpose(1, 2).reshape(B, S, C), p
+
+
+ATTN_CFGS = [  # (B, H, S, own, n_ref, adain, s_own_override)
+    (1, 2, 256, True, 0, False, None), (1, 1, 128, True, 0, False, None), (2, 2, 256, False, 2, False, None),
+    (1, 2, 256, True, 2, False, None), (2, 3, 256, False, 3, True, None), (1, 2, 64, True, 1, True, None),
+    (1, 2, 256, True, 0, False, 77), (1, 5, 1024, False, 4, True, None), (1, 5, 4096, False, 4, True, None),
+    (2, 20, 256, True, 4, True, None), (1, 10, 1024, False, 1, False, None), (1, 5, 1024, True, 8, True, None),
+    (3, 2, 64, False, 2, True, None),
+]
+
+
+def _attn_case(L, B, H, S, own, n_ref, adain, s_own_o, seed=4, want_mass=False):
+    g = _gen(seed)
+    C = H * 64
+    q = torch.randn(B, S, C, device="cuda", generator=g).half()
+    s_own = s_own_o or S
+    shared = s_own_o is not None
+    kc, vc, kw = [], [], {}
+    if own:
+        nb = 1 if shared else B
+        ko = torch.randn(nb, s_own, C, device="cuda", generator=g).half()
+        vo = torch.randn(nb, s_own, C, device="cuda", generator=g).half()
+        kc.append(ko.expand(B, -1, -1)); vc.append(vo.expand(B, -1, -1).float())
+        kw.update(k_own=ko.reshape(-1, C), v_own=vo.reshape(-1, C), s_own=s_own, own_shared=shared)
+    if n_ref:
+        kr = torch.randn(B, n_ref, S, C, device="cuda", generator=g).half()
+        vr = (torch.randn(B, n_ref, S, C, device="cuda", generator=g) * 1.5 + 0.3).half()
+        kw.update(k_ref=kr.reshape(-1, C), v_ref=vr.reshape(-1, C), n_ref=n_ref, s_ref=S)
+        if adain:
+            a_s = (torch.rand(B, n_ref, C, device="cuda", generator=g) + 0.5).contiguous()
+            a_b = torch.randn(B, n_ref, C, device="cuda", generator=g).contiguous()
+            kw.update(adain_scale=a_s, adain_shift=a_b)
+        for r in range(n_ref):
+            kc.append(kr[:, r])
+            vv = vr[:, r].float()
+            if adain:
+                vv = vv * a_s[:, r, None, :] + a_b[:, r, None, :]
+            vc.append(vv)
+    ref, p = _attn_ref(q, kc, vc, H, 0.125)
+    return q, kw, ref, p
+
+
+@pytest.mark.parametrize("cfg", ATTN_CFGS, ids=[str(c) for c in ATTN_CFGS])
+def test_shared_attention(L, cfg):
+    B, H, S, own, n_ref, adain, s_own_o = cfg
+    q, kw, ref, _ = _attn_case(L, *cfg)
+    out = L.shared_attn(q.reshape(-1, H * 64), heads=H, scale=0.125, batch=B, s_q=S, **kw)
+    assert rel_l2(out.reshape(B, S, -1), ref) <= TOL
+
+
+def test_shared_attention_reads_fused_qkv_in_place(L):
+    """q/k/v as column slices of one [B*S, 3C] projection output (what the engine passes): no copies."""
+    g = _gen(5)
+    B, H, S = 2, 2, 256
+    C = H * 64
+    qkv = torch.randn(B * S, 3 * C, device="cuda", generator=g).half()
+    out = L.shared_attn(qkv, heads=H, scale=0.125, batch=B, s_q=S, k_own=qkv[:, C:], v_own=qkv[:, 2 * C:], s_own=S)
+    q, k, v = (qkv[:, i * C:(i + 1) * C].reshape(B, S, C) for i in range(3))
+    ref, _ = _attn_ref(q, [k], [v.float()], H, 0.125)
+    assert rel_l2(out.reshape(B, S, C), ref) <= TOL
+
+
+def test_attention_linearity_in_values(L):
+    """Size-independent property at a full-size layer (S=4096, 5 heads, 4 refs): attention is linear in V."""
+    g = _gen(6)
+    B, H, S, N = 1, 5, 4096, 4
+    C = H * 64
+    q = torch.randn(B * S, C, device="cuda", generator=g).half()
+    k = torch.randn(B * N * S, C, device="cuda", generator=g).half()
+    v1 = torch.randn(B * N * S, C, device="cuda", generator=g).half()
+    v2 = torch.randn(B * N * S, C, device="cuda", generator=g).half()
+    f = lambda v: L.shared_attn(q, heads=H, scale=0.125, batch=B, s_q=S, k_ref=k, v_ref=v, n_ref=N, s_ref=S).float()
+    vsum = (v1.float() + v2.float()).half()
+    lhs, rhs = f(vsum), f(v1) + f(v2)
+    assert rel_l2(lhs, rhs) <= 3e-3     # three independently rounded fp16 results + rounded v1+v2
+
+
+def test_attention_constant_values_give_constant(L):
+    """softmax rows sum to one: V == c  =>  O == c, at the largest layer with 8 references."""
+    B, H, S, N = 1, 5, 4096, 8
+    C = H * 64
+    g = _gen(7)
+    q = torch.randn(B * S, C, device="cuda", generator=g).half()
+    k = torch.randn(B * N * S, C, device="cuda", generator=g).half()
+    v = torch.full((B * N * S, C), 0.75, device="cuda", dtype=torch.float16)
+    out = L.shared_attn(q, heads=H, scale=0.125, batch=B, s_q=S, k_ref=k, v_ref=v, n_ref=N, s_ref=S)
+    assert float((out.float() - 0.75).abs().max()) <= 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ norms & helpers
+@pytest.mark.parametrize("B,HW,C,silu", [(2, 4096, 320, True), (1, 64, 2560, True), (3, 256, 64, False), (1, 1024, 960, True), (2, 256, 1920, True)])
+def test_groupnorm(L, B, HW, C, silu):
+    g = _gen(8)
+    x = (torch.randn(B, HW, C, device="cuda", generator=g) * 2 + 0.5).half()
+    gm, bt = torch.randn(C, device="cuda", generator=g), torch.randn(C, device="cuda", generator=g)
+    ref = F.group_norm(x.float().transpose(1, 2), 32, gm, bt, 1e-5).transpose(1, 2)
+    if silu:
+        ref = F.silu(ref)
+    out = L.groupnorm(x.reshape(-1, C), gm, bt, batch=B, hw=HW, silu=silu)
+    assert rel_l2(out.reshape(B, HW, C), ref) <= TOL
+
+
+@pytest.mark.parametrize("R,C", [(4096, 320), (77, 1280), (1000, 64), (1, 640)])
+def test_layernorm(L, R, C):
+    g = _gen(9)
+    x = (torch.randn(R, C, device="cuda", generator=g) * 2 + 0.5).half()
+    gm, bt = torch.randn(C, device="cuda", generator=g), torch.randn(C, device="cuda", generator=g)
+    out = L.layernorm(x, gm, bt)
+    assert rel_l2(out, F.layer_norm(x.float(), (C,), gm, bt, 1e-5)) <= TOL
+
+
+def test_adain_coeffs_including_zeroed_slot(L):
+    g = _gen(10)
+    B, S, C, N = 2, 256, 128, 3
+    vo = (torch.randn(B, S, C, device="cuda", generator=g) * 1.3 + 0.2).half()
+    vr = (torch.randn(B, N, S, C, device="cuda", generator=g) * 0.7 - 0.4).half()
+    vr[1, 2] = 0       # padded slot: std 0 -> scale = style_std / eps, shift = style_mean (reference quirk)
+    sc, sh = L.adain_coeffs(vo.reshape(-1, C), vr.reshape(-1, C), batch=B, s_own=S, n_ref=N, s_ref=S, channels=C)
+    sm, ss = vo.float().mean(1, keepdim=True), vo.float().std(1, keepdim=True) + 1e-5
+    cm, cs = vr.float().mean(2), vr.float().std(2) + 1e-5
+    ref_sc = ss / cs
+    assert rel_l2(sc, ref_sc) <= 1e-5
+    assert rel_l2(sh, sm - cm * ref_sc) <= 1e-5
+    assert torch.allclose(sh[1, 2], sm[1, 0], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("B,H,Ch,Cs,bs,ss", [(2, 8, 128, 64, 1.4, 0.9), (1, 16, 1280, 640, 1.6, 0.2), (2, 32, 64, 32, 1.0, 1.0), (1, 8, 1280, 1280, 1.4, 0.9)])
+def test_concat_freeu(L, B, H, Ch, Cs, bs, ss):
+    g = _gen(11)
+    W = H
+    hid = torch.randn(B, H * W, Ch, device="cuda", generator=g).half()
+    sk = torch.randn(B, H * W, Cs, device="cuda", generator=g).half()
+    out = L.concat_freeu(hid.reshape(-1, Ch), sk.reshape(-1, Cs), batch=B, h=H, w=W, backbone_scale=bs, skip_scale=ss)
+    hh = hid.float().clone()
+    hh[..., : Ch // 2] *= bs
+    x = sk.float().reshape(B, H, W, Cs).permute(0, 3, 1, 2)
+    if ss != 1.0:
+        xf = torch.fft.fftshift(torch.fft.fftn(x, dim=(-2, -1)), dim=(-2, -1))
+        mask = torch.ones_like(x)
+        mask[..., H // 2 - 1: H // 2 + 1, W // 2 - 1: W // 2 + 1] = ss
+        x = torch.fft.ifftn(torch.fft.ifftshift(xf * mask, dim=(-2, -1)), dim=(-2, -1)).real
+    ref = torch.cat([hh, x.permute(0, 2, 3, 1).reshape(B, H * W, Cs)], -1)
+    assert rel_l2(out.reshape(B, H * W, -1), ref) <= TOL
+
+
+def test_upsample_is_exact(L):
+    g = _gen(12)
+    x = torch.randn(2, 8, 8, 64, device="cuda", generator=g).half()
+    out = L.upsample_nearest2x(x.reshape(-1, 64), batch=2, h=8, w=8)
+    ref = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(out.reshape(2, 16, 16, 64).float(), ref)
+
+
+def test_latent_in_out_roundtrip(L):
+    """add_noise then pred_original_sample with eps == noise returns the clean latent (scheduler identity)."""
+    g = _gen(13)
+    x = torch.randn(2, 4, 16, 16, device="cuda", generator=g)
+    nz = torch.randn(2, 4, 16, 16, device="cuda", generator=g)
+    a, s = 0.9, 0.3
+    xin = L.latent_in(x, nz, a, s)
+    ref = torch.zeros(2, 256, 64, device="cuda")
+    ref[..., :4] = (a * x + s * nz).permute(0, 2, 3, 1).reshape(2, 256, 4)
+    assert rel_l2(xin.reshape(2, 256, 64), ref) <= TOL
+    eps = torch.zeros(2 * 256, 8, device="cuda", dtype=torch.float16)
+    eps[:, :4] = nz.permute(0, 2, 3, 1).reshape(-1, 4).half()
+    x0 = L.latent_out(eps, x, nz, a, s)
+    assert float((x0 - x).abs().max()) <= 2e-3      # eps was rounded to fp16
+    e2 = torch.randn(2 * 256, 8, device="cuda", generator=g).half()
+    out = L.latent_out(e2, x, nz, a, s)
+    ref = ((a * x + s * nz) - s * e2[:, :4].float().reshape(2, 16, 16, 4).permute(0, 3, 1, 2)) / a
+    assert rel_l2(out, ref) <= 1e-5

@@ -1,0 +1,32 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, bench, ncu launch list (+ optional full capture). Logs -> gpurun_out/.
+# usage: tools/gpu_round.sh <tag> [tests|bench|ncu|full ...]   (default: tests bench ncu)
+set -u
+TAG=${1:-r01}; shift || true
+WHAT=${*:-tests bench ncu}
+OUT=gpurun_out; mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > $OUT/${TAG}_smi.csv 2>&1
+for w in $WHAT; do
+case $w in
+tests)
+  timeout 1500 python -m pytest tests -m gpu -x -q -s > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest_gpu.log
+  tail -5 $OUT/${TAG}_pytest_gpu.log
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/${TAG}_smoke.log; tail -2 $OUT/${TAG}_smoke.log ;;
+bench)
+  nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > $OUT/${TAG}_clocks.csv 2>/dev/null &
+  SMI=$!
+  timeout 900 python bench.py --steps 20 --warmup 3 --trace-out $OUT/${TAG}_kernels.json > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
+  kill $SMI 2>/dev/null
+  cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
+  timeout 600 python bench.py --steps 10 --warmup 3 --batch 8 --no-cpu-baseline --trace-out $OUT/${TAG}_kernels_b8.json > $OUT/${TAG}_bench_b8.json 2> $OUT/${TAG}_bench_b8.err; echo "bench b8 rc=$?"
+  cat $OUT/${TAG}_bench_b8.json; tail -3 $OUT/${TAG}_bench_b8.err ;;
+ncu)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_launches.csv \
+     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
+  wc -l $OUT/${TAG}_launches.csv ;;
+full)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-shared_attn} -s ${NCU_SKIP:-20} -c ${NCU_COUNT:-3} \
+     -f -o $OUT/${TAG}_prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+  ls -la $OUT/${TAG}_prof* ;;
+esac
+done
