@@ -94,7 +94,7 @@ def unet_parameter_shapes(spec: UNetSpec) -> List[Tuple[str, Tuple[int, ...], st
     return out
 
 
-def synthetic_unet_state_dict(spec: UNetSpec | None = None, seed: int = 0, lora_rank: int = 0, qk_gain: float = 2.5,
+def synthetic_unet_state_dict(spec: UNetSpec | None = None, seed: int = 0, lora_rank: int = 0, qk_gain: float = 1.25,
                               lora_b_std: float = 0.02, dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
     spec = spec or UNetSpec()
     g = torch.Generator().manual_seed(seed)

@@ -89,6 +89,7 @@ class UNetEngine:
         self.consume_refs, self.capture_kv = consume_refs, capture_kv
         self.freeu = freeu
         self.captured: List[RefKV] = []
+        self.debug: Optional[dict] = None     # set to {} to record per-module outputs (tools/debug_engine.py)
         dev = self.dev
         boc = spec.block_out_channels
         cap = caption_enc.detach().to(torch.float32).cpu()
@@ -229,39 +230,56 @@ class UNetEngine:
         """x: fp16 channel-last latent [B*H*W, 64] (4 real channels). Returns the model output [B*H*W, 4] fp16."""
         self.captured = []
         shared_idx = 0
+        dbg = self.debug
         h = self._conv(x, self.conv_in, B, H, W)
+        if dbg is not None:
+            dbg["conv_in"] = h
         skips = [(h, H, W)]
-        for layers, ds in self.down:
-            for res, tr in layers:
+        for i, (layers, ds) in enumerate(self.down):
+            for j, (res, tr) in enumerate(layers):
                 h = self._resnet(h, res, B, H, W)
+                if dbg is not None:
+                    dbg[f"down_blocks.{i}.resnets.{j}"] = h
                 if tr is not None:
                     h = self._transformer(h, tr, B, H * W)
+                    if dbg is not None:
+                        dbg[f"down_blocks.{i}.attentions.{j}"] = h
                 skips.append((h, H, W))
             if ds is not None:
                 h = self._conv(h, ds, B, H, W)
                 H, W = H // 2, W // 2
+                if dbg is not None:
+                    dbg[f"down_blocks.{i}.downsamplers.0"] = h
                 skips.append((h, H, W))
         r0, tr, r1 = self.mid
         h = self._resnet(h, r0, B, H, W)
         h = self._transformer(h, tr, B, H * W)
         h = self._resnet(h, r1, B, H, W)
+        if dbg is not None:
+            dbg["mid_block"] = h
         for i, (layers, us) in enumerate(self.up):
             bscale, sscale = 1.0, 1.0
             if self.freeu is not None and i < 2:
                 s1, s2, b1, b2 = self.freeu
                 bscale, sscale = (b1, s1) if i == 0 else (b2, s2)
-            for res, tr in layers:
+            for j, (res, tr) in enumerate(layers):
                 skip, sh, sw = skips.pop()
                 assert (sh, sw) == (H, W)
                 cat = L.concat_freeu(h, skip, batch=B, h=H, w=W, backbone_scale=bscale, skip_scale=sscale)
                 h = self._resnet(cat, res, B, H, W)
+                if dbg is not None:
+                    dbg[f"up_blocks.{i}.resnets.{j}"] = h
                 if tr is not None:
                     ref = ref_kv[shared_idx] if (self.consume_refs and ref_kv is not None) else None
                     shared_idx += 1
                     h = self._transformer(h, tr, B, H * W, ref, capture=self.capture_kv)
+                    if dbg is not None:
+                        dbg[f"up_blocks.{i}.attentions.{j}"] = h
             if us is not None:
                 h = L.upsample_nearest2x(h, batch=B, h=H, w=W)
                 H, W = 2 * H, 2 * W
                 h = self._conv(h, us, B, H, W)
+                if dbg is not None:
+                    dbg[f"up_blocks.{i}.upsamplers.0"] = h
         t = self._gn(h, self.norm_out, B, H * W, self.spec.norm_eps, True)
         return self._conv(t, self.conv_out, B, H, W)

@@ -34,7 +34,7 @@ class ModelFlags:
     train_reference_networks: bool = False
 
 
-def seeded_init_(model: nn.Module, seed: int, qk_gain: float = 2.5) -> nn.Module:
+def seeded_init_(model: nn.Module, seed: int, qk_gain: float = 1.25) -> nn.Module:
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for name, p in model.named_parameters():
