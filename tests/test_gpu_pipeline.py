@@ -17,7 +17,7 @@ from conftest import rel_l2
 pytestmark = pytest.mark.gpu
 
 OP_TOL = 1e-3
-PIPE_TOL = 5e-3
+PIPE_TOL = 1e-3
 
 
 @pytest.fixture(scope="module", autouse=True)
