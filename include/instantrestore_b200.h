@@ -60,6 +60,9 @@ unsigned long long ir_launch_count(void);
  *    act: IR_ACT_GEGLU expects W rows interleaved in blocks of 64 (64 value rows, then their 64 gate rows)
  *    and writes c_out/2 columns; IR_ACT_SILU applies x*sigmoid(x).
  * out: fp16 [M, c_out or c_out/2] with row stride out_row_stride.
+ * Small-M layers (few output tiles, large K) are split along K across a thread-block cluster and reduced through
+ * distributed shared memory in rank order: results are deterministic (no atomics); the split factor depends on the
+ * launch shape only.
  */
 typedef struct {
   const void* a;
@@ -74,7 +77,8 @@ typedef struct {
   int act;
   void* out;
   int out_row_stride;
-  int tile_n; /* 0 = auto; else 64, 128, 160 or 256 */
+  int tile_n;  /* 0 = auto; else 64, 128, 160 or 256 */
+  int split_k; /* 0 = auto; 1 = off; 2, 4, 8 = K split over a thread-block cluster of that size (DSMEM reduce) */
 } ir_conv_gemm_params;
 int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
 

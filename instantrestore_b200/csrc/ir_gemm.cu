@@ -12,6 +12,13 @@
 // Two CTAs are resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's epilogue overlaps the
 // other's main loop.
 //
+// Split-K over a thread-block cluster (small-M layers: 8x8 / 16x16 resolution convs and the B=1 linears launch only
+// 10-80 output tiles on 148 SMs and are weight-bandwidth bound): gridDim.z = cluster size S in {2,4,8}; CTA z
+// accumulates K-blocks [z*kb, (z+1)*kb) in its own TMEM, then the S partial tiles are reduce-scattered through
+// distributed shared memory — CTA z pushes column slice j of its accumulator into CTA j's (now idle) pipeline
+// buffers with st.shared::cluster, and CTA j sums the S slices in rank order (deterministic) and runs the epilogue
+// for its BN/S columns. No global workspace, no atomics, no second kernel.
+//
 // Roofline: tensor-core bound for C_in*taps >= ~600 (AI = 2*128*BN*K / ((128+BN)*K*2 B)); algorithmic FLOPs per
 // launch = 2 * M * c_out * taps * c_in.
 #include "ir_host.h"
@@ -31,6 +38,7 @@ struct GemmKParams {
   int tiles_w, tiles_h;
   int bw, bh, bn;
   int8_t tap_map[9], tap_dx[9], tap_dy[9];
+  int split, kb_per_split;
   const float* bias;
   const __half* residual;
   int res_stride;
@@ -42,6 +50,57 @@ struct GemmKParams {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
+
+
+// Epilogue for NC (8, 16 or 32) consecutive output columns of one row: + bias, fp16 round, + residual, activation,
+// 16-byte stores. v[] holds the fp32 accumulators.
+template <int NC>
+__device__ __forceinline__ void epilogue_store(float (&v)[NC], const GemmKParams& p, long grow, int gcol) {
+  if (gcol >= p.N) return;
+  const bool full = (gcol + NC <= p.N);
+  if (p.bias) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (full || gcol + i < p.N) v[i] += __ldg(p.bias + gcol + i);
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) v[i] = round_h(v[i]);
+  if (p.residual) {
+    const __half* rp = p.residual + grow * p.res_stride + gcol;
+    if (full) {
+#pragma unroll
+      for (int q = 0; q < NC / 8; ++q) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __half22float2(h2[j]);
+          v[q * 8 + 2 * j] += f.x;
+          v[q * 8 + 2 * j + 1] += f.y;
+        }
+      }
+    } else {
+      for (int i = 0; i < NC; ++i)
+        if (gcol + i < p.N) v[i] += __half2float(rp[i]);
+    }
+  }
+  if (p.act == IR_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = silu(v[i]);
+  }
+  __half* op = p.out + grow * p.out_stride + gcol;
+  if (full) {
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) {
+      uint4 u = make_uint4(pack_half2(v[q * 8], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
+                           pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+      reinterpret_cast<uint4*>(op)[q] = u;
+    }
+  } else {
+    for (int i = 0; i < NC; ++i)
+      if (gcol + i < p.N) op[i] = __float2half_rn(v[i]);
+  }
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ GemmKParams p) {
@@ -85,14 +144,17 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
 
   const int mt = blockIdx.x;
   const int nt = blockIdx.y;
-  const int num_k = p.taps * p.kc_per_tap;
+  const int num_k_total = p.taps * p.kc_per_tap;
+  const int k_begin = blockIdx.z * p.kb_per_split;                    // split-K: this CTA's K-block range
+  const int k_end = min(k_begin + p.kb_per_split, num_k_total);
+  const int num_k = k_end - k_begin;
 
   if (warp == 0) {
     if (lane == 0) {
       const int w0 = (mt % p.tiles_w) * p.bw;
       const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
       const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
-      int tap = 0, kc = 0;
+      int tap = k_begin / p.kc_per_tap, kc = k_begin % p.kc_per_tap;
       for (int ks = 0; ks < num_k; ++ks) {
         const int s = ks % STAGES;
         const uint32_t ph = (ks / STAGES) & 1;
@@ -100,7 +162,7 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
         mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
         tma_load_4d(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], &full_bar[s], kc * kBK, w0 + p.tap_dx[tap],
                     h0 + p.tap_dy[tap], n0);
-        tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], ks * kBK, nt * BN);
+        tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], (k_begin + ks) * kBK, nt * BN);
         if (++kc == p.kc_per_tap) {
           kc = 0;
           ++tap;
@@ -174,60 +236,56 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
         }
       }
     }
+  } else if (p.split > 1) {
+    // ---- split-K: reduce-scatter the S partial tiles through distributed shared memory
+    const int S = p.split;
+    const int W = BN / S;                       // columns owned by each CTA of the cluster (multiple of 8)
+    const uint32_t my_rank = cluster_ctarank();
+    cluster_sync_all();                          // every CTA of the cluster has drained its pipeline buffers
+    const uint32_t recv_local = smem_u32(smem);  // [src][W/4][128 rows] float4, reuses the stage buffers
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int col = c0 + q * 4;
+        const uint32_t owner = static_cast<uint32_t>(col / W);
+        const int c4 = (col - owner * W) >> 2;
+        const uint32_t off = ((my_rank * (W >> 2) + c4) * 128 + row) * 16;
+        dsmem_st_f4(dsmem_addr(recv_local + off, owner), __uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                    __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+      }
+    }
+    cluster_sync_all();                          // all partial slices have landed in their owner's shared memory
+    const float4* recv = reinterpret_cast<const float4*>(smem);
+    if (row_ok) {
+#pragma unroll 1
+      for (int c8 = 0; c8 < W; c8 += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int src = 0; src < S; ++src) {       // fixed order: deterministic sum
+          const float4 a = recv[(src * (W >> 2) + (c8 >> 2)) * 128 + row];
+          const float4 b = recv[(src * (W >> 2) + (c8 >> 2) + 1) * 128 + row];
+          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+          v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        epilogue_store<8>(v, p, grow, nt * BN + static_cast<int>(my_rank) * W + c8);
+      }
+    }
   } else {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(taddr + c0, r);
       tmem_ld_wait();
-      const int gcol = nt * BN + c0;
-      if (row_ok && gcol < p.N) {
-        const bool full = (gcol + 32 <= p.N);
+      if (row_ok) {
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (full || gcol + i < p.N) v[i] += __ldg(p.bias + gcol + i);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = round_h(v[i]);
-        if (p.residual) {
-          const __half* rp = p.residual + grow * p.res_stride + gcol;
-          if (full) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
-              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(h2[j]);
-                v[q * 8 + 2 * j] += f.x;
-                v[q * 8 + 2 * j + 1] += f.y;
-              }
-            }
-          } else {
-            for (int i = 0; i < 32; ++i)
-              if (gcol + i < p.N) v[i] += __half2float(rp[i]);
-          }
-        }
-        if (p.act == IR_ACT_SILU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = silu(v[i]);
-        }
-        __half* op = p.out + grow * p.out_stride + gcol;
-        if (full) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 u = make_uint4(pack_half2(v[q * 8], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
-                                 pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
-            reinterpret_cast<uint4*>(op)[q] = u;
-          }
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (gcol + i < p.N) op[i] = __float2half_rn(v[i]);
-        }
+        epilogue_store<32>(v, p, grow, nt * BN + c0);
       }
     }
   }
@@ -246,8 +304,26 @@ static int launch(const GemmKParams& kp, int m_tiles, cudaStream_t stream) {
     if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm<%d>): %s", BN, cudaGetErrorString(e));
     attr_done = true;
   }
-  dim3 grid(m_tiles, (kp.N + BN - 1) / BN);
-  conv_gemm_kernel<BN, STAGES><<<grid, 128, smem, stream>>>(kp);
+  dim3 grid(m_tiles, (kp.N + BN - 1) / BN, kp.split);
+  if (kp.split == 1) {
+    conv_gemm_kernel<BN, STAGES><<<grid, 128, smem, stream>>>(kp);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = kp.split;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, STAGES>, kp);
+    if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "conv_gemm cluster launch (split %d): %s", kp.split, cudaGetErrorString(e));
+  }
   IR_CUDA_LAUNCH_CHECK("conv_gemm launch");
   return 0;
 }
@@ -362,6 +438,33 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
   }
   if (geglu && bn_tile % 128 != 0) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: GEGLU needs tile_n 128 or 256");
   (void)pow2_floor;
+
+  // split-K over a cluster when the output tiles alone cannot fill the 148 SMs (see the header comment)
+  const int num_k = taps * kp.kc_per_tap;
+  int split = 1;
+  if (p->split_k < 0 || p->split_k > 8 || (p->split_k & (p->split_k - 1)))
+    return set_error(IR_ERR_ARG, "ir_conv_gemm: split_k=%d (0 = auto, 1, 2, 4 or 8)", p->split_k);
+  const bool can_split = !geglu && p->c_out % 64 == 0 && p->c_out % 8 == 0;
+  if (p->split_k > 1) {
+    if (!can_split) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: split_k needs c_out %% 64 == 0 and no GEGLU");
+    split = p->split_k;
+  }
+  if (can_split && (p->split_k == 0 || p->split_k > 1) && p->tile_n == 0) {
+    // narrower N tile first when even 8-way split of 128-wide tiles leaves most SMs idle
+    if (static_cast<long>(m_tiles) * ((p->c_out + bn_tile - 1) / bn_tile) * 8 < 148 && bn_tile > 64) bn_tile = 64;
+  }
+  if (can_split && p->split_k == 0 && p->c_out % bn_tile == 0 && (bn_tile == 64 || bn_tile == 128)) {
+    const long tiles = static_cast<long>(m_tiles) * (p->c_out / bn_tile);
+    while (split < 8 && tiles * split < 148 && tiles * split * 2 <= 296 && num_k / (split * 2) >= 4) split *= 2;
+  }
+  if (split > 1 && (p->c_out % bn_tile != 0 || (bn_tile / split) % 8 != 0 || num_k < split))
+    return set_error(IR_ERR_SHAPE, "ir_conv_gemm: split_k=%d incompatible with tile_n=%d, c_out=%d, k-blocks=%d", split, bn_tile, p->c_out, num_k);
+  kp.split = split;
+  kp.kb_per_split = (num_k + split - 1) / split;
+  if (split > 1 && kp.kb_per_split * (split - 1) >= num_k) {   // every CTA of the cluster must own >= 1 K-block
+    kp.split = split = 1;
+    kp.kb_per_split = num_k;
+  }
 
   {
     uint64_t dims[2] = {static_cast<uint64_t>(taps) * p->c_in, static_cast<uint64_t>(p->c_out)};

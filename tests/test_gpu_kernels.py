@@ -81,6 +81,42 @@ def test_conv3x3(L, B, H, W, Ci, Co, stride, tile_n):
     assert rel_l2(out, ref) <= TOL
 
 
+@pytest.mark.parametrize("M,K,N,split,tile_n", [
+    (256, 1280, 1280, 4, 0), (256, 1280, 1280, 8, 0), (64, 1280, 1280, 8, 64), (1024, 640, 640, 2, 0),
+    (256, 5120, 1280, 8, 128), (77, 1024, 320, 4, 64), (256, 1280, 1280, 0, 0), (64, 1280, 320, 0, 0),
+])
+def test_linear_split_k_cluster(L, M, K, N, split, tile_n):
+    """Split-K across a thread-block cluster with the DSMEM reduce-scatter; split=0 exercises the auto heuristic."""
+    g = _gen(21)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, N, device="cuda", generator=g).half()
+    out = L.conv_gemm(a, w, batch=1, h_in=1, w_in=M, c_in=K, bias=bias, residual=r, tile_n=tile_n, split_k=split)
+    ref = (a.float() @ w.float().T + bias).half().float() + r.float()
+    assert rel_l2(out, ref) <= TOL
+    again = L.conv_gemm(a, w, batch=1, h_in=1, w_in=M, c_in=K, bias=bias, residual=r, tile_n=tile_n, split_k=split)
+    assert torch.equal(out, again)                  # deterministic: fixed-order reduction, no atomics
+    unsplit = L.conv_gemm(a, w, batch=1, h_in=1, w_in=M, c_in=K, bias=bias, residual=r, tile_n=tile_n, split_k=1)
+    assert rel_l2(out, unsplit) <= 5e-4
+
+
+@pytest.mark.parametrize("B,H,Ci,Co,stride,split", [
+    (1, 8, 1280, 1280, 1, 8), (1, 16, 1280, 1280, 1, 8), (1, 8, 2560, 1280, 1, 0), (4, 8, 1280, 1280, 1, 0),
+    (1, 16, 1280, 1280, 2, 4), (1, 32, 640, 640, 1, 2), (2, 4, 128, 64, 1, 2), (1, 32, 1280, 640, 1, 0),
+])
+def test_conv3x3_split_k_cluster(L, B, H, Ci, Co, stride, split):
+    g = _gen(22)
+    x = torch.randn(B, Ci, H, H, device="cuda", generator=g).half()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Ci)).half()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    ref = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
+    a = x.permute(0, 2, 3, 1).contiguous().reshape(-1, Ci)
+    wk = w.permute(0, 2, 3, 1).contiguous().reshape(Co, 9 * Ci)
+    out = L.conv_gemm(a, wk, batch=B, h_in=H, w_in=H, c_in=Ci, ksize=3, stride=stride, bias=bias, split_k=split)
+    assert rel_l2(out, ref) <= TOL
+
+
 def test_conv_rejects_bad_shapes(L):
     a = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
     w = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
