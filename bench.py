@@ -321,6 +321,10 @@ def trace_roofline(eng, dev_in, a, ms_step):
     eng.use_cuda_graph = False
     try:
         eng.forward_latents(*dev_in)           # eager warm-up
+        torch.cuda.synchronize()
+        # head start: a spin kernel keeps the GPU busy while the CPU enqueues the ~850 launches of the step, so every
+        # event pair brackets back-to-back device execution and not the CPU's launch latency
+        torch.cuda._sleep(int(0.06 * 1.9e9))
         with L.Trace() as tr:
             eng.forward_latents(*dev_in)
         rows = tr.summary()

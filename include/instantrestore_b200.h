@@ -124,12 +124,13 @@ typedef struct {
 int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * ir_groupnorm — GroupNorm(+optional SiLU) on channel-last fp16, statistics in fp32 (two passes, centred).
+ * ir_groupnorm — GroupNorm(+optional SiLU) on channel-last fp16, statistics in fp32 (slab-parallel partial moments
+ * merged with Chan's formula, then one affine(+SiLU) pass).
  * Replaces diffusers ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm and
  * unet.py:1167-1169 (conv_norm_out + conv_act).
  * x: fp16 [batch, hw, channels] (row stride x_row_stride); gamma/beta fp32 [channels];
  * out fp16 [batch, hw, channels]; workspace: ir_groupnorm_workspace_bytes(batch, groups) bytes of device memory
- * (per-(batch, group) mean / rstd), caller-owned.
+ * (per-(batch, slab, group) partial moments), caller-owned.
  */
 typedef struct {
   const void* x;
@@ -167,7 +168,7 @@ int ir_layernorm(const ir_layernorm_params* p, ir_stream_t stream);
  *   (std unbiased, +1e-5 added to the std as in the reference).
  * v_own: fp16 [batch, s_own, *] columns v_col_off .. +channels; v_ref: fp16 [batch, n_ref, s_ref, *].
  * scale/shift: fp32 [batch, n_ref, channels].
- * workspace: ir_adain_workspace_bytes(batch, n_ref, channels) bytes (per-chunk mean / std), caller-owned.
+ * workspace: ir_adain_workspace_bytes(batch, n_ref, channels) bytes (per-slab partial moments), caller-owned.
  */
 typedef struct {
   const void* v_own;

@@ -249,7 +249,8 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch
     if out is None:
         out = torch.empty((batch * hw, channels), dtype=torch.float16, device=x.device)
     if workspace is None:
-        workspace = torch.empty(batch * groups * 2, dtype=torch.float32, device=x.device)
+        workspace = torch.empty(load().ir_groupnorm_workspace_bytes(batch, groups) // 4, dtype=torch.float32,
+                                device=x.device)
     p = GroupNormParams(x=ptr(x), x_row_stride=x.stride(-2), batch=batch, hw=hw, channels=channels, groups=groups,
                         eps=eps, gamma=ptr(gamma), beta=ptr(beta), silu=int(silu), out=ptr(out),
                         out_row_stride=out.stride(-2), workspace=ptr(workspace))
@@ -282,7 +283,8 @@ def adain_coeffs(v_own: torch.Tensor, v_ref: torch.Tensor, *, batch: int, s_own:
     if shift is None:
         shift = torch.empty((batch, n_ref, channels), dtype=torch.float32, device=dev)
     if workspace is None:
-        workspace = torch.empty(batch * (1 + n_ref) * channels * 2, dtype=torch.float32, device=dev)
+        workspace = torch.empty(load().ir_adain_workspace_bytes(batch, n_ref, channels) // 4, dtype=torch.float32,
+                                device=dev)
     p = AdainCoeffsParams(v_own=ptr(v_own), own_row_stride=v_own.stride(-2), v_col_off=v_col_off, s_own=s_own,
                           v_ref=ptr(v_ref), ref_row_stride=v_ref.stride(-2), ref_col_off=ref_col_off, n_ref=n_ref,
                           s_ref=s_ref, batch=batch, channels=channels, eps=eps, scale=ptr(scale), shift=ptr(shift),

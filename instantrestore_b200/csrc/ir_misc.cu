@@ -6,17 +6,18 @@
 namespace ir {
 
 // ------------------------------------------------------------------------------------------------ AdaIN
-// Column statistics (over tokens) of a token-major fp16 matrix slab: 64 channels per CTA, two passes
-// (mean, then centred sum of squares; unbiased). grid = (channels/64, 1 + n_ref, batch), block = 256.
-// ws[((b * (1 + n_ref) + chunk) * channels + c) * 2 + {0,1}] = {mean, std_unbiased}
+// Column statistics (over tokens) of token-major fp16 matrices. grid = (channels/64, slabs, (1 + n_ref) * batch),
+// block = 256 = 32 row lanes x 8 sixteen-byte vectors: a CTA reads a [rows_per_slab x 64-channel] slab with coalesced
+// 128-byte rows, 4 loads in flight per thread, and writes per-channel partial (mean, M2) moments:
+//   ws[(((b * (1 + n_ref) + chunk) * slabs + slab) * channels + c)] = (mean, M2)
 __global__ void __launch_bounds__(256) colstats_kernel(const __half* __restrict__ v_own, int own_stride, int own_col_off,
                                                        int s_own, const __half* __restrict__ v_ref, int ref_stride,
-                                                       int ref_col_off, int n_ref, int s_ref, int channels,
-                                                       float* __restrict__ ws) {
-  __shared__ float red[8][64];
-  __shared__ float mean_s[64];
-  const int cb = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                                       int ref_col_off, int n_ref, int s_ref, int channels, int slabs,
+                                                       float2* __restrict__ ws) {
+  __shared__ float red[2][32][64 + 1];
+  const int cb = blockIdx.x, slab = blockIdx.y;
+  const int chunk = blockIdx.z % (1 + n_ref), b = blockIdx.z / (1 + n_ref);
+  const int vec = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const __half* base;
   int stride, rows;
   if (chunk == 0) {
@@ -28,57 +29,91 @@ __global__ void __launch_bounds__(256) colstats_kernel(const __half* __restrict_
     stride = ref_stride;
     rows = s_ref;
   }
-  // pass 1: mean
-  float sx = 0.f, sy = 0.f;
-  for (int r = warp; r < rows; r += 8) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(base + static_cast<size_t>(r) * stride + 2 * lane));
-    sx += f.x;
-    sy += f.y;
+  const int rps = (rows + slabs - 1) / slabs;
+  const int r0 = slab * rps, r1 = min(r0 + rps, rows);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  int r = r0 + rl;
+  for (; r + 96 < r1; r += 128) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(r + 32 * k) * stride + (vec << 3));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        s[2 * j] += f.x; q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+        s[2 * j + 1] += f.y; q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+      }
+    }
   }
-  red[warp][2 * lane] = sx;
-  red[warp][2 * lane + 1] = sy;
+  for (; r < r1; r += 32) {
+    const uint4 u = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(r) * stride + (vec << 3));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      s[2 * j] += f.x; q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+      s[2 * j + 1] += f.y; q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][rl][vec * 8 + j] = s[j];
+    red[1][rl][vec * 8 + j] = q[j];
+  }
   __syncthreads();
   if (threadIdx.x < 64) {
-    float t = 0.f;
+    float ts = 0.f, tq = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-    mean_s[threadIdx.x] = t / rows;
-  }
-  __syncthreads();
-  const float mx = mean_s[2 * lane], my = mean_s[2 * lane + 1];
-  float qx = 0.f, qy = 0.f;
-  for (int r = warp; r < rows; r += 8) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(base + static_cast<size_t>(r) * stride + 2 * lane));
-    qx += (f.x - mx) * (f.x - mx);
-    qy += (f.y - my) * (f.y - my);
-  }
-  __syncthreads();
-  red[warp][2 * lane] = qx;
-  red[warp][2 * lane + 1] = qy;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-    const float var = rows > 1 ? t / (rows - 1) : 0.f;
-    const size_t o = ((static_cast<size_t>(b) * (1 + n_ref) + chunk) * channels + cb * 64 + threadIdx.x) * 2;
-    ws[o] = mean_s[threadIdx.x];
-    ws[o + 1] = sqrtf(var);
+    for (int w = 0; w < 32; ++w) {
+      ts += red[0][w][threadIdx.x];
+      tq += red[1][w][threadIdx.x];
+    }
+    const float n = static_cast<float>(r1 - r0);
+    const float mean = n > 0.f ? ts / n : 0.f;
+    ws[((static_cast<size_t>(blockIdx.z) * slabs + slab) * channels) + cb * 64 + threadIdx.x] =
+        make_float2(mean, fmaxf(tq - ts * mean, 0.f));
   }
 }
 
-__global__ void adain_finalize_kernel(const float* __restrict__ ws, int n_ref, int channels, float eps,
-                                      float* __restrict__ scale, float* __restrict__ shift, int total) {
+// merges the slab moments of channel c of chunk `chunk_idx` (Chan), returns mean and the UNBIASED std
+__device__ __forceinline__ void colstats_merge(const float2* __restrict__ ws, size_t chunk_idx, int slabs, int channels,
+                                               int c, int rows, float* mean_out, float* std_out) {
+  const int rps = (rows + slabs - 1) / slabs;
+  float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
+  for (int sl = 0; sl < slabs; ++sl) {
+    const float n_b = static_cast<float>(min(rps, rows - sl * rps));
+    if (n_b <= 0.f) break;
+    const float2 pm = ws[(chunk_idx * slabs + sl) * channels + c];
+    if (n_a == 0.f) {
+      n_a = n_b; mean_a = pm.x; m2_a = pm.y;
+    } else {
+      const float n = n_a + n_b, d = pm.x - mean_a, f = n_b / n;
+      mean_a = fmaf(d, f, mean_a);
+      m2_a = m2_a + pm.y + d * d * n_a * f;
+      n_a = n;
+    }
+  }
+  *mean_out = mean_a;
+  *std_out = rows > 1 ? sqrtf(m2_a / (rows - 1)) : 0.f;
+}
+
+__global__ void adain_finalize_kernel(const float2* __restrict__ ws, int n_ref, int channels, int slabs, int s_own,
+                                      int s_ref, float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                      int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = i % channels;
   const int r = (i / channels) % n_ref;
   const int b = i / (channels * n_ref);
-  const size_t so = ((static_cast<size_t>(b) * (1 + n_ref)) * channels + c) * 2;
-  const size_t ro = ((static_cast<size_t>(b) * (1 + n_ref) + 1 + r) * channels + c) * 2;
-  const float style_mean = ws[so], style_std = ws[so + 1] + eps;
-  const float cm = ws[ro], cs = ws[ro + 1] + eps;
-  const float a = style_std / cs;
+  float style_mean, style_std, cm, cs;
+  colstats_merge(ws, static_cast<size_t>(b) * (1 + n_ref), slabs, channels, c, s_own, &style_mean, &style_std);
+  colstats_merge(ws, static_cast<size_t>(b) * (1 + n_ref) + 1 + r, slabs, channels, c, s_ref, &cm, &cs);
+  const float a = (style_std + eps) / (cs + eps);
   scale[i] = a;
   shift[i] = style_mean - cm * a;
 }
@@ -233,8 +268,18 @@ static inline int grid_for(long total, int block, int cap = 148 * 16) {
 
 }  // namespace ir
 
+static int adain_slabs(int batch, int n_ref, int channels, int rows) {
+  const long base = static_cast<long>(channels / 64) * (1 + n_ref) * batch;
+  long want = (592 + base - 1) / base;               // ~4 CTAs per SM in total
+  const long max_slabs = rows / 32 > 0 ? rows / 32 : 1;
+  if (want > max_slabs) want = max_slabs;
+  if (want > 32) want = 32;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+
 extern "C" size_t ir_adain_workspace_bytes(int batch, int n_ref, int channels) {
-  return static_cast<size_t>(batch) * (1 + n_ref) * channels * 2 * sizeof(float);
+  return static_cast<size_t>(batch) * (1 + n_ref) * 32 * channels * sizeof(float2);   // up to 32 slabs per chunk
 }
 
 extern "C" int ir_adain_coeffs(const ir_adain_coeffs_params* p, ir_stream_t stream_) {
@@ -243,17 +288,20 @@ extern "C" int ir_adain_coeffs(const ir_adain_coeffs_params* p, ir_stream_t stre
   if (int rc = check_arch()) return rc;
   if (p->channels % 64 != 0 || p->n_ref <= 0 || p->batch <= 0 || p->s_own <= 0 || p->s_ref <= 0)
     return set_error(IR_ERR_SHAPE, "ir_adain_coeffs: channels=%d n_ref=%d", p->channels, p->n_ref);
-  if ((p->own_row_stride | p->ref_row_stride | p->v_col_off | p->ref_col_off) & 1)
-    return set_error(IR_ERR_ALIGN, "ir_adain_coeffs: strides/offsets must be even");
+  if ((p->own_row_stride | p->ref_row_stride | p->v_col_off | p->ref_col_off) & 7)
+    return set_error(IR_ERR_ALIGN, "ir_adain_coeffs: strides/offsets must be multiples of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(p->v_own) | reinterpret_cast<uintptr_t>(p->v_ref)) & 15)
+    return set_error(IR_ERR_ALIGN, "ir_adain_coeffs: pointers must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  dim3 grid(p->channels / 64, 1 + p->n_ref, p->batch);
+  const int slabs = adain_slabs(p->batch, p->n_ref, p->channels, p->s_own < p->s_ref ? p->s_own : p->s_ref);
+  dim3 grid(p->channels / 64, slabs, (1 + p->n_ref) * p->batch);
   colstats_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(p->v_own), p->own_row_stride, p->v_col_off, p->s_own,
                                             static_cast<const __half*>(p->v_ref), p->ref_row_stride, p->ref_col_off, p->n_ref,
-                                            p->s_ref, p->channels, static_cast<float*>(p->workspace));
+                                            p->s_ref, p->channels, slabs, static_cast<float2*>(p->workspace));
   IR_CUDA_LAUNCH_CHECK("colstats launch");
   const int total = p->batch * p->n_ref * p->channels;
-  adain_finalize_kernel<<<(total + 255) / 256, 256, 0, stream>>>(static_cast<const float*>(p->workspace), p->n_ref, p->channels,
-                                                                 p->eps, p->scale, p->shift, total);
+  adain_finalize_kernel<<<(total + 127) / 128, 128, 0, stream>>>(static_cast<const float2*>(p->workspace), p->n_ref, p->channels,
+                                                                 slabs, p->s_own, p->s_ref, p->eps, p->scale, p->shift, total);
   IR_CUDA_LAUNCH_CHECK("adain_finalize launch");
   return 0;
 }
