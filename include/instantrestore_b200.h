@@ -100,6 +100,8 @@ int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
  * out:    fp16 [batch, s_q, heads*64] (row stride out_row_stride).
  * chunk_mass: optional fp32 [batch, heads, n_chunks] — attention probability mass per KV chunk averaged over
  *         queries (what gradio_demo.py:118-133 derives from the dense matrix). NULL to skip.
+ * When batch * heads * ceil(s_q / 256) cannot fill the 148 SMs (a single identity), the KV sequence is split into
+ * ranges handled by separate CTAs; partial (O, max, sum) land in `workspace` and are merged in split order.
  */
 typedef struct {
   const void* q;
@@ -120,7 +122,12 @@ typedef struct {
   void* out;
   int out_row_stride;
   float* chunk_mass;
+  int kv_splits;          /* 0 = auto; 1 = off; 2..16 = KV ranges processed by separate CTAs and merged (needs workspace) */
+  void* workspace;        /* device scratch for split-KV partials (may be NULL: splitting is then disabled) */
+  size_t workspace_bytes;
 } ir_shared_attn_params;
+/* Upper bound of the split-KV scratch for (batch, heads, s_q); 0 when the shape never splits. */
+size_t ir_shared_attn_workspace_bytes(int batch, int heads, int s_q);
 int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

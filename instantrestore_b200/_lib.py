@@ -17,6 +17,7 @@ IR_ACT_NONE, IR_ACT_GEGLU, IR_ACT_SILU = 0, 1, 2
 
 EXPORTED_SYMBOLS = [
     "ir_last_error_string", "ir_version", "ir_check_device", "ir_launch_count", "ir_conv_gemm", "ir_shared_attn_fwd",
+    "ir_shared_attn_workspace_bytes",
     "ir_groupnorm", "ir_groupnorm_workspace_bytes", "ir_layernorm", "ir_adain_coeffs", "ir_adain_workspace_bytes",
     "ir_concat_freeu", "ir_upsample_nearest2x", "ir_latent_in", "ir_latent_out",
 ]
@@ -43,6 +44,7 @@ class SharedAttnParams(C.Structure):
         ("adain_scale", C.c_void_p), ("adain_shift", C.c_void_p),
         ("batch", C.c_int), ("heads", C.c_int), ("s_q", C.c_int), ("scale", C.c_float),
         ("out", C.c_void_p), ("out_row_stride", C.c_int), ("chunk_mass", C.c_void_p),
+        ("kv_splits", C.c_int), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -96,6 +98,7 @@ def load() -> C.CDLL:
     lib.ir_launch_count.restype = C.c_ulonglong
     lib.ir_groupnorm_workspace_bytes.restype = C.c_size_t
     lib.ir_adain_workspace_bytes.restype = C.c_size_t
+    lib.ir_shared_attn_workspace_bytes.restype = C.c_size_t
     lib.ir_conv_gemm.argtypes = [C.POINTER(ConvGemmParams), C.c_void_p]
     lib.ir_shared_attn_fwd.argtypes = [C.POINTER(SharedAttnParams), C.c_void_p]
     lib.ir_groupnorm.argtypes = [C.POINTER(GroupNormParams), C.c_void_p]
@@ -185,6 +188,18 @@ def _f(t: torch.Tensor | None, name: str) -> torch.Tensor | None:
     return t
 
 
+_scratch_bufs: dict = {}
+
+
+def _scratch(device, nbytes: int) -> torch.Tensor:
+    """Per-device scratch for split-KV partials. Kernels of one stream run in order, so one buffer serves every
+    layer; it only grows, and superseded buffers stay alive because captured CUDA graphs hold their addresses."""
+    bufs = _scratch_bufs.setdefault(str(device), [])
+    if not bufs or bufs[-1].numel() < nbytes:
+        bufs.append(torch.empty(nbytes, dtype=torch.uint8, device=device))
+    return bufs[-1]
+
+
 # ------------------------------------------------------------------------------------------------- wrappers
 def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: int, c_in: int, ksize: int = 1,
               stride: int = 1, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
@@ -216,7 +231,7 @@ def shared_attn(q: torch.Tensor, *, heads: int, scale: float, batch: int, s_q: i
                 own_shared: bool = False, q_col_off: int = 0, k_own_col_off: int = 0, v_own_col_off: int = 0,
                 k_ref: torch.Tensor | None = None, v_ref: torch.Tensor | None = None, n_ref: int = 0, s_ref: int = 0,
                 ref_col_off: int = 0, adain_scale: torch.Tensor | None = None, adain_shift: torch.Tensor | None = None,
-                out: torch.Tensor | None = None) -> torch.Tensor:
+                out: torch.Tensor | None = None, kv_splits: int = 0) -> torch.Tensor:
     """q: fp16 [batch*s_q, row]; k_own/v_own: fp16 [(batch|1)*s_own, row]; k_ref/v_ref: fp16 [batch*n_ref*s_ref, row]."""
     _h(q, "q")
     if out is None:
@@ -228,7 +243,12 @@ def shared_attn(q: torch.Tensor, *, heads: int, scale: float, batch: int, s_q: i
         k_ref=ptr(k_ref), v_ref=ptr(v_ref), ref_row_stride=k_ref.stride(-2) if k_ref is not None else 0,
         ref_col_off=ref_col_off, n_ref=n_ref, s_ref=s_ref,
         adain_scale=ptr(_f(adain_scale, "adain_scale")), adain_shift=ptr(_f(adain_shift, "adain_shift")),
-        batch=batch, heads=heads, s_q=s_q, scale=scale, out=ptr(out), out_row_stride=out.stride(-2), chunk_mass=None)
+        batch=batch, heads=heads, s_q=s_q, scale=scale, out=ptr(out), out_row_stride=out.stride(-2), chunk_mass=None,
+        kv_splits=kv_splits)
+    ws_bytes = load().ir_shared_attn_workspace_bytes(batch, heads, s_q) if kv_splits != 1 else 0
+    if ws_bytes:
+        ws = _scratch(q.device, ws_bytes)
+        p.workspace, p.workspace_bytes = ptr(ws), ws.numel()
     if k_own is not None:
         _h(k_own, "k_own"); _h(v_own, "v_own")
         assert k_own.stride(-2) == v_own.stride(-2)

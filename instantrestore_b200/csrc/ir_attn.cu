@@ -1,30 +1,39 @@
 // ir_shared_attn_fwd — fused shared-image attention for sm_100a (head_dim 64).
 //
-// CTA = one 128-query tile of one (batch, head). KV is streamed in 128-key tiles, chunk by chunk
-// ([own tokens] ++ reference 0 ++ reference 1 ...), never concatenated in memory:
-//   warp 4 (one lane): TMA producer — Q once, then K/V tiles straight out of the token-major projection outputs
-//       (the head split is just the TMA column coordinate), 128B-swizzled, multi-stage ring.
-//   warp 5 (one lane): tcgen05.mma issuer — S_j = Q K_j^T into one of two TMEM score buffers, then
-//       O_{j-1} = P_{j-1} V_{j-1} (P from shared memory, V consumed MN-major so no transpose is needed);
-//       QK of tile j+1 overlaps the softmax of tile j.
-//   warps 0-3: online softmax, thread == query row: tcgen05.ld the scores, running max/sum in the exp2 domain,
-//       P written to shared memory in the UMMA K-major swizzled layout, per-tile O read back from TMEM and
-//       accumulated in registers with the AdaIN affine of the tile's reference:
-//           sum_r P_r (a_r*V_r + b_r) = a_r*(P_r V_r) + b_r*rowsum(P_r).
+// A CTA owns TWO 128-query tiles of one (batch, head) and streams KV in 128-key tiles, chunk by chunk
+// ([own tokens] ++ reference 0 ++ reference 1 ...), never concatenated in memory. 10 warps:
+//   warps 0-3 / 4-7: softmax warpgroup of query tile 0 / 1, thread == query row. One tcgen05.ld pass brings the 128
+//       scores of the row into registers (which frees the TMEM score buffer for the next QK^T at once), row max,
+//       exp2, fp16 P into shared memory in the UMMA K-major swizzled layout. The two warpgroups run out of phase, so
+//       the MUFU pipe (the bound at d=64: 16 exp/clk/SM vs 8192 MMA FLOP/clk/SM) always has work while the tensor
+//       pipe runs the other tile's QK^T / PV.
+//   warp 8 (one lane): TMA producer — both Q tiles once, then K/V tiles straight out of the token-major projection
+//       outputs (the head split is just the TMA column coordinate), 128B-swizzled, 3-stage ring.
+//   warp 9 (one lane): tcgen05.mma issuer — S_i = Q_i K_j^T (TMEM, 128 columns per tile), O_i += P_i V_j (V consumed
+//       MN-major, no transpose). O accumulates IN TMEM across the KV tiles of a segment; the running max is only
+//       raised when it grows by more than 2^8 (lazy rescale, done in TMEM by the softmax warps), so the common tile
+//       costs no accumulator traffic at all.
+// AdaIN: sum_r P_r (a_r*V_r + b_r) = a_r*(P_r V_r) + b_r*rowsum(P_r) — a segment is one reference chunk; at its end
+//   the segment accumulator is folded with the chunk's affine into a second TMEM accumulator.
+// Split-KV (few (batch, head, query) units, e.g. one identity): gridDim.x also enumerates KV ranges; CTAs write
+//   un-normalised partials (O, m, l) and a small combine kernel merges them in a fixed order.
 //
-// Roofline: tensor-core bound (AI ~ 3300 FLOP/B at S=4096, N=4); algorithmic FLOPs per launch =
-// 4 * batch * heads * s_q * s_kv_total * 64.  At d=64 the MUFU exp rate caps tensor utilisation near 50%.
+// Roofline: tensor-core bound by FLOPs (AI ~ 3300 FLOP/B at S=4096, N=4) but capped by the exp rate: 2 x 128 x 128
+// exps per KV step = 2048 MUFU cycles vs 1024 MMA cycles, i.e. <= 50 % of the tcgen05 peak without exp emulation.
+// Algorithmic FLOPs per launch = 4 * batch * heads * s_q * s_kv_total * 64.
 #include "ir_host.h"
 #include "ir_ptx.cuh"
 
 namespace ir {
 
-constexpr int kQT = 128;       // query rows per CTA
-constexpr int kKT = 128;       // keys per tile
-constexpr int kD = 64;         // head dim
-constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB: Q, K or V tile
+constexpr int kQT = 128;                  // query rows per tile (two tiles per CTA)
+constexpr int kKT = 128;                  // keys per tile
+constexpr int kD = 64;                    // head dim
+constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB: a Q, K or V tile, or one 64-key half of a P tile
 constexpr int kKVStages = 3;
 constexpr int kMaxRef = 16;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8, exact in fp16 / fp32 accumulation
+constexpr int kAttnThreads = 320;
 
 struct AttnKParams {
   CUtensorMap tma_q, tma_k_own, tma_v_own, tma_k_ref, tma_v_ref;
@@ -37,20 +46,71 @@ struct AttnKParams {
   const float* adain_shift;
   __half* out;
   int out_stride;
-  float* chunk_mass;
-  int n_chunks;
+  int own_tiles, ref_tiles, total_tiles;
+  int n_splits, tiles_per_split;
+  float* part_o;      // [batch, heads, q tiles, n_splits, 128, 64] fp32 un-normalised partial outputs
+  float2* part_ml;    // [batch, heads, q tiles, n_splits, 128] (running max in log2 units, row sum)
 };
 
 // shared-memory carve-up (bytes, from the 1024-aligned base)
-constexpr int kOffQ = 0;
-constexpr int kOffK = kOffQ + kTileBytes;
+constexpr int kOffQ = 0;                                    // 2 tiles
+constexpr int kOffK = kOffQ + 2 * kTileBytes;
 constexpr int kOffV = kOffK + kKVStages * kTileBytes;
-constexpr int kOffP = kOffV + kKVStages * kTileBytes;       // 2 buffers x 32 KB
+constexpr int kOffP = kOffV + kKVStages * kTileBytes;       // 2 query tiles x 32 KB
 constexpr int kOffAdain = kOffP + 2 * 2 * kTileBytes;       // [kMaxRef][2][64] fp32
 constexpr int kOffBar = kOffAdain + kMaxRef * 2 * 64 * 4;
 constexpr int kAttnSmem = kOffBar + 256 + 1024;
 
-__global__ void __launch_bounds__(192, 1) shared_attn_kernel(const __grid_constant__ AttnKParams p) {
+// TMEM columns: S0 | S1 | O0 | O1 | ACC0 | ACC1
+constexpr uint32_t kTmemS = 0, kTmemO = 256, kTmemAcc = 384;
+
+struct TileRef {
+  int chunk;   // 0 = own (when present), else 1 + reference index (or reference index when no own chunk)
+  int ref;     // -1 for the own chunk
+  int t;       // tile index inside the chunk
+};
+
+__device__ __forceinline__ TileRef locate_tile(const AttnKParams& p, int g) {
+  TileRef r;
+  if (g < p.own_tiles) {
+    r.chunk = 0; r.ref = -1; r.t = g;
+  } else {
+    const int gg = g - p.own_tiles;
+    r.ref = gg / p.ref_tiles;
+    r.t = gg - r.ref * p.ref_tiles;
+    r.chunk = r.ref + (p.has_own ? 1 : 0);
+  }
+  return r;
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// multiplies 64 fp32 TMEM columns of this thread's lane by f
+__device__ __forceinline__ void tmem_scale64(uint32_t taddr, float f) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+    tmem_st32(taddr + c * 32, r);
+  }
+}
+
+template <bool ADAIN>
+__global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __grid_constant__ AttnKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + kOffQ;
@@ -59,25 +119,24 @@ __global__ void __launch_bounds__(192, 1) shared_attn_kernel(const __grid_consta
   uint8_t* sP = smem + kOffP;
   float* sAd = reinterpret_cast<float*>(smem + kOffAdain);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* q_full = bars;                 // 1
-  uint64_t* kv_full = bars + 1;            // kKVStages
-  uint64_t* kv_empty = kv_full + kKVStages;
-  uint64_t* s_full = kv_empty + kKVStages; // 2
+  uint64_t* q_full = bars;                   // 1
+  uint64_t* kv_full = bars + 1;              // kKVStages
+  uint64_t* kv_empty = kv_full + kKVStages;  // kKVStages
+  uint64_t* s_full = kv_empty + kKVStages;   // 2 (per query tile)
   uint64_t* s_empty = s_full + 2;
   uint64_t* p_full = s_empty + 2;
-  uint64_t* o_full = p_full + 2;
-  uint64_t* o_empty = o_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* o_done = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int pair = blockIdx.x / p.n_splits, split = blockIdx.x - pair * p.n_splits;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int g_begin = split * p.tiles_per_split;
+  const int g_end = min(g_begin + p.tiles_per_split, p.total_tiles);
+  const int n_tiles = g_end - g_begin;
 
-  const int own_tiles = p.has_own ? (p.s_own + kKT - 1) / kKT : 0;
-  const int ref_tiles = p.n_ref > 0 ? (p.s_ref + kKT - 1) / kKT : 0;
-  const int total_tiles = own_tiles + p.n_ref * ref_tiles;
-
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.tma_q);
     if (p.has_own) { tma_prefetch_desc(&p.tma_k_own); tma_prefetch_desc(&p.tma_v_own); }
     if (p.n_ref) { tma_prefetch_desc(&p.tma_k_ref); tma_prefetch_desc(&p.tma_v_ref); }
@@ -87,17 +146,16 @@ __global__ void __launch_bounds__(192, 1) shared_attn_kernel(const __grid_consta
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 128);
       mbar_init(&p_full[i], 128);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 128);
+      mbar_init(&o_done[i], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  // stage the AdaIN affine of every reference for this (batch, head): sAd[r][0][d] = scale, sAd[r][1][d] = shift
-  if (p.adain_scale != nullptr) {
+  if (ADAIN) {
+    // stage the AdaIN affine of every reference for this (batch, head): sAd[r][0][d] = scale, sAd[r][1][d] = shift
     const int C = p.heads * kD;
     for (int i = threadIdx.x; i < p.n_ref * kD; i += blockDim.x) {
       const int r = i / kD, d = i % kD;
@@ -110,201 +168,316 @@ __global__ void __launch_bounds__(192, 1) shared_attn_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;         // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;   // 2 x 64 columns
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_3d(sQ, &p.tma_q, q_full, p.q_col_off + head * kD, qt * kQT, b);
-      int j = 0;
-      for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
-        const bool is_own = p.has_own && chunk == 0;
-        const int r = chunk - (p.has_own ? 1 : 0);
-        const int tiles = is_own ? own_tiles : ref_tiles;
-        for (int t = 0; t < tiles; ++t, ++j) {
-          const int s = j % kKVStages;
-          const uint32_t ph = (j / kKVStages) & 1;
-          mbar_wait(&kv_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&kv_full[s], 2 * kTileBytes);
-          if (is_own) {
-            const int bb = p.own_shared ? 0 : b;
-            tma_load_3d(sK + s * kTileBytes, &p.tma_k_own, &kv_full[s], p.k_own_col_off + head * kD, t * kKT, bb);
-            tma_load_3d(sV + s * kTileBytes, &p.tma_v_own, &kv_full[s], p.v_own_col_off + head * kD, t * kKT, bb);
-          } else {
-            tma_load_4d(sK + s * kTileBytes, &p.tma_k_ref, &kv_full[s], p.ref_col_off + head * kD, t * kKT, r, b);
-            tma_load_4d(sV + s * kTileBytes, &p.tma_v_ref, &kv_full[s], p.ref_col_off + head * kD, t * kKT, r, b);
-          }
+      mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+      tma_load_3d(sQ, &p.tma_q, q_full, p.q_col_off + head * kD, (2 * pair) * kQT, b);
+      tma_load_3d(sQ + kTileBytes, &p.tma_q, q_full, p.q_col_off + head * kD, (2 * pair + 1) * kQT, b);
+      for (int jj = 0; jj < n_tiles; ++jj) {
+        const TileRef tr = locate_tile(p, g_begin + jj);
+        const int s = jj % kKVStages;
+        mbar_wait(&kv_empty[s], ((jj / kKVStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * kTileBytes);
+        if (tr.ref < 0) {
+          const int bb = p.own_shared ? 0 : b;
+          tma_load_3d(sK + s * kTileBytes, &p.tma_k_own, &kv_full[s], p.k_own_col_off + head * kD, tr.t * kKT, bb);
+          tma_load_3d(sV + s * kTileBytes, &p.tma_v_own, &kv_full[s], p.v_own_col_off + head * kD, tr.t * kKT, bb);
+        } else {
+          tma_load_4d(sK + s * kTileBytes, &p.tma_k_ref, &kv_full[s], p.ref_col_off + head * kD, tr.t * kKT, tr.ref, b);
+          tma_load_4d(sV + s * kTileBytes, &p.tma_v_ref, &kv_full[s], p.ref_col_off + head * kD, tr.t * kKT, tr.ref, b);
         }
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t IDESC_QK = umma_idesc_f16(128, kKT, 0, 0);   // A = Q (K-major), B = K (K-major)
       constexpr uint32_t IDESC_PV = umma_idesc_f16(128, kD, 0, 1);    // A = P (K-major), B = V (MN-major)
-      const uint32_t q_base = smem_u32(sQ);
-      auto issue_pv = [&](int i) {
-        const int bi = i & 1, s = i % kKVStages;
-        mbar_wait(&p_full[bi], (i >> 1) & 1);
-        mbar_wait(&o_empty[bi], ((i >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t p_base = smem_u32(sP + bi * 2 * kTileBytes);
+      auto issue_pv = [&](int k) {
+        const int g = g_begin + k, s = k % kKVStages;
+        // a segment (AdaIN: one chunk; otherwise the whole range) starts with a fresh accumulator
+        const bool fresh = (k == 0) || (ADAIN && locate_tile(p, g).chunk != locate_tile(p, g - 1).chunk);
         const uint32_t v_base = smem_u32(sV + s * kTileBytes);
 #pragma unroll
-        for (int kk = 0; kk < kKT / 16; ++kk) {
-          const uint64_t adesc = umma_smem_desc(p_base + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc(v_base + kk * 2048, 1024, 1024);
-          umma_f16_ss(tmem_O + bi * kD, adesc, bdesc, IDESC_PV, kk != 0 ? 1u : 0u);
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(&p_full[i], k & 1);
+          tc_fence_after();
+          const uint32_t p_base = smem_u32(sP + i * 2 * kTileBytes);
+#pragma unroll
+          for (int kk = 0; kk < kKT / 16; ++kk) {
+            const uint64_t adesc = umma_smem_desc(p_base + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(v_base + kk * 2048, 1024, 1024);
+            umma_f16_ss(tmem_base + kTmemO + i * kD, adesc, bdesc, IDESC_PV, (kk != 0 || !fresh) ? 1u : 0u);
+          }
+          umma_commit(&o_done[i]);
         }
-        umma_commit(&o_full[bi]);
         umma_commit(&kv_empty[s]);
       };
       mbar_wait(q_full, 0);
-      for (int j = 0; j < total_tiles; ++j) {
-        const int s = j % kKVStages, bj = j & 1;
-        mbar_wait(&kv_full[s], (j / kKVStages) & 1);
-        mbar_wait(&s_empty[bj], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
+      for (int jj = 0; jj < n_tiles; ++jj) {
+        const int s = jj % kKVStages;
+        mbar_wait(&kv_full[s], (jj / kKVStages) & 1);
         const uint32_t k_base = smem_u32(sK + s * kTileBytes);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          const uint64_t adesc = umma_smem_desc(q_base + k * 32, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc(k_base + k * 32, 16, 1024);
-          umma_f16_ss(tmem_S + bj * kKT, adesc, bdesc, IDESC_QK, k != 0 ? 1u : 0u);
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(&s_empty[i], (jj & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t q_base = smem_u32(sQ + i * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < kD / 16; ++k) {
+            const uint64_t adesc = umma_smem_desc(q_base + k * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(k_base + k * 32, 16, 1024);
+            umma_f16_ss(tmem_base + kTmemS + i * kKT, adesc, bdesc, IDESC_QK, k != 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[i]);
         }
-        umma_commit(&s_full[bj]);
-        if (j >= 1) issue_pv(j - 1);
+        if (jj >= 1) issue_pv(jj - 1);
       }
-      issue_pv(total_tiles - 1);
+      if (n_tiles > 0) issue_pv(n_tiles - 1);
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ softmax / accumulate (thread == row)
-    const int row = warp * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    const bool use_adain = p.adain_scale != nullptr;
-    float m_run = -INFINITY, l_run = 0.f;
-    float acc[kD];
-#pragma unroll
-    for (int d = 0; d < kD; ++d) acc[d] = 0.f;
-    float alpha_pend = 1.f, rs_pend = 0.f;
-    int ref_pend = -1;
+    // ------------------------------------------------------------------ softmax warpgroups (thread == query row)
+    const int i = warp >> 2;                         // query tile of this warpgroup
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t t_S = tmem_base + kTmemS + i * kKT + lane_addr;
+    const uint32_t t_O = tmem_base + kTmemO + i * kD + lane_addr;
+    const uint32_t t_A = tmem_base + kTmemAcc + i * kD + lane_addr;
+    uint8_t* prow = sP + i * 2 * kTileBytes + row * 128;
+    const float c = p.scale_log2;
 
-    auto consume = [&](int i, float alpha, float rs, int ref) {
-      const int bi = i & 1;
-      mbar_wait(&o_full[bi], (i >> 1) & 1);
+    float m_ref = -INFINITY;     // reference max (log2 units) every stored exponential is relative to
+    float l_seg = 0.f;           // row sum of the current segment
+    float l_tot = 0.f;           // row sum of the finished segments (AdaIN path)
+    bool acc_valid = false;      // the second accumulator holds finished segments
+
+    for (int jj = 0; jj < n_tiles; ++jj) {
+      const int g = g_begin + jj;
+      const TileRef tr = locate_tile(p, g);
+      const bool seg_first = (jj == 0) || (ADAIN && locate_tile(p, g - 1).chunk != tr.chunk);
+      const bool seg_last = (jj == n_tiles - 1) || (ADAIN && locate_tile(p, g + 1).chunk != tr.chunk);
+      const int len = tr.ref < 0 ? p.s_own : p.s_ref;
+      const int valid = min(kKT, len - tr.t * kKT);   // keys of this tile that exist
+
+      mbar_wait(&s_full[i], jj & 1);
       tc_fence_after();
-      const float* ad = sAd + (ref < 0 ? 0 : ref) * 2 * kD;
-      const bool affine = use_adain && ref >= 0;
+      uint32_t sr[128];
+      tmem_ld32(t_S, sr);
+      tmem_ld32(t_S + 32, sr + 32);
+      tmem_ld32(t_S + 64, sr + 64);
+      tmem_ld32(t_S + 96, sr + 96);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[i]);                       // the score buffer is free for the next QK^T
+
+      if (valid < kKT) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_O + bi * kD + c * 32 + lane_addr, r);
-        tmem_ld_wait();
+        for (int k = 0; k < 128; ++k)
+          if (k >= valid) sr[k] = 0xff800000u;        // -inf: exp2 -> 0, ignored by the max
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int d = 0; d < 32; ++d) {
-          float o = __uint_as_float(r[d]);
-          if (affine) o = fmaf(ad[c * 32 + d], o, ad[kD + c * 32 + d] * rs);
-          acc[c * 32 + d] = fmaf(acc[c * 32 + d], alpha, o);
+      for (int k = 0; k < 128; k += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[k]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sr[k + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sr[k + 3]));
+      }
+      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+
+      if (jj == 0) {
+        m_ref = m_new;                                // nothing accumulated yet
+      } else {
+        const bool need = m_new > m_ref + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {          // TMEM ld/st are warp-collective: the warp rescales together
+          mbar_wait(&o_done[i], (jj - 1) & 1);        // PV of the previous tile has landed: O is stable
+          tc_fence_after();
+          const float f = need ? fast_exp2(m_ref - m_new) : 1.0f;
+          if (need) m_ref = m_new;
+          if (!seg_first) tmem_scale64(t_O, f);
+          if (ADAIN && acc_valid) tmem_scale64(t_A, f);
+          tmem_st_wait();
+          tc_fence_before();
+          l_seg *= f;
+          l_tot *= f;
         }
       }
-      tc_fence_before();
-      mbar_arrive(&o_empty[bi]);
-    };
 
-    int j = 0;
-    for (int chunk = 0; chunk < p.n_chunks; ++chunk) {
-      const bool is_own = p.has_own && chunk == 0;
-      const int ref = is_own ? -1 : chunk - (p.has_own ? 1 : 0);
-      const int tiles = is_own ? own_tiles : ref_tiles;
-      const int len = is_own ? p.s_own : p.s_ref;
-      for (int t = 0; t < tiles; ++t, ++j) {
-        const int bj = j & 1;
-        const int valid = min(kKT, len - t * kKT);   // keys of this tile that exist
-        mbar_wait(&s_full[bj], (j >> 1) & 1);
+      // P = exp2(s * c - m_ref) as fp16, written in the swizzled K-major A-operand layout, 16 bytes (8 keys) at a
+      // time so only the scores stay live in registers
+      if (jj > 0) mbar_wait(&o_done[i], (jj - 1) & 1);   // the previous PV has finished reading the P buffer
+      const float neg_m = -m_ref;
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int k = q * 8;
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[k]), c, neg_m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[k + 1]), c, neg_m));
+        const float p2 = fast_exp2(fmaf(__uint_as_float(sr[k + 2]), c, neg_m));
+        const float p3 = fast_exp2(fmaf(__uint_as_float(sr[k + 3]), c, neg_m));
+        const float p4 = fast_exp2(fmaf(__uint_as_float(sr[k + 4]), c, neg_m));
+        const float p5 = fast_exp2(fmaf(__uint_as_float(sr[k + 5]), c, neg_m));
+        const float p6 = fast_exp2(fmaf(__uint_as_float(sr[k + 6]), c, neg_m));
+        const float p7 = fast_exp2(fmaf(__uint_as_float(sr[k + 7]), c, neg_m));
+        rs0 += p0 + p4; rs1 += p1 + p5; rs2 += p2 + p6; rs3 += p3 + p7;
+        // 16-byte chunk q of the row: 64-key atom (q >> 3), chunk (q & 7) inside the atom, XOR-swizzled by the row
+        uint8_t* dst = prow + (q >> 3) * kTileBytes + (((q & 7) ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_half2(p0, p1), pack_half2(p2, p3), pack_half2(p4, p5), pack_half2(p6, p7));
+      }
+      l_seg += (rs0 + rs1) + (rs2 + rs3);
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[i]);
+
+      if (ADAIN && seg_last) {
+        // fold the finished segment into the second accumulator: acc += a * O_seg + b * rowsum(P_seg)
+        mbar_wait(&o_done[i], jj & 1);
         tc_fence_after();
-        const uint32_t s_addr = tmem_S + bj * kKT + lane_addr;
-        // pass 1: row max
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(s_addr + c * 32, r);
+        const bool affine = tr.ref >= 0;
+        const float* ad = sAd + (affine ? tr.ref : 0) * 2 * kD;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t o[32];
+          tmem_ld32(t_O + h * 32, o);
           tmem_ld_wait();
+          if (affine) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = __uint_as_float(r[i]);
-            if (c * 32 + i < valid) mx = fmaxf(mx, v);
+            for (int d = 0; d < 32; ++d)
+              o[d] = __float_as_uint(fmaf(ad[h * 32 + d], __uint_as_float(o[d]), ad[kD + h * 32 + d] * l_seg));
           }
+          if (acc_valid) {
+            uint32_t a[32];
+            tmem_ld32(t_A + h * 32, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) + __uint_as_float(a[d]));
+          }
+          tmem_st32(t_A + h * 32, o);
         }
-        const float m_new = fmaxf(m_run, mx * p.scale_log2);
-        const float alpha = fast_exp2(m_run - m_new);
-        // pass 2: P = exp2(s*scale_log2 - m_new), fp16, into the swizzled K-major A-operand layout
-        float rowsum = 0.f;
-        uint8_t* prow = sP + bj * 2 * kTileBytes + row * 128;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tmem_ld32(s_addr + c * 32, r);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_new));
-            float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_new));
-            if (c * 32 + i >= valid) p0 = 0.f;
-            if (c * 32 + i + 1 >= valid) p1 = 0.f;
-            rowsum += p0 + p1;
-            pk[i >> 1] = pack_half2(p0, p1);
-          }
-          // 32 columns = 4 x 16-byte chunks; chunk index within the 64-column atom: (c & 1) * 4 + q
-          uint8_t* atom = prow + (c >> 1) * kTileBytes;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int kc = (c & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(atom + ((kc ^ (row & 7)) << 4)) =
-                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
-        }
+        tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&s_empty[bj]);
-        fence_proxy_async_smem();
-        mbar_arrive(&p_full[bj]);
-
-        l_run = fmaf(l_run, alpha, rowsum);
-        m_run = m_new;
-        if (j > 0) consume(j - 1, alpha_pend, rs_pend, ref_pend);
-        alpha_pend = alpha;
-        rs_pend = rowsum;
-        ref_pend = ref;
+        acc_valid = true;
+        l_tot += l_seg;
+        l_seg = 0.f;
       }
     }
-    consume(total_tiles - 1, alpha_pend, rs_pend, ref_pend);
 
-    const int qrow = qt * kQT + row;
-    if (qrow < p.s_q) {
-      const float inv = 1.0f / l_run;
-      __half* op = p.out + (static_cast<size_t>(b) * p.s_q + qrow) * p.out_stride + head * kD;
+    // ---------------------------------------------------------------- epilogue
+    const int qrow = (2 * pair + i) * kQT + row;
+    if (n_tiles > 0) {
+      if (!ADAIN) {
+        mbar_wait(&o_done[i], (n_tiles - 1) & 1);
+        tc_fence_after();
+      }
+      const uint32_t t_src = ADAIN ? t_A : t_O;
+      const float l = ADAIN ? l_tot : l_seg;
+      if (p.n_splits == 1) {
+        const float inv = 1.0f / l;
+        __half* op = p.out + (static_cast<size_t>(b) * p.s_q + qrow) * p.out_stride + head * kD;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint4 u = make_uint4(pack_half2(acc[q * 8] * inv, acc[q * 8 + 1] * inv),
-                             pack_half2(acc[q * 8 + 2] * inv, acc[q * 8 + 3] * inv),
-                             pack_half2(acc[q * 8 + 4] * inv, acc[q * 8 + 5] * inv),
-                             pack_half2(acc[q * 8 + 6] * inv, acc[q * 8 + 7] * inv));
-        reinterpret_cast<uint4*>(op)[q] = u;
+        for (int h = 0; h < 2; ++h) {
+          uint32_t o[32];
+          tmem_ld32(t_src + h * 32, o);
+          tmem_ld_wait();
+          if (qrow < p.s_q) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = make_uint4(
+                  pack_half2(__uint_as_float(o[q * 8]) * inv, __uint_as_float(o[q * 8 + 1]) * inv),
+                  pack_half2(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv),
+                  pack_half2(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv),
+                  pack_half2(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv));
+              reinterpret_cast<uint4*>(op)[h * 4 + q] = u;
+            }
+          }
+        }
+      } else {
+        const int n_qt = 2 * (gridDim.x / p.n_splits);
+        const size_t unit = ((static_cast<size_t>(b) * p.heads + head) * n_qt + (2 * pair + i)) * p.n_splits + split;
+        float* po = p.part_o + (unit * 128 + row) * kD;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t o[32];
+          tmem_ld32(t_src + h * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            reinterpret_cast<uint4*>(po)[h * 8 + q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
+        p.part_ml[unit * 128 + row] = make_float2(m_ref, l);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 512);
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+// Merges the split-KV partials of one query row in split order: out = sum_s 2^(m_s - M) O_s / sum_s 2^(m_s - M) l_s.
+// grid = (q tiles, heads, batch), block = 128 (thread == row).
+__global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
+                                                           int n_splits, int n_qt, int heads, int s_q,
+                                                           __half* __restrict__ out, int out_stride) {
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z, row = threadIdx.x;
+  const int qrow = qt * kQT + row;
+  if (qrow >= s_q) return;
+  const size_t unit0 = ((static_cast<size_t>(b) * heads + head) * n_qt + qt) * n_splits;
+  float M = -INFINITY;
+  for (int s = 0; s < n_splits; ++s) M = fmaxf(M, part_ml[(unit0 + s) * 128 + row].x);
+  float acc[kD];
+#pragma unroll
+  for (int d = 0; d < kD; ++d) acc[d] = 0.f;
+  float l = 0.f;
+  for (int s = 0; s < n_splits; ++s) {
+    const float2 ml = part_ml[(unit0 + s) * 128 + row];
+    const float w = fast_exp2(ml.x - M);
+    l = fmaf(ml.y, w, l);
+    const float4* po = reinterpret_cast<const float4*>(part_o + ((unit0 + s) * 128 + row) * kD);
+#pragma unroll
+    for (int q = 0; q < kD / 4; ++q) {
+      const float4 v = po[q];
+      acc[4 * q] = fmaf(v.x, w, acc[4 * q]);
+      acc[4 * q + 1] = fmaf(v.y, w, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(v.z, w, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(v.w, w, acc[4 * q + 3]);
+    }
+  }
+  const float inv = 1.0f / l;
+  __half* op = out + (static_cast<size_t>(b) * s_q + qrow) * out_stride + head * kD;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    reinterpret_cast<uint4*>(op)[q] =
+        make_uint4(pack_half2(acc[q * 8] * inv, acc[q * 8 + 1] * inv), pack_half2(acc[q * 8 + 2] * inv, acc[q * 8 + 3] * inv),
+                   pack_half2(acc[q * 8 + 4] * inv, acc[q * 8 + 5] * inv), pack_half2(acc[q * 8 + 6] * inv, acc[q * 8 + 7] * inv));
+}
+
+// Split-KV plan: the number of KV ranges that minimises (rounds over 148 SMs) x (tiles per range), with a small
+// charge per split for the partial write + combine.
+static int plan_splits(long units, int total_tiles, int requested) {
+  if (requested > 0) return requested < total_tiles ? requested : total_tiles;
+  if (units >= 120 || total_tiles < 4) return 1;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 16 && s <= total_tiles / 2; ++s) {
+    const int tps = (total_tiles + s - 1) / s;
+    const long rounds = (units * s + 147) / 148;
+    const double cost = static_cast<double>(rounds) * (tps + 1.5) + (s > 1 ? 1.0 + 0.25 * s : 0.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 }  // namespace ir
+
+extern "C" size_t ir_shared_attn_workspace_bytes(int batch, int heads, int s_q) {
+  const size_t pairs = static_cast<size_t>((s_q + 255) / 256);
+  if (pairs * heads * batch >= 120) return 0;   // plan_splits never splits these
+  return static_cast<size_t>(batch) * heads * 2 * pairs * 16 * 128 * (ir::kD * sizeof(float) + sizeof(float2));
+}
 
 extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t stream_) {
   using namespace ir;
@@ -328,6 +501,7 @@ extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t st
   if ((p->q_col_off | p->k_own_col_off | p->v_own_col_off | p->ref_col_off) % 8)
     return set_error(IR_ERR_ALIGN, "ir_shared_attn_fwd: column offsets must be multiples of 8");
   if (reinterpret_cast<uintptr_t>(p->out) & 15) return set_error(IR_ERR_ALIGN, "ir_shared_attn_fwd: out not 16-byte aligned");
+  if (p->kv_splits < 0 || p->kv_splits > 16) return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: kv_splits=%d (0 = auto, 1..16)", p->kv_splits);
 
   AttnKParams kp;
   memset(&kp, 0, sizeof(kp));
@@ -366,21 +540,47 @@ extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t st
   kp.s_q = p->s_q;
   kp.heads = p->heads;
   kp.scale_log2 = p->scale * 1.4426950408889634f;
-  kp.adain_scale = p->n_ref > 0 ? p->adain_scale : nullptr;
-  kp.adain_shift = p->n_ref > 0 ? p->adain_shift : nullptr;
+  const bool adain = p->n_ref > 0 && p->adain_scale != nullptr;
+  kp.adain_scale = adain ? p->adain_scale : nullptr;
+  kp.adain_shift = adain ? p->adain_shift : nullptr;
   kp.out = static_cast<__half*>(p->out);
   kp.out_stride = p->out_row_stride;
-  kp.chunk_mass = nullptr;
-  kp.n_chunks = (has_own ? 1 : 0) + p->n_ref;
+  kp.own_tiles = has_own ? (p->s_own + kKT - 1) / kKT : 0;
+  kp.ref_tiles = p->n_ref > 0 ? (p->s_ref + kKT - 1) / kKT : 1;
+  kp.total_tiles = kp.own_tiles + p->n_ref * (p->n_ref > 0 ? kp.ref_tiles : 0);
+
+  const int pairs = (p->s_q + 2 * kQT - 1) / (2 * kQT);
+  int n_splits = plan_splits(static_cast<long>(pairs) * p->heads * p->batch, kp.total_tiles, p->kv_splits);
+  if (n_splits > 1 && !p->workspace) {
+    if (p->kv_splits > 1) return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: kv_splits=%d needs a workspace", p->kv_splits);
+    n_splits = 1;
+  }
+  kp.tiles_per_split = (kp.total_tiles + n_splits - 1) / n_splits;
+  n_splits = (kp.total_tiles + kp.tiles_per_split - 1) / kp.tiles_per_split;   // no empty ranges
+  kp.n_splits = n_splits;
+  if (n_splits > 1) {
+    const size_t units = static_cast<size_t>(p->batch) * p->heads * (2 * pairs) * n_splits;
+    if (p->workspace_bytes < units * 128 * (kD * sizeof(float) + sizeof(float2)))
+      return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: workspace too small (%zu bytes)", p->workspace_bytes);
+    kp.part_o = static_cast<float*>(p->workspace);
+    kp.part_ml = reinterpret_cast<float2*>(kp.part_o + units * 128 * kD);
+  }
 
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(shared_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    cudaError_t e = cudaFuncSetAttribute(shared_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(shared_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(shared_attn): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  dim3 grid((p->s_q + kQT - 1) / kQT, p->heads, p->batch);
-  shared_attn_kernel<<<grid, 192, kAttnSmem, stream>>>(kp);
+  dim3 grid(pairs * n_splits, p->heads, p->batch);
+  if (adain) shared_attn_kernel<true><<<grid, kAttnThreads, kAttnSmem, stream>>>(kp);
+  else shared_attn_kernel<false><<<grid, kAttnThreads, kAttnSmem, stream>>>(kp);
   IR_CUDA_LAUNCH_CHECK("shared_attn launch");
+  if (n_splits > 1) {
+    attn_combine_kernel<<<dim3(2 * pairs, p->heads, p->batch), 128, 0, stream>>>(kp.part_o, kp.part_ml, n_splits, 2 * pairs, p->heads,
+                                                                                 p->s_q, kp.out, kp.out_stride);
+    IR_CUDA_LAUNCH_CHECK("attn_combine launch");
+  }
   return 0;
 }

@@ -169,6 +169,12 @@ __device__ __forceinline__ void dsmem_st_f4(uint32_t addr, float a, float b, flo
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// register reallocation between warp roles (warp-collective; counts are multiples of 8)
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---------------------------------------------------------------- descriptors
 // UMMA shared-memory matrix descriptor (64-bit):
 //  [0,14)  start address >> 4      [16,30) leading-dim byte offset >> 4

@@ -304,3 +304,39 @@ def test_latent_in_out_roundtrip(L):
     out = L.latent_out(e2, x, nz, a, s)
     ref = ((a * x + s * nz) - s * e2[:, :4].float().reshape(2, 16, 16, 4).permute(0, 3, 1, 2)) / a
     assert rel_l2(out, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("cfg,splits", [((1, 5, 1024, False, 4, True, None), 4), ((1, 2, 256, True, 2, True, None), 3),
+                                        ((1, 5, 4096, False, 4, True, None), 7), ((1, 2, 512, True, 0, False, None), 2),
+                                        ((1, 5, 4096, False, 4, False, None), 0), ((1, 10, 1024, True, 4, True, None), 0)])
+def test_shared_attention_split_kv(L, cfg, splits):
+    """Split-KV partials + fixed-order combine (explicit split counts and the auto plan for a single identity)."""
+    B, H, S, own, n_ref, adain, s_own_o = cfg
+    q, kw, ref, _ = _attn_case(L, *cfg, seed=31)
+    out = L.shared_attn(q.reshape(-1, H * 64), heads=H, scale=0.125, batch=B, s_q=S, kv_splits=splits, **kw)
+    assert rel_l2(out.reshape(B, S, -1), ref) <= TOL
+    again = L.shared_attn(q.reshape(-1, H * 64), heads=H, scale=0.125, batch=B, s_q=S, kv_splits=splits, **kw)
+    assert torch.equal(out, again)
+    unsplit = L.shared_attn(q.reshape(-1, H * 64), heads=H, scale=0.125, batch=B, s_q=S, kv_splits=1, **kw)
+    assert rel_l2(out, unsplit) <= 5e-4
+
+
+def test_shared_attention_large_logits_lazy_rescale(L):
+    """Scores that keep growing along the KV axis force the lazy (threshold 2^8) accumulator rescale to fire."""
+    g = _gen(32)
+    B, H, S, N = 1, 2, 256, 4
+    C = H * 64
+    q = torch.randn(B, S, C, device="cuda", generator=g).half()
+    kr = torch.randn(B, N, S, C, device="cuda", generator=g)
+    ramp = torch.linspace(0.2, 6.0, N * S, device="cuda").view(1, N, S, 1)     # later keys get much larger logits
+    kr = (kr * ramp).half()
+    vr = torch.randn(B, N, S, C, device="cuda", generator=g).half()
+    a_s = (torch.rand(B, N, C, device="cuda", generator=g) + 0.5).contiguous()
+    a_b = torch.randn(B, N, C, device="cuda", generator=g).contiguous()
+    for adain in (False, True):
+        vc = [vr[:, r].float() * (a_s[:, r, None] if adain else 1) + (a_b[:, r, None] if adain else 0) for r in range(N)]
+        ref, _ = _attn_ref(q, [kr[:, r] for r in range(N)], vc, H, 0.125)
+        kw = dict(adain_scale=a_s, adain_shift=a_b) if adain else {}
+        out = L.shared_attn(q.reshape(-1, C), heads=H, scale=0.125, batch=B, s_q=S, k_ref=kr.reshape(-1, C),
+                            v_ref=vr.reshape(-1, C), n_ref=N, s_ref=S, kv_splits=1, **kw)
+        assert rel_l2(out.reshape(B, S, C), ref) <= 2 * TOL
