@@ -3,14 +3,16 @@
 // A CTA owns TWO 128-query tiles of one (batch, head) and streams KV in 128-key tiles, chunk by chunk
 // ([own tokens] ++ reference 0 ++ reference 1 ...), never concatenated in memory. 10 warps:
 //   warps 0-3 / 4-7: softmax warpgroup of query tile 0 / 1, thread == query row. One tcgen05.ld pass brings the 128
-//       scores of the row into registers (which frees the TMEM score buffer for the next QK^T at once), row max,
-//       exp2, fp16 P into shared memory in the UMMA K-major swizzled layout. The two warpgroups run out of phase, so
-//       the MUFU pipe (the bound at d=64: 16 exp/clk/SM vs 8192 MMA FLOP/clk/SM) always has work while the tensor
-//       pipe runs the other tile's QK^T / PV.
+//       scores of the row into registers, row max, exp2, and P goes back as packed fp16 INTO THE SAME TMEM COLUMNS
+//       (tcgen05.st), from where the PV MMA reads it as its A operand: P never touches shared memory, which keeps the
+//       128 B/clk shared-memory port for the K/V operand reads. The two warpgroups run out of phase, so the MUFU pipe
+//       (the bound at d=64: 16 exp/clk/SM vs 8192 MMA FLOP/clk/SM) always has work while the tensor pipe runs the
+//       other tile's QK^T / PV.
 //   warp 8 (one lane): TMA producer — both Q tiles once, then K/V tiles straight out of the token-major projection
-//       outputs (the head split is just the TMA column coordinate), 128B-swizzled, 3-stage ring.
-//   warp 9 (one lane): tcgen05.mma issuer — S_i = Q_i K_j^T (TMEM, 128 columns per tile), O_i += P_i V_j (V consumed
-//       MN-major, no transpose). O accumulates IN TMEM across the KV tiles of a segment; the running max is only
+//       outputs (the head split is just the TMA column coordinate), 128B-swizzled, 4-stage ring.
+//   warp 9 (one lane): tcgen05.mma issuer — S_i = Q_i K_j^T (TMEM, 128 columns per tile), O_i += P_i V_j (A = P from
+//       TMEM, B = V consumed MN-major, no transpose), issued as PV_i(j), QK_i(j+1) back to back so the score
+//       buffer is refilled as soon as its P has been consumed. O accumulates IN TMEM across the KV tiles of a segment; the running max is only
 //       raised when it grows by more than 2^8 (lazy rescale, done in TMEM by the softmax warps), so the common tile
 //       costs no accumulator traffic at all.
 // AdaIN: sum_r P_r (a_r*V_r + b_r) = a_r*(P_r V_r) + b_r*rowsum(P_r) — a segment is one reference chunk; at its end
@@ -30,7 +32,7 @@ constexpr int kQT = 128;                  // query rows per tile (two tiles per 
 constexpr int kKT = 128;                  // keys per tile
 constexpr int kD = 64;                    // head dim
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB: a Q, K or V tile, or one 64-key half of a P tile
-constexpr int kKVStages = 3;
+constexpr int kKVStages = 4;
 constexpr int kMaxRef = 16;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8, exact in fp16 / fp32 accumulation
 constexpr int kAttnThreads = 320;
@@ -56,12 +58,11 @@ struct AttnKParams {
 constexpr int kOffQ = 0;                                    // 2 tiles
 constexpr int kOffK = kOffQ + 2 * kTileBytes;
 constexpr int kOffV = kOffK + kKVStages * kTileBytes;
-constexpr int kOffP = kOffV + kKVStages * kTileBytes;       // 2 query tiles x 32 KB
-constexpr int kOffAdain = kOffP + 2 * 2 * kTileBytes;       // [kMaxRef][2][64] fp32
+constexpr int kOffAdain = kOffV + kKVStages * kTileBytes;   // [kMaxRef][2][64] fp32
 constexpr int kOffBar = kOffAdain + kMaxRef * 2 * 64 * 4;
 constexpr int kAttnSmem = kOffBar + 256 + 1024;
 
-// TMEM columns: S0 | S1 | O0 | O1 | ACC0 | ACC1
+// TMEM columns: S0 | S1 | O0 | O1 | ACC0 | ACC1   (P_i = packed fp16, aliases the first 64 columns of S_i)
 constexpr uint32_t kTmemS = 0, kTmemO = 256, kTmemAcc = 384;
 
 struct TileRef {
@@ -116,15 +117,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
   uint8_t* sQ = smem + kOffQ;
   uint8_t* sK = smem + kOffK;
   uint8_t* sV = smem + kOffV;
-  uint8_t* sP = smem + kOffP;
   float* sAd = reinterpret_cast<float*>(smem + kOffAdain);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars;                   // 1
   uint64_t* kv_full = bars + 1;              // kKVStages
   uint64_t* kv_empty = kv_full + kKVStages;  // kKVStages
   uint64_t* s_full = kv_empty + kKVStages;   // 2 (per query tile)
-  uint64_t* s_empty = s_full + 2;
-  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_full = s_full + 2;
   uint64_t* o_done = p_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
@@ -144,7 +143,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     for (int s = 0; s < kKVStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
       mbar_init(&p_full[i], 128);
       mbar_init(&o_done[i], 1);
     }
@@ -195,48 +193,47 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t IDESC_QK = umma_idesc_f16(128, kKT, 0, 0);   // A = Q (K-major), B = K (K-major)
-      constexpr uint32_t IDESC_PV = umma_idesc_f16(128, kD, 0, 1);    // A = P (K-major), B = V (MN-major)
-      auto issue_pv = [&](int k) {
-        const int g = g_begin + k, s = k % kKVStages;
-        // a segment (AdaIN: one chunk; otherwise the whole range) starts with a fresh accumulator
-        const bool fresh = (k == 0) || (ADAIN && locate_tile(p, g).chunk != locate_tile(p, g - 1).chunk);
-        const uint32_t v_base = smem_u32(sV + s * kTileBytes);
+      constexpr uint32_t IDESC_PV = umma_idesc_f16(128, kD, 0, 1);    // A = P (TMEM), B = V (MN-major)
+      auto issue_qk = [&](int jj, int i) {
+        const uint32_t k_base = smem_u32(sK + (jj % kKVStages) * kTileBytes);
+        const uint32_t q_base = smem_u32(sQ + i * kTileBytes);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_full[i], k & 1);
-          tc_fence_after();
-          const uint32_t p_base = smem_u32(sP + i * 2 * kTileBytes);
-#pragma unroll
-          for (int kk = 0; kk < kKT / 16; ++kk) {
-            const uint64_t adesc = umma_smem_desc(p_base + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
-            const uint64_t bdesc = umma_smem_desc(v_base + kk * 2048, 1024, 1024);
-            umma_f16_ss(tmem_base + kTmemO + i * kD, adesc, bdesc, IDESC_PV, (kk != 0 || !fresh) ? 1u : 0u);
-          }
-          umma_commit(&o_done[i]);
+        for (int k = 0; k < kD / 16; ++k) {
+          const uint64_t adesc = umma_smem_desc(q_base + k * 32, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc(k_base + k * 32, 16, 1024);
+          umma_f16_ss(tmem_base + kTmemS + i * kKT, adesc, bdesc, IDESC_QK, k != 0 ? 1u : 0u);
         }
-        umma_commit(&kv_empty[s]);
+        umma_commit(&s_full[i]);
       };
       mbar_wait(q_full, 0);
+      if (n_tiles > 0) {
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_qk(0, 0);
+        issue_qk(0, 1);
+      }
       for (int jj = 0; jj < n_tiles; ++jj) {
-        const int s = jj % kKVStages;
-        mbar_wait(&kv_full[s], (jj / kKVStages) & 1);
-        const uint32_t k_base = smem_u32(sK + s * kTileBytes);
+        const int g = g_begin + jj, s = jj % kKVStages;
+        // a segment (AdaIN: one chunk; otherwise the whole range) starts with a fresh accumulator
+        const bool fresh = (jj == 0) || (ADAIN && locate_tile(p, g).chunk != locate_tile(p, g - 1).chunk);
+        const uint32_t v_base = smem_u32(sV + s * kTileBytes);
+        if (jj + 1 < n_tiles) mbar_wait(&kv_full[(jj + 1) % kKVStages], ((jj + 1) / kKVStages) & 1);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          mbar_wait(&s_empty[i], (jj & 1) ^ 1);
+          mbar_wait(&p_full[i], jj & 1);
           tc_fence_after();
-          const uint32_t q_base = smem_u32(sQ + i * kTileBytes);
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k) {
-            const uint64_t adesc = umma_smem_desc(q_base + k * 32, 16, 1024);
-            const uint64_t bdesc = umma_smem_desc(k_base + k * 32, 16, 1024);
-            umma_f16_ss(tmem_base + kTmemS + i * kKT, adesc, bdesc, IDESC_QK, k != 0 ? 1u : 0u);
+          for (int kk = 0; kk < kKT / 16; ++kk) {
+            const uint64_t bdesc = umma_smem_desc(v_base + kk * 2048, 1024, 1024);
+            umma_f16_ts(tmem_base + kTmemO + i * kD, tmem_base + kTmemS + i * kKT + kk * 8, bdesc, IDESC_PV,
+                        (kk != 0 || !fresh) ? 1u : 0u);
           }
-          umma_commit(&s_full[i]);
+          umma_commit(&o_done[i]);
+          // tcgen05.mma executes in issue order: the next QK^T refills S_i only after this PV has read P_i out of it
+          if (jj + 1 < n_tiles) issue_qk(jj + 1, i);
         }
-        if (jj >= 1) issue_pv(jj - 1);
+        umma_commit(&kv_empty[s]);
       }
-      if (n_tiles > 0) issue_pv(n_tiles - 1);
     }
     __syncwarp();
   } else {
@@ -247,7 +244,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     const uint32_t t_S = tmem_base + kTmemS + i * kKT + lane_addr;
     const uint32_t t_O = tmem_base + kTmemO + i * kD + lane_addr;
     const uint32_t t_A = tmem_base + kTmemAcc + i * kD + lane_addr;
-    uint8_t* prow = sP + i * 2 * kTileBytes + row * 128;
     const float c = p.scale_log2;
 
     float m_ref = -INFINITY;     // reference max (log2 units) every stored exponential is relative to
@@ -271,8 +267,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
       tmem_ld32(t_S + 64, sr + 64);
       tmem_ld32(t_S + 96, sr + 96);
       tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_empty[i]);                       // the score buffer is free for the next QK^T
 
       if (valid < kKT) {
 #pragma unroll
@@ -294,8 +288,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
       } else {
         const bool need = m_new > m_ref + kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {          // TMEM ld/st are warp-collective: the warp rescales together
-          mbar_wait(&o_done[i], (jj - 1) & 1);        // PV of the previous tile has landed: O is stable
-          tc_fence_after();
+          // s_full(jj) was committed after PV(jj-1): the accumulators are stable until we publish P(jj)
           const float f = need ? fast_exp2(m_ref - m_new) : 1.0f;
           if (need) m_ref = m_new;
           if (!seg_first) tmem_scale64(t_O, f);
@@ -307,29 +300,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
         }
       }
 
-      // P = exp2(s * c - m_ref) as fp16, written in the swizzled K-major A-operand layout, 16 bytes (8 keys) at a
-      // time so only the scores stay live in registers
-      if (jj > 0) mbar_wait(&o_done[i], (jj - 1) & 1);   // the previous PV has finished reading the P buffer
+      // P = exp2(s * c - m_ref) as packed fp16 (keys 2c, 2c+1 in TMEM column c), written over the scores just read
       const float neg_m = -m_ref;
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int k = q * 8;
-        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[k]), c, neg_m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[k + 1]), c, neg_m));
-        const float p2 = fast_exp2(fmaf(__uint_as_float(sr[k + 2]), c, neg_m));
-        const float p3 = fast_exp2(fmaf(__uint_as_float(sr[k + 3]), c, neg_m));
-        const float p4 = fast_exp2(fmaf(__uint_as_float(sr[k + 4]), c, neg_m));
-        const float p5 = fast_exp2(fmaf(__uint_as_float(sr[k + 5]), c, neg_m));
-        const float p6 = fast_exp2(fmaf(__uint_as_float(sr[k + 6]), c, neg_m));
-        const float p7 = fast_exp2(fmaf(__uint_as_float(sr[k + 7]), c, neg_m));
-        rs0 += p0 + p4; rs1 += p1 + p5; rs2 += p2 + p6; rs3 += p3 + p7;
-        // 16-byte chunk q of the row: 64-key atom (q >> 3), chunk (q & 7) inside the atom, XOR-swizzled by the row
-        uint8_t* dst = prow + (q >> 3) * kTileBytes + (((q & 7) ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_half2(p0, p1), pack_half2(p2, p3), pack_half2(p4, p5), pack_half2(p6, p7));
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int k = 0; k < 64; k += 4) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[h * 64 + k]), c, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[h * 64 + k + 1]), c, neg_m));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(sr[h * 64 + k + 2]), c, neg_m));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(sr[h * 64 + k + 3]), c, neg_m));
+          rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+          pk[k >> 1] = pack_half2(p0, p1);
+          pk[(k >> 1) + 1] = pack_half2(p2, p3);
+        }
+        tmem_st32(t_S + h * 32, pk);
       }
       l_seg += (rs0 + rs1) + (rs2 + rs3);
-      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(&p_full[i]);
 
       if (ADAIN && seg_last) {
