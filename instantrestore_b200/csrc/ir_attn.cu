@@ -36,6 +36,8 @@ constexpr int kKVStages = 4;
 constexpr int kMaxRef = 16;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8, exact in fp16 / fp32 accumulation
 constexpr int kAttnThreads = 320;
+constexpr bool kPingPong = false;         // strict alternation of the two warpgroups on the exp pass
+constexpr int kPolyOf8 = 2;               // of every 8 exponentials, this many run on the FMA pipes instead of MUFU
 
 struct AttnKParams {
   CUtensorMap tma_q, tma_k_own, tma_v_own, tma_k_ref, tma_v_ref;
@@ -95,6 +97,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // multiplies 64 fp32 TMEM columns of this thread's lane by f
@@ -108,6 +118,71 @@ __device__ __forceinline__ void tmem_scale64(uint32_t taddr, float f) {
     for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
     tmem_st32(taddr + c * 32, r);
   }
+}
+
+// Row max over the 128 scores of this thread's row (two 64-column TMEM reads). MASKED: keys >= valid do not exist.
+template <bool MASKED>
+__device__ __forceinline__ float row_max128(uint32_t t_S, int valid) {
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t sr[64];
+    tmem_ld32(t_S + h * 64, sr);
+    tmem_ld32(t_S + h * 64 + 32, sr + 32);
+    tmem_ld_wait();
+#pragma unroll
+    for (int k = 0; k < 64; k += 4) {
+      float a = __uint_as_float(sr[k]), b = __uint_as_float(sr[k + 1]);
+      float cc = __uint_as_float(sr[k + 2]), d = __uint_as_float(sr[k + 3]);
+      if (MASKED) {
+        if (h * 64 + k >= valid) a = -INFINITY;
+        if (h * 64 + k + 1 >= valid) b = -INFINITY;
+        if (h * 64 + k + 2 >= valid) cc = -INFINITY;
+        if (h * 64 + k + 3 >= valid) d = -INFINITY;
+      }
+      mx0 = fmaxf(mx0, a); mx1 = fmaxf(mx1, b); mx2 = fmaxf(mx2, cc); mx3 = fmaxf(mx3, d);
+    }
+  }
+  return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+}
+
+// P = exp2(s * c - m_ref) as packed fp16 (keys 2k, 2k+1 in TMEM column k), written over the scores: chunk q reads
+// score columns [32q, 32q+32) and writes P columns [16q, 16q+16), always behind the read pointer. kPolyOf8 of every
+// 8 exponentials run on the FMA pipes. Returns the row sum of the (unrounded) exponentials.
+template <bool MASKED>
+__device__ __forceinline__ float exp_pass128(uint32_t t_S, float c, float neg_m, int valid) {
+  float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+  uint32_t sa[32], sb[32];
+  tmem_ld32(t_S, sa);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t* cur = (q & 1) ? sb : sa;
+    uint32_t* nxt = (q & 1) ? sa : sb;
+    tmem_ld_wait();
+    if (q < 3) tmem_ld32(t_S + (q + 1) * 32, nxt);     // prefetch the next chunk while this one is exponentiated
+    uint32_t pk[16];
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) {
+      const float x0 = fmaf(__uint_as_float(cur[k]), c, neg_m), x1 = fmaf(__uint_as_float(cur[k + 1]), c, neg_m);
+      const float x2 = fmaf(__uint_as_float(cur[k + 2]), c, neg_m), x3 = fmaf(__uint_as_float(cur[k + 3]), c, neg_m);
+      // (k & 4): elements 4..7 of every 8; the first kPolyOf8 of those take the polynomial path
+      float p0 = ((k & 4) && kPolyOf8 > 0) ? poly_exp2(x0) : fast_exp2(x0);
+      float p1 = ((k & 4) && kPolyOf8 > 1) ? poly_exp2(x1) : fast_exp2(x1);
+      float p2 = ((k & 4) && kPolyOf8 > 2) ? poly_exp2(x2) : fast_exp2(x2);
+      float p3 = ((k & 4) && kPolyOf8 > 3) ? poly_exp2(x3) : fast_exp2(x3);
+      if (MASKED) {
+        if (q * 32 + k >= valid) p0 = 0.f;
+        if (q * 32 + k + 1 >= valid) p1 = 0.f;
+        if (q * 32 + k + 2 >= valid) p2 = 0.f;
+        if (q * 32 + k + 3 >= valid) p3 = 0.f;
+      }
+      rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
+      pk[k >> 1] = pack_half2(p0, p1);
+      pk[(k >> 1) + 1] = pack_half2(p2, p3);
+    }
+    tmem_st16(t_S + q * 16, pk);
+  }
+  return (rs0 + rs1) + (rs2 + rs3);
 }
 
 template <bool ADAIN>
@@ -246,6 +321,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     const uint32_t t_A = tmem_base + kTmemAcc + i * kD + lane_addr;
     const float c = p.scale_log2;
 
+    // The two warpgroups take turns on the MUFU-bound exp pass (named barriers 1 and 2): while one exponentiates, the
+    // other waits for / reads its next scores and the tensor pipe runs its PV and QK^T.
+    if (kPingPong && i == 1) named_bar_arrive(1, 256);
     float m_ref = -INFINITY;     // reference max (log2 units) every stored exponential is relative to
     float l_seg = 0.f;           // row sum of the current segment
     float l_tot = 0.f;           // row sum of the finished segments (AdaIN path)
@@ -261,27 +339,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
 
       mbar_wait(&s_full[i], jj & 1);
       tc_fence_after();
-      uint32_t sr[128];
-      tmem_ld32(t_S, sr);
-      tmem_ld32(t_S + 32, sr + 32);
-      tmem_ld32(t_S + 64, sr + 64);
-      tmem_ld32(t_S + 96, sr + 96);
-      tmem_ld_wait();
-
-      if (valid < kKT) {
-#pragma unroll
-        for (int k = 0; k < 128; ++k)
-          if (k >= valid) sr[k] = 0xff800000u;        // -inf: exp2 -> 0, ignored by the max
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < 128; k += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sr[k]));
-        mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sr[k + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sr[k + 3]));
-      }
-      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+      // pass 1: row max (TMEM reads are cheap; keeping all 128 scores live across both passes would spill)
+      const float m_new = (valid < kKT ? row_max128<true>(t_S, valid) : row_max128<false>(t_S, valid)) * c;
 
       if (jj == 0) {
         m_ref = m_new;                                // nothing accumulated yet
@@ -300,25 +359,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
         }
       }
 
-      // P = exp2(s * c - m_ref) as packed fp16 (keys 2c, 2c+1 in TMEM column c), written over the scores just read
-      const float neg_m = -m_ref;
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int k = 0; k < 64; k += 4) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[h * 64 + k]), c, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[h * 64 + k + 1]), c, neg_m));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(sr[h * 64 + k + 2]), c, neg_m));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(sr[h * 64 + k + 3]), c, neg_m));
-          rs0 += p0; rs1 += p1; rs2 += p2; rs3 += p3;
-          pk[k >> 1] = pack_half2(p0, p1);
-          pk[(k >> 1) + 1] = pack_half2(p2, p3);
-        }
-        tmem_st32(t_S + h * 32, pk);
-      }
-      l_seg += (rs0 + rs1) + (rs2 + rs3);
+      // pass 2: exponentials -> P (TMEM), row sum
+      if (kPingPong) named_bar_sync(1 + i, 256);            // my turn on the MUFU pipe
+      l_seg += valid < kKT ? exp_pass128<true>(t_S, c, -m_ref, valid) : exp_pass128<false>(t_S, c, -m_ref, valid);
+      if (kPingPong && !(i == 1 && jj == n_tiles - 1)) named_bar_arrive(1 + (i ^ 1), 256);   // hand the MUFU pipe over
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[i]);

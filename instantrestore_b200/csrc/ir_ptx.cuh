@@ -219,6 +219,26 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// exp2 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (relative error 7.5e-5, below one fp16 ulp), exponent patched in with an integer add.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: the low mantissa bits of t now hold n
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.055171653628349304f, f, 0.2426111251115799f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// named barriers (id 1..15) between subsets of warps
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
