@@ -79,6 +79,8 @@ typedef struct {
   int out_row_stride;
   int tile_n;  /* 0 = auto; else 64, 128, 160 or 256 */
   int split_k; /* 0 = auto; 1 = off; 2, 4, 8 = K split over a thread-block cluster of that size (DSMEM reduce) */
+  int pad_hi_only; /* 3x3 stride 2 only: 0 = zero padding 1 on every side; 1 = one row/column of zeros at the
+                      bottom/right only (diffusers Downsample2D(padding=0) of the VAE encoder) */
 } ir_conv_gemm_params;
 int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
 
@@ -225,6 +227,24 @@ int ir_latent_in(const float* x, const float* noise, float a, float s, void* out
                  int c_pad, ir_stream_t stream);
 int ir_latent_out(const void* eps, int eps_row_stride, const float* x, const float* noise, float a, float s, float* out,
                   int batch, int c, int hw, ir_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * VAE side of the pipeline (reference pix2pix_turbo.py:245,291,333; models/model.py:15-63).
+ * ir_softmax_rows — in-place row softmax of an fp16 [rows, cols] score matrix, fp32 math: p = softmax(x * scale).
+ *   (the VAE mid-block attention is single-head with head_dim 512: scores are materialised by ir_conv_gemm exactly as
+ *   the reference's baddbmm does, diffusers Attention.get_attention_scores.)
+ * ir_image_in  — fp16 or fp32 NCHW image [batch, c, hw] -> fp16 channel-last [batch, hw, c_pad] (zero-padded).
+ * ir_image_out — fp16 channel-last [batch, hw, >= c] (row stride y_row_stride) -> NCHW clamp(lo, hi), fp16 or fp32.
+ * ir_vae_sample — DiagonalGaussianDistribution.sample() * scaling_factor with the normal draw injected:
+ *   moments fp16 channel-last [batch, hw, >= 2c] (mean | logvar); out[b,c,hw] = (mean + exp(0.5*clamp(logvar,-30,20))
+ *   * eps[b,c,hw]) * scale, fp32 NCHW; eps may be NULL (mode).
+ */
+int ir_softmax_rows(void* x, int rows, int cols, int row_stride, float scale, ir_stream_t stream);
+int ir_image_in(const void* x, int x_is_fp32, void* out, int batch, int c, int hw, int c_pad, ir_stream_t stream);
+int ir_image_out(const void* y, int y_row_stride, float lo, float hi, void* out, int out_is_fp32, int batch, int c,
+                 int hw, ir_stream_t stream);
+int ir_vae_sample(const void* moments, int m_row_stride, const float* eps, float scale, float* out, int batch, int c,
+                  int hw, ir_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "ir_shared_attn_workspace_bytes",
     "ir_groupnorm", "ir_groupnorm_workspace_bytes", "ir_layernorm", "ir_adain_coeffs", "ir_adain_workspace_bytes",
     "ir_concat_freeu", "ir_upsample_nearest2x", "ir_latent_in", "ir_latent_out",
+    "ir_softmax_rows", "ir_image_in", "ir_image_out", "ir_vae_sample",
 ]
 
 
@@ -29,7 +30,7 @@ class ConvGemmParams(C.Structure):
         ("a_row_stride", C.c_int), ("ksize", C.c_int), ("stride", C.c_int),
         ("w", C.c_void_p), ("c_out", C.c_int), ("bias", C.c_void_p), ("residual", C.c_void_p),
         ("res_row_stride", C.c_int), ("act", C.c_int), ("out", C.c_void_p), ("out_row_stride", C.c_int),
-        ("tile_n", C.c_int), ("split_k", C.c_int),
+        ("tile_n", C.c_int), ("split_k", C.c_int), ("pad_hi_only", C.c_int),
     ]
 
 
@@ -110,6 +111,12 @@ def load() -> C.CDLL:
                                  C.c_int, C.c_void_p]
     lib.ir_latent_out.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int,
                                   C.c_int, C.c_int, C.c_void_p]
+    lib.ir_softmax_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    lib.ir_image_in.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.ir_image_out.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p]
+    lib.ir_vae_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p]
     lib.ir_debug_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_uint] * 6 + [C.c_void_p]
     _lib = lib
     return lib
@@ -204,7 +211,7 @@ def _scratch(device, nbytes: int) -> torch.Tensor:
 def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: int, c_in: int, ksize: int = 1,
               stride: int = 1, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
               act: int = IR_ACT_NONE, out: torch.Tensor | None = None, tile_n: int = 0, split_k: int = 0,
-              a_row_stride: int | None = None) -> torch.Tensor:
+              a_row_stride: int | None = None, pad_hi_only: bool = False) -> torch.Tensor:
     """a: fp16 channel-last [batch*h_in*w_in, >=c_in]; w: fp16 [c_out, ksize*ksize*c_in]."""
     _h(a, "a"); _h(w, "w"); _f(bias, "bias")
     c_out = w.shape[0]
@@ -218,7 +225,8 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
         a_row_stride=a_row_stride if a_row_stride is not None else a.stride(-2),
         ksize=ksize, stride=stride, w=ptr(w), c_out=c_out, bias=ptr(bias),
         residual=ptr(residual), res_row_stride=residual.stride(-2) if residual is not None else 0,
-        act=act, out=ptr(out), out_row_stride=out.stride(-2), tile_n=tile_n, split_k=split_k)
+        act=act, out=ptr(out), out_row_stride=out.stride(-2), tile_n=tile_n, split_k=split_k,
+        pad_hi_only=int(pad_hi_only))
     k_tot = ksize * ksize * c_in
     _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks{ksize}s{stride}", 2.0 * m * k_tot * c_out,
          2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out),
@@ -359,4 +367,47 @@ def latent_out(eps: torch.Tensor, x: torch.Tensor, noise: torch.Tensor | None, a
         out = torch.empty_like(x)
     check(load().ir_latent_out(ptr(eps), eps.stride(-2), ptr(x), ptr(noise), a, s, ptr(out), b, c, hh * ww,
                                stream_ptr()), "ir_latent_out")
+    return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float) -> torch.Tensor:
+    """In-place softmax(x * scale) over the last dim of an fp16 [rows, cols] matrix (fp32 math)."""
+    _h(x, "x")
+    rows, cols = x.shape
+    _run("ir_softmax_rows", f"r{rows}_c{cols}", 0.0, 4.0 * rows * cols, load().ir_softmax_rows, ptr(x), rows, cols,
+         x.stride(0), scale, stream_ptr())
+    return x
+
+
+def image_in(x: torch.Tensor, *, c_pad: int = 64, out: torch.Tensor | None = None) -> torch.Tensor:
+    """x: fp16/fp32 NCHW image batch -> fp16 channel-last [B*H*W, c_pad] (zero-padded channels)."""
+    if not x.is_cuda or not x.is_contiguous() or x.dtype not in (torch.float16, torch.float32):
+        raise TypeError("image_in: expected a contiguous CUDA fp16/fp32 NCHW tensor")
+    b, c, hh, ww = x.shape
+    if out is None:
+        out = torch.empty((b * hh * ww, c_pad), dtype=torch.float16, device=x.device)
+    _run("ir_image_in", f"b{b}_hw{hh * ww}", 0.0, b * hh * ww * (c * x.element_size() + 2.0 * c_pad), load().ir_image_in,
+         ptr(x), int(x.dtype == torch.float32), ptr(out), b, c, hh * ww, c_pad, stream_ptr())
+    return out
+
+
+def image_out(y: torch.Tensor, *, batch: int, c: int, h: int, w: int, lo: float = -1.0, hi: float = 1.0,
+              dtype: torch.dtype = torch.float16, out: torch.Tensor | None = None) -> torch.Tensor:
+    """y: fp16 channel-last [B*H*W, >=c] -> NCHW clamp(lo, hi)."""
+    _h(y, "y")
+    if out is None:
+        out = torch.empty((batch, c, h, w), dtype=dtype, device=y.device)
+    _run("ir_image_out", f"b{batch}_hw{h * w}", 0.0, batch * h * w * c * (2.0 + out.element_size()), load().ir_image_out,
+         ptr(y), y.stride(-2), lo, hi, ptr(out), int(out.dtype == torch.float32), batch, c, h * w, stream_ptr())
+    return out
+
+
+def vae_sample(moments: torch.Tensor, eps: torch.Tensor | None, scale: float, *, batch: int, c: int, h: int, w: int,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+    """moments: fp16 channel-last [B*H*W, >=2c] (mean | logvar); eps fp32 NCHW or None -> fp32 NCHW latent * scale."""
+    _h(moments, "moments"); _f(eps, "eps")
+    if out is None:
+        out = torch.empty((batch, c, h, w), dtype=torch.float32, device=moments.device)
+    check(load().ir_vae_sample(ptr(moments), moments.stride(-2), ptr(eps), scale, ptr(out), batch, c, h * w, stream_ptr()),
+          "ir_vae_sample")
     return out

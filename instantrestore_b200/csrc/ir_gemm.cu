@@ -344,6 +344,8 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
   if (p->c_in <= 0 || p->c_in % 64 != 0) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: c_in=%d must be a positive multiple of 64", p->c_in);
   if (!((p->ksize == 1 && p->stride == 1) || (p->ksize == 3 && (p->stride == 1 || p->stride == 2))))
     return set_error(IR_ERR_SHAPE, "ir_conv_gemm: unsupported ksize=%d stride=%d", p->ksize, p->stride);
+  if (p->pad_hi_only && !(p->ksize == 3 && p->stride == 2))
+    return set_error(IR_ERR_ARG, "ir_conv_gemm: pad_hi_only applies to 3x3 stride-2 convolutions");
   if (p->a_row_stride < p->c_in || p->a_row_stride % 8 != 0) return set_error(IR_ERR_ALIGN, "ir_conv_gemm: a_row_stride=%d", p->a_row_stride);
   if (p->batch <= 0 || p->h_in <= 0 || p->w_in <= 0 || p->c_out <= 0) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: non-positive dims");
   const bool geglu = p->act == IR_ACT_GEGLU;
@@ -407,7 +409,10 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
           kp.tap_dy[ky * 3 + kx] = static_cast<int8_t>(ky - 1);
         }
     } else {
-      // input row 2i + ky - 1: ky=0 -> odd phase, offset -1; ky=1 -> even phase; ky=2 -> odd phase, offset 0
+      // pad_lo = 1 (symmetric padding 1): input row 2i + ky - 1: ky=0 -> odd phase, offset -1; ky=1 -> even phase;
+      // ky=2 -> odd phase, offset 0.  pad_lo = 0 (diffusers Downsample2D(padding=0): F.pad (0,1,0,1) then a
+      // valid conv): input row 2i + ky: ky=0 -> even phase; ky=1 -> odd phase; ky=2 -> even phase, offset +1
+      // (the row past the bottom/right edge is TMA zero fill).
       uint64_t dims[4] = {static_cast<uint64_t>(p->c_in), static_cast<uint64_t>(w_out), static_cast<uint64_t>(h_out),
                           static_cast<uint64_t>(p->batch)};
       uint64_t str[3] = {rs * 2, rs * p->w_in * 2, rs * p->w_in * p->h_in};
@@ -418,10 +423,17 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
         }
       for (int ky = 0; ky < 3; ++ky)
         for (int kx = 0; kx < 3; ++kx) {
-          const int pr = (ky == 1) ? 0 : 1, pc = (kx == 1) ? 0 : 1;
-          kp.tap_map[ky * 3 + kx] = static_cast<int8_t>(pr * 2 + pc);
-          kp.tap_dx[ky * 3 + kx] = static_cast<int8_t>(kx == 0 ? -1 : 0);
-          kp.tap_dy[ky * 3 + kx] = static_cast<int8_t>(ky == 0 ? -1 : 0);
+          if (p->pad_hi_only) {
+            const int pr = (ky == 1) ? 1 : 0, pc = (kx == 1) ? 1 : 0;
+            kp.tap_map[ky * 3 + kx] = static_cast<int8_t>(pr * 2 + pc);
+            kp.tap_dx[ky * 3 + kx] = static_cast<int8_t>(kx == 2 ? 1 : 0);
+            kp.tap_dy[ky * 3 + kx] = static_cast<int8_t>(ky == 2 ? 1 : 0);
+          } else {
+            const int pr = (ky == 1) ? 0 : 1, pc = (kx == 1) ? 0 : 1;
+            kp.tap_map[ky * 3 + kx] = static_cast<int8_t>(pr * 2 + pc);
+            kp.tap_dx[ky * 3 + kx] = static_cast<int8_t>(kx == 0 ? -1 : 0);
+            kp.tap_dy[ky * 3 + kx] = static_cast<int8_t>(ky == 0 ? -1 : 0);
+          }
         }
     }
   }

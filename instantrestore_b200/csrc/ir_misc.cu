@@ -259,6 +259,128 @@ __global__ void latent_out_kernel(const __half* __restrict__ eps, int eps_stride
   out[i] = (xt - s * e) / a;
 }
 
+// ------------------------------------------------------------------------------------------------ VAE helpers
+// In-place row softmax, one CTA (256 threads) per row; the row (<= 8192 fp16) is held in registers between passes.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, int cols, int row_stride, float scale_log2) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  __half* xr = x + static_cast<size_t>(blockIdx.x) * row_stride;
+  const int nvec = cols >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kMaxVec = 4;                       // 256 threads x 4 vectors x 8 = 8192 columns
+  uint4 v[kMaxVec];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < nvec) {
+      v[k] = *reinterpret_cast<const uint4*>(xr + (i << 3));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        mx = fmaxf(mx, fmaxf(f.x, f.y));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    bc = m;
+  }
+  __syncthreads();
+  const float m = bc * scale_log2;
+  float e[kMaxVec][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < nvec) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        e[k][2 * j] = fast_exp2(fmaf(f.x, scale_log2, -m));
+        e[k][2 * j + 1] = fast_exp2(fmaf(f.y, scale_log2, -m));
+        sum += e[k][2 * j] + e[k][2 * j + 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    bc = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = bc;
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < nvec)
+      *reinterpret_cast<uint4*>(xr + (i << 3)) =
+          make_uint4(pack_half2(e[k][0] * inv, e[k][1] * inv), pack_half2(e[k][2] * inv, e[k][3] * inv),
+                     pack_half2(e[k][4] * inv, e[k][5] * inv), pack_half2(e[k][6] * inv, e[k][7] * inv));
+  }
+}
+
+template <typename T>
+__global__ void image_in_kernel(const T* __restrict__ x, __half* __restrict__ out, int c, int hw, int c_pad, long total_px) {
+  // one thread per pixel: reads c planes (coalesced across threads), writes c_pad halfs (16-byte stores)
+  const long px = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (px >= total_px) return;
+  const long b = px / hw, p = px - b * hw;
+  __half* o = out + px * c_pad;
+  for (int c0 = 0; c0 < c_pad; c0 += 8) {
+    __half h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = c0 + j;
+      h[j] = ch < c ? __float2half_rn(static_cast<float>(x[(b * c + ch) * hw + p])) : __float2half_rn(0.f);
+    }
+    *reinterpret_cast<uint4*>(o + c0) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+template <typename T>
+__global__ void image_out_kernel(const __half* __restrict__ y, int stride, float lo, float hi, T* __restrict__ out, int c,
+                                 int hw, long total) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;   // NCHW index
+  if (i >= total) return;
+  const int p = static_cast<int>(i % hw);
+  const long bc = i / hw;
+  const int ch = static_cast<int>(bc % c);
+  const long b = bc / c;
+  const float v = __half2float(y[(b * hw + p) * stride + ch]);
+  out[i] = static_cast<T>(fminf(fmaxf(v, lo), hi));
+}
+
+__global__ void vae_sample_kernel(const __half* __restrict__ mom, int stride, const float* __restrict__ eps, float scale,
+                                  float* __restrict__ out, int c, int hw, long total) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;   // NCHW index
+  if (i >= total) return;
+  const int p = static_cast<int>(i % hw);
+  const long bc = i / hw;
+  const int ch = static_cast<int>(bc % c);
+  const long b = bc / c;
+  const __half* m = mom + (b * hw + p) * stride;
+  const float mean = __half2float(m[ch]);
+  float v = mean;
+  if (eps) {
+    const float logvar = fminf(fmaxf(__half2float(m[c + ch]), -30.0f), 20.0f);
+    v = fmaf(__expf(0.5f * logvar), eps[i], mean);
+  }
+  out[i] = v * scale;
+}
+
 static inline int grid_for(long total, int block, int cap = 148 * 16) {
   long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -364,5 +486,60 @@ extern "C" int ir_latent_out(const void* eps, int eps_row_stride, const float* x
   latent_out_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __half*>(eps), eps_row_stride, x, noise, a, s, out, c, hw, total);
   IR_CUDA_LAUNCH_CHECK("latent_out launch");
+  return 0;
+}
+
+extern "C" int ir_softmax_rows(void* x, int rows, int cols, int row_stride, float scale, ir_stream_t stream_) {
+  using namespace ir;
+  if (!x) return set_error(IR_ERR_ARG, "ir_softmax_rows: NULL argument");
+  if (int rc = check_arch()) return rc;
+  if (rows <= 0 || cols <= 0 || cols % 8 != 0 || cols > 8192 || row_stride % 8 != 0 || row_stride < cols)
+    return set_error(IR_ERR_SHAPE, "ir_softmax_rows: rows=%d cols=%d stride=%d (cols %% 8 == 0, cols <= 8192)", rows, cols, row_stride);
+  if (reinterpret_cast<uintptr_t>(x) & 15) return set_error(IR_ERR_ALIGN, "ir_softmax_rows: pointer not 16-byte aligned");
+  softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<__half*>(x), cols, row_stride,
+                                                                            scale * 1.4426950408889634f);
+  IR_CUDA_LAUNCH_CHECK("softmax_rows launch");
+  return 0;
+}
+
+extern "C" int ir_image_in(const void* x, int x_is_fp32, void* out, int batch, int c, int hw, int c_pad, ir_stream_t stream_) {
+  using namespace ir;
+  if (!x || !out) return set_error(IR_ERR_ARG, "ir_image_in: NULL argument");
+  if (int rc = check_arch()) return rc;
+  if (c_pad < c || c_pad % 8 != 0 || batch <= 0 || c <= 0 || hw <= 0) return set_error(IR_ERR_SHAPE, "ir_image_in: c=%d c_pad=%d", c, c_pad);
+  const long total_px = static_cast<long>(batch) * hw;
+  const int blocks = static_cast<int>((total_px + 255) / 256);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (x_is_fp32) image_in_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<__half*>(out), c, hw, c_pad, total_px);
+  else image_in_kernel<__half><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(out), c, hw, c_pad, total_px);
+  IR_CUDA_LAUNCH_CHECK("image_in launch");
+  return 0;
+}
+
+extern "C" int ir_image_out(const void* y, int y_row_stride, float lo, float hi, void* out, int out_is_fp32, int batch, int c,
+                            int hw, ir_stream_t stream_) {
+  using namespace ir;
+  if (!y || !out) return set_error(IR_ERR_ARG, "ir_image_out: NULL argument");
+  if (int rc = check_arch()) return rc;
+  if (y_row_stride < c || batch <= 0 || c <= 0 || hw <= 0) return set_error(IR_ERR_SHAPE, "ir_image_out: c=%d stride=%d", c, y_row_stride);
+  const long total = static_cast<long>(batch) * c * hw;
+  const int blocks = static_cast<int>((total + 255) / 256);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (out_is_fp32) image_out_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(y), y_row_stride, lo, hi, static_cast<float*>(out), c, hw, total);
+  else image_out_kernel<__half><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(y), y_row_stride, lo, hi, static_cast<__half*>(out), c, hw, total);
+  IR_CUDA_LAUNCH_CHECK("image_out launch");
+  return 0;
+}
+
+extern "C" int ir_vae_sample(const void* moments, int m_row_stride, const float* eps, float scale, float* out, int batch, int c,
+                             int hw, ir_stream_t stream_) {
+  using namespace ir;
+  if (!moments || !out) return set_error(IR_ERR_ARG, "ir_vae_sample: NULL argument");
+  if (int rc = check_arch()) return rc;
+  if (m_row_stride < 2 * c || batch <= 0 || c <= 0 || hw <= 0) return set_error(IR_ERR_SHAPE, "ir_vae_sample: c=%d stride=%d", c, m_row_stride);
+  const long total = static_cast<long>(batch) * c * hw;
+  vae_sample_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __half*>(moments), m_row_stride, eps, scale, out, c, hw, total);
+  IR_CUDA_LAUNCH_CHECK("vae_sample launch");
   return 0;
 }

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 static void gn_plan(int batch, int hw, int* slabs, int* rows_per_slab) {
   // <= 32 slabs per batch entry: the apply kernel's prologue merges them (8 lanes x 4 dependent steps); even at
   // batch 1 thirty-two CTAs pull a <= 8 MB activation out of L2/HBM in a couple of microseconds.
-  int want = 32;
+  int want = hw >= 65536 ? 256 : (hw >= 16384 ? 128 : 32);   // VAE-resolution tensors need more CTAs to reach HBM speed
   int max_slabs = hw / 8 > 0 ? hw / 8 : 1;         // >= 8 rows per slab
   if (want > max_slabs) want = max_slabs;
   (void)batch;
@@ -259,7 +259,7 @@ static void gn_plan(int batch, int hw, int* slabs, int* rows_per_slab) {
 }
 
 extern "C" size_t ir_groupnorm_workspace_bytes(int batch, int groups) {
-  return static_cast<size_t>(batch) * 32 * groups * sizeof(float2);   // up to 32 slabs per batch entry
+  return static_cast<size_t>(batch) * 256 * groups * sizeof(float2);   // up to 256 slabs per batch entry
 }
 
 extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {

@@ -1,0 +1,164 @@
+"""Inference entry with the reference's API (face_replace/inference/test.py:38-163):
+
+    predictor = Predictor(checkpoint_path)
+    pred_image, visualization, attn_probs = predictor.predict(input_img, cond_imgs, target_img=None)
+
+`checkpoint_path` is a reference training checkpoint: `torch.load` dict {'state_dict', 'cfg'[, 'optimizer']}
+(written by face_replace/training/coach.py:712-718) with the whole FaceReplaceModel under the `net.` prefix
+(`net.module.` under DDP, stripped like test.py:49): net.unet.*, net.original_unet.*, net.vae.*, net.original_vae.*,
+net.text_encoder.*. LoRA leaves (peft key layout) are merged at load.
+
+The caption encoding is a constant of the model (pix2pix_turbo.py:100-106) but is NOT stored in the state_dict; it is
+taken from, in order: the `caption_enc` argument, a 'caption_enc' entry of the checkpoint dict, or recomputed with
+transformers' CLIPTextModel from net.text_encoder.* when the sd-turbo tokenizer files are available locally.
+"""
+from __future__ import annotations
+
+import logging
+from pathlib import Path
+from types import SimpleNamespace
+from typing import Any, List, Optional
+
+import numpy as np
+import torch
+from PIL import Image
+
+from .pipeline import ModelFlags, RestorePipeline
+
+PROMPT = "A high-quality photo of a person; professional, 8k"       # pix2pix_turbo.py:100
+MODEL_NAME = "stabilityai/sd-turbo"                                    # pix2pix_turbo.py:17
+
+
+def decode_cfg(cfg: Any) -> SimpleNamespace:
+    """Minimal stand-in for pyrallis.decode(TrainConfig, ckpt['cfg']) (test.py:43): nested dict -> attribute access,
+    with the ModelConfig / DataConfig defaults the inference path reads (configs/train_config.py:111,118-147)."""
+    cfg = dict(cfg or {})
+    model = dict(net_type="pix2pix_turbo", lora_rank_unet=16, lora_rank_vae=16, condition_on_face_embeds=False,
+                 use_shared_attention=True, noise_timestep=249, use_shortcuts=False, train_reference_networks=False,
+                 use_adain=False, train_input=True)
+    model.update(cfg.get("model", {}) or {})
+    data = dict(max_conditioning_images=4)
+    data.update({k: v for k, v in (cfg.get("data", {}) or {}).items() if k in data})
+    return SimpleNamespace(model=SimpleNamespace(**model), data=SimpleNamespace(**data), raw=cfg)
+
+
+def split_state_dict(sd: dict) -> dict:
+    """'net.<part>.<key>' (optionally with DDP's '.module.') -> {part: {key: tensor}}."""
+    parts: dict = {}
+    for k, v in sd.items():
+        k = k.replace(".module.", ".")
+        if k.startswith("module."):
+            k = k[len("module."):]
+        if k.startswith("net."):
+            k = k[len("net."):]
+        head, _, rest = k.partition(".")
+        parts.setdefault(head, {})[rest] = v
+    return parts
+
+
+def image_to_tensor(img: Image.Image, size: int = 512) -> torch.Tensor:
+    """test.py:54-59: Resize(size, LANCZOS) (shorter side), CenterCrop(size), ToTensor, Normalize(0.5, 0.5) -> [-1, 1]."""
+    img = img.convert("RGB")
+    w, h = img.size
+    if (w, h) != (size, size):
+        if w <= h:
+            nw, nh = size, max(size, int(size * h / w))
+        else:
+            nw, nh = max(size, int(size * w / h)), size
+        img = img.resize((nw, nh), Image.LANCZOS)
+        left, top = int(round((nw - size) / 2.0)), int(round((nh - size) / 2.0))
+        img = img.crop((left, top, left + size, top + size))
+    x = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255.0)
+    return x.sub_(0.5).div_(0.5)
+
+
+def tensor2im(var: torch.Tensor, unnorm: bool = False) -> Image.Image:
+    """face_replace/training/utils/vis_utils.py:14-23."""
+    var = var.detach().float().cpu().clone()
+    if unnorm:
+        var = var * 0.5 + 0.5
+    arr = var.permute(1, 2, 0).numpy()
+    arr = np.clip(arr, 0.0, 1.0) * 255
+    return Image.fromarray(arr.astype("uint8"))
+
+
+def _caption_from_text_encoder(text_encoder_sd: dict, device) -> Optional[torch.Tensor]:
+    try:
+        from transformers import AutoTokenizer, CLIPTextConfig, CLIPTextModel
+        tok = AutoTokenizer.from_pretrained(MODEL_NAME, subfolder="tokenizer", local_files_only=True)
+        cfg = CLIPTextConfig.from_pretrained(MODEL_NAME, subfolder="text_encoder", local_files_only=True)
+        enc = CLIPTextModel(cfg)
+        enc.load_state_dict({k: v.float() for k, v in text_encoder_sd.items()}, strict=False)
+        ids = tok(PROMPT, max_length=tok.model_max_length, padding="max_length", truncation=True, return_tensors="pt").input_ids
+        with torch.no_grad():
+            return enc.eval()(ids)[0]
+    except Exception as e:  # noqa: BLE001
+        logging.info("caption encoding could not be recomputed (%s)", e)
+        return None
+
+
+class Predictor:
+    logging.basicConfig(level=logging.INFO)
+
+    def __init__(self, checkpoint_path: Path, caption_enc: Optional[torch.Tensor] = None, device="cuda:0",
+                 use_cuda_graph: bool = True):
+        ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+        self.cfg = decode_cfg(ckpt.get("cfg"))
+        m = self.cfg.model
+        if m.net_type != "pix2pix_turbo":
+            raise ValueError(f"Invalid encoder type: {m.net_type}")
+        parts = split_state_dict(ckpt["state_dict"])
+        for need in ("unet", "original_unet", "vae", "original_vae"):
+            if need not in parts:
+                raise KeyError(f"checkpoint has no net.{need}.* weights")
+        if caption_enc is None:
+            caption_enc = ckpt.get("caption_enc")
+        if caption_enc is None and "text_encoder" in parts:
+            caption_enc = _caption_from_text_encoder(parts["text_encoder"], device)
+        if caption_enc is None:
+            raise RuntimeError("caption_enc is not in the checkpoint and the sd-turbo tokenizer/text-encoder config are "
+                               "not available locally: pass Predictor(..., caption_enc=<(1,77,1024) tensor>)")
+        flags = ModelFlags(use_shared_attention=m.use_shared_attention, use_adain=m.use_adain, train_input=m.train_input,
+                           condition_on_face_embeds=m.condition_on_face_embeds, lora_rank_unet=m.lora_rank_unet)
+        self.max_conditioning_images = self.cfg.data.max_conditioning_images
+        self.dtype = torch.float16
+        self.device = torch.device(device)
+        logging.info("Moving model to GPU")
+        self.net = RestorePipeline(parts["unet"], parts["original_unet"], parts["vae"], parts["original_vae"], caption_enc,
+                                   flags, use_shortcuts=m.use_shortcuts, device=device, noise_timestep=249,
+                                   use_cuda_graph=use_cuda_graph)
+        self.net.noise_timesteps = [249]                                # test.py:62
+
+    def _apply_transforms_on_image_list(self, images: List[Image.Image]) -> List[torch.Tensor]:
+        return [image_to_tensor(im) for im in images]
+
+    def _forward_batch(self, input_images: torch.Tensor, conditioning_images: torch.Tensor, face_embeds=None,
+                       calc_attn_probs: bool = False):
+        if calc_attn_probs:
+            raise NotImplementedError("attention_probs are never materialised by the fused kernel")
+        valid_indices = torch.ones(input_images.size(0), dtype=torch.int64) * self.max_conditioning_images
+        x_pred, _, _ = self.net.forward(input_images.to(self.device, self.dtype),
+                                        conditioning_images=conditioning_images.to(self.device, self.dtype),
+                                        valid_indices=valid_indices)
+        return x_pred, None
+
+    def prepare_conditioning_images(self, cond_imgs: List[Image.Image]):
+        if self.cfg.model.condition_on_face_embeds:
+            raise NotImplementedError("condition_on_face_embeds is False in the released configs")
+        return torch.stack(self._apply_transforms_on_image_list(cond_imgs), dim=0), None, None
+
+    def parse_results(self, outputs: torch.Tensor, input_img: Image.Image, target_img: Optional[Image.Image] = None):
+        pred_image = [tensor2im(out, unnorm=True) for out in outputs][0]
+        to_join = [np.asarray(input_img.convert("RGB").resize(pred_image.size)), np.asarray(pred_image)]
+        if target_img is not None:
+            to_join.append(np.asarray(target_img.convert("RGB").resize(pred_image.size)))
+        return pred_image, Image.fromarray(np.concatenate(to_join, axis=0))
+
+    def predict(self, input_img: Image.Image, cond_imgs: Optional[List[Image.Image]] = None,
+                target_img: Optional[Image.Image] = None, calc_attn_probs: bool = False):
+        input_t = image_to_tensor(input_img).unsqueeze(0)
+        conds_t, _, _ = self.prepare_conditioning_images(cond_imgs)
+        outputs, attn_probs = self._forward_batch(input_t, conditioning_images=conds_t.unsqueeze(0),
+                                                  calc_attn_probs=calc_attn_probs)
+        pred_image, visualization = self.parse_results(outputs, input_img=input_img, target_img=target_img)
+        return pred_image, visualization, attn_probs

@@ -121,3 +121,113 @@ class RestoreEngine:
             st["out"] = self._step(st["enc"], st["refs"], st["noise_main"], st["noise_ref"], valid)
         st["graph"] = graph
         return st
+
+
+class RestorePipeline:
+    """Image-level single-step restoration: `Pix2Pix_Turbo.forward` of the reference (pix2pix_turbo.py:281-343) —
+    VAE-encode the degraded image and the reference images, reference-UNet K/V extraction, main UNet with the shared
+    attention, scheduler step, VAE decode with clamp — as one CUDA graph per (batch, n_ref) shape.
+
+        out, x_conds, attn_maps = pipe.forward(c_t, conditioning_images=cond, valid_indices=valid)
+
+    keeps the reference's call signature and return triple; `x_conds` (decoded reference latents,
+    pix2pix_turbo.py:277-278, never consumed at inference, test.py:100) and `attn_maps` are None. The four normal
+    draws of the reference forward (two VAE posterior samples :245,:291, two DDPM noises :248,:308) are drawn on the
+    device per call unless injected (`eps_main`, `eps_ref`, `noise_main`, `noise_ref`) — parity tests inject them.
+    """
+
+    def __init__(self, unet_sd, original_unet_sd, vae_sd, original_vae_sd, caption_enc: torch.Tensor, flags: ModelFlags,
+                 *, spec: Optional[UNetSpec] = None, vae_block_out_channels=(128, 256, 512, 512), use_shortcuts: bool = False,
+                 scaling_factor: float = 0.18215, device="cuda:0", noise_timestep: int = 249, use_cuda_graph: bool = True):
+        from .vae_engine import VaeEngine
+        self.engine = RestoreEngine(unet_sd, original_unet_sd, caption_enc, flags, spec=spec, device=device,
+                                    noise_timestep=noise_timestep, use_cuda_graph=False)
+        self.dev = self.engine.dev
+        self.flags = flags
+        self.vae = VaeEngine(vae_sd, self.dev, block_out_channels=vae_block_out_channels, use_shortcuts=use_shortcuts,
+                             scaling_factor=scaling_factor)
+        self.original_vae = (VaeEngine(original_vae_sd, self.dev, block_out_channels=vae_block_out_channels,
+                                       scaling_factor=scaling_factor, decoder=False)
+                             if flags.use_shared_attention else None)
+        self.use_cuda_graph = use_cuda_graph
+        self.out_dtype = torch.float16
+        self._graphs: Dict[Tuple, dict] = {}
+        self.noise_timesteps = [noise_timestep]        # attribute the reference entry sets (test.py:62)
+        self._gen = torch.Generator(device=self.dev)
+        self._gen.manual_seed(0)
+
+    def _step(self, c_t, cond, eps_main, eps_ref, noise_main, noise_ref, valid):
+        B = c_t.shape[0]
+        ref_lat = None
+        if cond is not None and self.original_vae is not None:
+            N = cond.shape[1]
+            lat = self.original_vae.encode(cond.reshape(B * N, *cond.shape[2:]), eps_ref)
+            ref_lat = lat.view(B, N, *lat.shape[1:])
+        enc = self.vae.encode(c_t, eps_main)                 # records the skip activations for the decoder
+        skips = self.vae.skip_acts
+        x0 = self.engine._step(enc, ref_lat, noise_main, noise_ref, valid)
+        return self.vae.decode(x0, skip_acts=skips, dtype=self.out_dtype)
+
+    @torch.no_grad()
+    def forward(self, c_t: torch.Tensor, face_embeds=None, conditioning_images: Optional[torch.Tensor] = None,
+                valid_indices=None, mask=None, return_self_attention_maps: bool = False, *, eps_main=None, eps_ref=None,
+                noise_main=None, noise_ref=None):
+        if face_embeds is not None:
+            raise NotImplementedError("condition_on_face_embeds is False in the released configs")
+        if return_self_attention_maps:
+            raise NotImplementedError("the fused attention kernel never materialises attention maps")
+        dev = self.dev
+        c_t = c_t.to(dev)
+        if c_t.dtype not in (torch.float16, torch.float32):
+            c_t = c_t.float()
+        B, _, H, W = c_t.shape
+        h, w = H // 8, W // 8
+        cond = None
+        if conditioning_images is not None and self.flags.use_shared_attention:
+            cond = conditioning_images.to(dev, c_t.dtype)
+        N = 0 if cond is None else cond.shape[1]
+        rnd = lambda *s: torch.randn(*s, device=dev, dtype=torch.float32, generator=self._gen)
+        eps_main = rnd(B, 4, h, w) if eps_main is None else eps_main.to(dev, torch.float32)
+        noise_main = rnd(B, 4, h, w) if noise_main is None else noise_main.to(dev, torch.float32)
+        if cond is not None:
+            eps_ref = rnd(B * N, 4, h, w) if eps_ref is None else eps_ref.to(dev, torch.float32)
+            noise_ref = rnd(B * N, 4, h, w) if noise_ref is None else noise_ref.to(dev, torch.float32)
+        else:
+            eps_ref = noise_ref = None
+        valid = None
+        if valid_indices is not None and cond is not None:
+            valid = [int(v) for v in valid_indices]
+            if all(v >= N for v in valid):
+                valid = None
+        ins = dict(c_t=c_t.contiguous(), cond=None if cond is None else cond.contiguous(), eps_main=eps_main.contiguous(),
+                   eps_ref=eps_ref, noise_main=noise_main.contiguous(), noise_ref=noise_ref)
+        if not self.use_cuda_graph:
+            out = self._step(ins["c_t"], ins["cond"], ins["eps_main"], ins["eps_ref"], ins["noise_main"], ins["noise_ref"], valid)
+            return out, None, None
+        key = (tuple(c_t.shape), c_t.dtype, None if cond is None else tuple(cond.shape), tuple(valid) if valid else None)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(ins, valid)
+            self._graphs[key] = g
+        for k, v in ins.items():
+            if v is not None:
+                g[k].copy_(v, non_blocking=True)
+        g["graph"].replay()
+        return g["out"], None, None
+
+    __call__ = forward
+
+    def _capture(self, ins, valid):
+        st = {k: (None if v is None else v.clone()) for k, v in ins.items()}
+        args = lambda: (st["c_t"], st["cond"], st["eps_main"], st["eps_ref"], st["noise_main"], st["noise_ref"], valid)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self._step(*args())                      # warm-up: allocator, function attributes
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            st["out"] = self._step(*args())
+        st["graph"] = graph
+        return st

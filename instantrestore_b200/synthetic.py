@@ -141,3 +141,116 @@ def synthetic_latents(batch: int, n_ref: int, size: int = 64, seed: int = 1234):
     noise_main = torch.randn(batch, 4, size, size, generator=g)
     noise_ref = torch.randn(batch * n_ref, 4, size, size, generator=g)
     return enc, refs, noise_main, noise_ref
+
+
+VAE_LORA_TARGETS = ("conv1", "conv2", "conv_in", "conv_shortcut", "conv", "conv_out", "to_k", "to_q", "to_v", "to_out.0")
+# reference pix2pix_turbo.py:150-153
+
+
+def vae_parameter_shapes(block_out_channels=(128, 256, 512, 512), layers_per_block: int = 2, latent_channels: int = 4,
+                         use_shortcuts: bool = False):
+    """(module path, weight shape, kind) for AutoencoderKL (sd-vae-ft-mse layout) incl. the reference's optional
+    decoder.skip_conv_{1..4} (pix2pix_turbo.py:46-52)."""
+    boc = tuple(block_out_channels)
+    rboc = list(reversed(boc))
+    out = []
+
+    def resnet(p, cin, cout):
+        out.append((f"{p}.norm1", (cin,), "norm"))
+        out.append((f"{p}.conv1", (cout, cin, 3, 3), "conv"))
+        out.append((f"{p}.norm2", (cout,), "norm"))
+        out.append((f"{p}.conv2", (cout, cout, 3, 3), "conv"))
+        if cin != cout:
+            out.append((f"{p}.conv_shortcut", (cout, cin, 1, 1), "conv"))
+
+    def mid(p, c):
+        a = f"{p}.attentions.0"
+        out.append((f"{a}.group_norm", (c,), "norm"))
+        for n in ("to_q", "to_k", "to_v", "to_out.0"):
+            out.append((f"{a}.{n}", (c, c), "linear"))
+        resnet(f"{p}.resnets.0", c, c)
+        resnet(f"{p}.resnets.1", c, c)
+
+    out.append(("encoder.conv_in", (boc[0], 3, 3, 3), "conv"))
+    ch = boc[0]
+    for i, c in enumerate(boc):
+        for j in range(layers_per_block):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", ch if j == 0 else c, c)
+        if i != len(boc) - 1:
+            out.append((f"encoder.down_blocks.{i}.downsamplers.0.conv", (c, c, 3, 3), "conv"))
+        ch = c
+    mid("encoder.mid_block", boc[-1])
+    out.append(("encoder.conv_norm_out", (boc[-1],), "norm"))
+    out.append(("encoder.conv_out", (2 * latent_channels, boc[-1], 3, 3), "conv"))
+    out.append(("decoder.conv_in", (boc[-1], latent_channels, 3, 3), "conv"))
+    mid("decoder.mid_block", boc[-1])
+    prev = rboc[0]
+    for i, c in enumerate(rboc):
+        for j in range(layers_per_block + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else c, c)
+        if i != len(boc) - 1:
+            out.append((f"decoder.up_blocks.{i}.upsamplers.0.conv", (c, c, 3, 3), "conv"))
+        prev = c
+    out.append(("decoder.conv_norm_out", (boc[0],), "norm"))
+    out.append(("decoder.conv_out", (3, boc[0], 3, 3), "conv"))
+    if use_shortcuts:
+        out.append(("decoder.skip_conv_1", (rboc[0], boc[2], 1, 1), "conv_nobias"))
+        out.append(("decoder.skip_conv_2", (rboc[0], boc[1], 1, 1), "conv_nobias"))
+        out.append(("decoder.skip_conv_3", (rboc[1], boc[0], 1, 1), "conv_nobias"))
+        out.append(("decoder.skip_conv_4", (rboc[2], boc[0], 1, 1), "conv_nobias"))
+    out.append(("quant_conv", (2 * latent_channels, 2 * latent_channels, 1, 1), "conv"))
+    out.append(("post_quant_conv", (latent_channels, latent_channels, 1, 1), "conv"))
+    return out
+
+
+def synthetic_vae_state_dict(block_out_channels=(128, 256, 512, 512), seed: int = 100, lora_rank: int = 0,
+                             use_shortcuts: bool = False, latent_channels: int = 4, lora_b_std: float = 0.02
+                             ) -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    targets = VAE_LORA_TARGETS + (("skip_conv_1", "skip_conv_2", "skip_conv_3", "skip_conv_4") if use_shortcuts else ())
+    for mod, shape, kind in vae_parameter_shapes(block_out_channels, 2, latent_channels, use_shortcuts):
+        if kind == "norm":
+            sd[f"{mod}.weight"] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+            sd[f"{mod}.bias"] = 0.1 * torch.randn(shape, generator=g)
+            continue
+        fan_in = 1
+        for d in shape[1:]:
+            fan_in *= d
+        w = torch.randn(shape, generator=g) * fan_in ** -0.5
+        b = None if kind == "conv_nobias" else 0.1 * torch.randn(shape[0], generator=g)
+        if mod == "quant_conv":                      # moderate posterior std
+            w[latent_channels:] *= 0.1
+            b[latent_channels:] = -3.0
+        if mod == "decoder.conv_out":
+            w *= 0.5
+        if mod.startswith("decoder.skip_conv"):
+            w *= 0.1
+        leaf = mod.rsplit(".", 1)[-1] if not mod.endswith("to_out.0") else "to_out.0"
+        wrap = lora_rank > 0 and (leaf in targets) and mod not in ("quant_conv", "post_quant_conv")
+        if wrap:
+            sd[f"{mod}.base_layer.weight"] = w
+            if b is not None:
+                sd[f"{mod}.base_layer.bias"] = b
+            a_shape = (lora_rank,) + tuple(shape[1:])
+            b_shape = (shape[0], lora_rank) + ((1, 1) if len(shape) == 4 else ())
+            sd[f"{mod}.lora_A.vae_skip.weight"] = torch.randn(a_shape, generator=g) / lora_rank
+            sd[f"{mod}.lora_B.vae_skip.weight"] = torch.randn(b_shape, generator=g) * lora_b_std
+        else:
+            sd[f"{mod}.weight"] = w
+            if b is not None:
+                sd[f"{mod}.bias"] = b
+    return sd
+
+
+def synthetic_images(batch: int, n_ref: int, size: int = 512, seed: int = 4321):
+    """Degraded image (B,3,S,S) and reference images (B,N,3,S,S) in [-1, 1]: smooth random fields + noise, fp16."""
+    g = torch.Generator().manual_seed(seed)
+
+    def img(*lead):
+        low = torch.randn(*lead, 3, size // 8, size // 8, generator=g)
+        x = torch.nn.functional.interpolate(low.flatten(0, -4), size=(size, size), mode="bilinear", align_corners=False)
+        x = x + 0.1 * torch.randn(x.shape, generator=g)
+        return (0.6 * x).clamp(-1, 1).reshape(*lead, 3, size, size).to(torch.float16)
+
+    return img(batch), img(batch, n_ref)

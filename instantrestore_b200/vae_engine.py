@@ -1,0 +1,205 @@
+"""B200 execution of the VAE on either side of the UNet (reference pix2pix_turbo.py:245 reference-image encode,
+:291 degraded-image encode, :333 decode; patched forwards models/model.py:15-63) on the C-ABI kernels.
+
+AutoencoderKL "stabilityai/sd-vae-ft-mse" geometry (block_out_channels 128/256/512/512, 2 resnets per encoder block,
+3 per decoder block, single-head 512-wide mid-block attention, GroupNorm eps 1e-6). Channel-last fp16 activations
+throughout. Folded once at load: LoRA (adapter "vae_skip", pix2pix_turbo.py:150-162) into the base weights;
+quant_conv (1x1) into encoder.conv_out; post_quant_conv (1x1) into decoder.conv_in — its bias becomes a constant
+shift of the latent (W_pq^-1 b_pq) so the zero padding of conv_in stays exact; the value-projection bias of the
+mid-block attention moves behind the softmax (rows sum to 1) into the output projection's bias.
+
+Mid-block attention (head_dim 512): scores = Q K^T are materialised in fp16 by ir_conv_gemm exactly like the
+reference's baddbmm under autocast (diffusers Attention.get_attention_scores), softmax-ed in place in fp32
+(ir_softmax_rows), and P V runs as a GEMM against V^T, which a GEMM with swapped operands produces directly.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import _lib as L
+from .weights import StateDictView, conv_weight_khwc
+
+GN_EPS = 1e-6
+GROUPS = 32
+
+
+class _Conv:
+    def __init__(self, w4: torch.Tensor, b: Optional[torch.Tensor], dev, stride: int = 1, c_in_pad: int = 0,
+                 pad_hi_only: bool = False):
+        self.ksize, self.stride, self.pad_hi_only = w4.shape[-1], stride, pad_hi_only
+        self.c_in, self.c_out = max(w4.shape[1], c_in_pad), w4.shape[0]
+        self.w = conv_weight_khwc(w4, c_in_pad).to(dev)
+        self.b = None if b is None else b.to(torch.float32).contiguous().to(dev)
+
+
+class _Lin:
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], dev):
+        self.w = w.to(torch.float16).contiguous().to(dev)
+        self.b = None if b is None else b.to(torch.float32).contiguous().to(dev)
+        self.c_out, self.c_in = self.w.shape
+
+
+class _Norm:
+    def __init__(self, v: StateDictView, name: str, dev):
+        self.g = v.param(f"{name}.weight").contiguous().to(dev)
+        self.b = v.param(f"{name}.bias").contiguous().to(dev)
+
+
+class VaeEngine:
+    def __init__(self, sd, device, *, block_out_channels=(128, 256, 512, 512), layers_per_block: int = 2,
+                 latent_channels: int = 4, scaling_factor: float = 0.18215, use_shortcuts: bool = False,
+                 encoder: bool = True, decoder: bool = True):
+        L.load()
+        v = sd if isinstance(sd, StateDictView) else StateDictView(sd)
+        self.dev = torch.device(device)
+        self.boc = tuple(block_out_channels)
+        self.lat = latent_channels
+        self.sf = scaling_factor
+        self.use_shortcuts = use_shortcuts
+        dev = self.dev
+        boc = self.boc
+        if encoder:
+            e = v.sub("encoder")
+            self.e_conv_in = _Conv(e.weight("conv_in"), e.bias("conv_in"), dev, c_in_pad=64)
+            self.e_down = []
+            for i in range(len(boc)):
+                blk = e.sub(f"down_blocks.{i}")
+                res = [self._load_resnet(blk.sub(f"resnets.{j}")) for j in range(layers_per_block)]
+                ds = None
+                if i != len(boc) - 1:
+                    d = blk.sub("downsamplers.0")
+                    ds = _Conv(d.weight("conv"), d.bias("conv"), dev, stride=2, pad_hi_only=True)
+                self.e_down.append((res, ds))
+            self.e_mid = self._load_mid(e.sub("mid_block"))
+            self.e_norm_out = _Norm(e, "conv_norm_out", dev)
+            # quant_conv (1x1, 2*lat -> 2*lat) folded into conv_out (3x3, C -> 2*lat)
+            wq = v.weight("quant_conv")[:, :, 0, 0]
+            w_out = torch.einsum("om,mikl->oikl", wq, e.weight("conv_out"))
+            b_out = wq @ e.bias("conv_out") + v.bias("quant_conv")
+            self.e_conv_out = _Conv(w_out, b_out, dev)
+        if decoder:
+            d = v.sub("decoder")
+            wpq = v.weight("post_quant_conv")[:, :, 0, 0]
+            w_in = torch.einsum("omkl,mi->oikl", d.weight("conv_in"), wpq)
+            self.d_conv_in = _Conv(w_in, d.bias("conv_in"), dev, c_in_pad=64)
+            self.d_latent_shift = torch.linalg.solve(wpq.double(), v.bias("post_quant_conv").double()).float().to(dev)
+            self.d_mid = self._load_mid(d.sub("mid_block"))
+            self.d_up = []
+            for i in range(len(boc)):
+                blk = d.sub(f"up_blocks.{i}")
+                res = [self._load_resnet(blk.sub(f"resnets.{j}")) for j in range(layers_per_block + 1)]
+                us = None
+                if i != len(boc) - 1:
+                    u = blk.sub("upsamplers.0")
+                    us = _Conv(u.weight("conv"), u.bias("conv"), dev)
+                self.d_up.append((res, us))
+            self.d_norm_out = _Norm(d, "conv_norm_out", dev)
+            self.d_conv_out = _Conv(d.weight("conv_out"), d.bias("conv_out"), dev)
+            self.d_skip = None
+            if use_shortcuts:   # reference pix2pix_turbo.py:46-52, model.py:41-49
+                self.d_skip = [_Lin(d.weight(f"skip_conv_{k}")[:, :, 0, 0], None, dev) for k in (1, 2, 3, 4)]
+        self.skip_acts: Optional[List[torch.Tensor]] = None
+
+    # ------------------------------------------------------------------------------------------ loading
+    def _load_resnet(self, v: StateDictView):
+        dev = self.dev
+        sc = None
+        if v.has("conv_shortcut.weight"):
+            sc = _Lin(v.weight("conv_shortcut")[:, :, 0, 0], v.bias("conv_shortcut"), dev)
+        return dict(norm1=_Norm(v, "norm1", dev), conv1=_Conv(v.weight("conv1"), v.bias("conv1"), dev),
+                    norm2=_Norm(v, "norm2", dev), conv2=_Conv(v.weight("conv2"), v.bias("conv2"), dev), shortcut=sc)
+
+    def _load_mid(self, v: StateDictView):
+        dev = self.dev
+        a = v.sub("attentions.0")
+        wq, wk, wv, wo = a.weight("to_q"), a.weight("to_k"), a.weight("to_v"), a.weight("to_out.0")
+        bq, bk, bv, bo = a.bias("to_q"), a.bias("to_k"), a.bias("to_v"), a.bias("to_out.0")
+        return dict(
+            res0=self._load_resnet(v.sub("resnets.0")), res1=self._load_resnet(v.sub("resnets.1")),
+            norm=_Norm(a, "group_norm", dev),
+            q=_Lin(wq, bq, dev), k=_Lin(wk, bk, dev),
+            v_t=wv.to(torch.float16).contiguous().to(dev),           # used as the A operand: V^T = W_v X^T
+            out=_Lin(wo, bo + wo @ bv, dev),                            # value bias moved behind the softmax
+            ch=wq.shape[0])
+
+    # ------------------------------------------------------------------------------------------ ops
+    def _conv(self, x, cv: _Conv, B, H, W, residual=None):
+        return L.conv_gemm(x, cv.w, batch=B, h_in=H, w_in=W, c_in=cv.c_in, ksize=cv.ksize, stride=cv.stride, bias=cv.b,
+                           residual=residual, pad_hi_only=cv.pad_hi_only)
+
+    def _lin(self, x, lin: _Lin, residual=None):
+        return L.conv_gemm(x, lin.w, batch=1, h_in=1, w_in=x.shape[0], c_in=lin.c_in, bias=lin.b, residual=residual)
+
+    def _gn(self, x, n: _Norm, B, HW, silu):
+        return L.groupnorm(x, n.g, n.b, batch=B, hw=HW, groups=GROUPS, eps=GN_EPS, silu=silu)
+
+    def _resnet(self, x, p, B, H, W):
+        t = self._gn(x, p["norm1"], B, H * W, True)
+        h = self._conv(t, p["conv1"], B, H, W)
+        t = self._gn(h, p["norm2"], B, H * W, True)
+        skip = x if p["shortcut"] is None else self._lin(x, p["shortcut"])
+        return self._conv(t, p["conv2"], B, H, W, residual=skip)
+
+    def _mid(self, x, p, B, H, W):
+        S, C = H * W, p["ch"]
+        x = self._resnet(x, p["res0"], B, H, W)
+        t = self._gn(x, p["norm"], B, S, False)
+        q_all, k_all = self._lin(t, p["q"]), self._lin(t, p["k"])           # [B*S, C] each
+        attn = torch.empty((B * S, C), dtype=torch.float16, device=x.device)
+        scale = float(C) ** -0.5
+        for b in range(B):
+            rows = slice(b * S, (b + 1) * S)
+            q, k, tb = q_all[rows], k_all[rows], t[rows]
+            scores = L.conv_gemm(q, k, batch=1, h_in=1, w_in=S, c_in=C)     # [S, S] = Q K^T (fp16, like baddbmm)
+            L.softmax_rows(scores, scale)
+            v_t = L.conv_gemm(p["v_t"], tb, batch=1, h_in=1, w_in=C, c_in=C)   # [C, S] = W_v X^T
+            L.conv_gemm(scores, v_t, batch=1, h_in=1, w_in=S, c_in=S, out=attn[rows])
+        x = self._lin(attn, p["out"], residual=x)
+        return self._resnet(x, p["res1"], B, H, W)
+
+    # ------------------------------------------------------------------------------------------ public
+    def encode(self, images: torch.Tensor, eps: Optional[torch.Tensor]) -> torch.Tensor:
+        """images: (B,3,H,W) fp16/fp32 CUDA in [-1,1]; eps: (B,4,H/8,W/8) fp32 normal draw or None (posterior mode).
+        Returns latent_dist.sample() * scaling_factor, fp32 NCHW. Records the skip activations (model.py:19-30)."""
+        B, _, H, W = images.shape
+        x = L.image_in(images.contiguous())
+        x = self._conv(x, self.e_conv_in, B, H, W)
+        skips = []
+        for res, ds in self.e_down:
+            skips.append((x, H, W))
+            for r in res:
+                x = self._resnet(x, r, B, H, W)
+            if ds is not None:
+                x = self._conv(x, ds, B, H, W)
+                H, W = H // 2, W // 2
+        x = self._mid(x, self.e_mid, B, H, W)
+        t = self._gn(x, self.e_norm_out, B, H * W, True)
+        mom = self._conv(t, self.e_conv_out, B, H, W)                    # [B*hw, 2*lat] mean | logvar
+        self.skip_acts = skips
+        return L.vae_sample(mom, eps, self.sf, batch=B, c=self.lat, h=H, w=W)
+
+    def decode(self, latents: torch.Tensor, skip_acts=None, dtype: torch.dtype = torch.float16) -> torch.Tensor:
+        """latents: (B,4,h,w) fp32 CUDA (already scaled by scaling_factor, as the UNet works on them); returns
+        vae.decode(latents / scaling_factor).sample.clamp(-1, 1) as NCHW `dtype` (pix2pix_turbo.py:333)."""
+        B, _, H, W = latents.shape
+        z = latents / self.sf + self.d_latent_shift.view(1, -1, 1, 1)
+        x = L.latent_in(z.contiguous(), None, 1.0, 0.0)
+        x = self._conv(x, self.d_conv_in, B, H, W)
+        x = self._mid(x, self.d_mid, B, H, W)
+        skips = skip_acts if skip_acts is not None else self.skip_acts
+        for i, (res, us) in enumerate(self.d_up):
+            if self.d_skip is not None:
+                s_act, sh, sw = skips[::-1][i]
+                assert (sh, sw) == (H, W)
+                x = self._lin(s_act, self.d_skip[i], residual=x)          # sample + skip_conv(act * gamma), gamma = 1
+            for r in res:
+                x = self._resnet(x, r, B, H, W)
+            if us is not None:
+                x = L.upsample_nearest2x(x, batch=B, h=H, w=W)
+                H, W = 2 * H, 2 * W
+                x = self._conv(x, us, B, H, W)
+        t = self._gn(x, self.d_norm_out, B, H * W, True)
+        y = self._conv(t, self.d_conv_out, B, H, W)                      # [B*HW, 3]
+        return L.image_out(y, batch=B, c=y.shape[1], h=H, w=W, dtype=dtype)

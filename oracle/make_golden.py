@@ -85,6 +85,51 @@ def build_pipeline(RefUNet, ref_ap, cfg, flags, lora_rank, seed=0):
     return LatentRestorePipeline(ref_unet, ref_orig, cap, flags, processors=ref_ap)
 
 
+VAE_CASES = [  # name, use_shortcuts, lora_rank
+    ("vae_tiny_plain", False, 0),
+    ("vae_tiny_lora", False, 4),
+    ("vae_tiny_shortcuts", True, 4),
+]
+IMAGE_CASES = [  # name, batch, n_ref, use_adain, train_input, lora_rank_unet, lora_rank_vae, use_shortcuts
+    ("image_tiny_final", 1, 2, True, False, 4, 4, False),
+    ("image_tiny_shortcuts", 2, 2, False, True, 0, 4, True),
+]
+IMAGE_SIZE, IMAGE_LATENT = 128, 16
+
+
+def bind_reference_vae_forwards(vae):
+    """Replaces the oracle's encoder/decoder forwards with the REFERENCE'S OWN face_replace/models/model.py
+    my_vae_encoder_fwd / my_vae_decoder_fwd (what pix2pix_turbo.py:40-41 does)."""
+    from face_replace.models import model as ref_model
+    vae.encoder.forward = ref_model.my_vae_encoder_fwd.__get__(vae.encoder, vae.encoder.__class__)
+    vae.decoder.forward = ref_model.my_vae_decoder_fwd.__get__(vae.decoder, vae.decoder.__class__)
+    return vae
+
+
+def tiny_image_models(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, reference_forwards, RefUNet=None, ref_ap=None):
+    from oracle import synth
+    from oracle.pipeline import ImageRestorePipeline, LatentRestorePipeline
+    from oracle.unet import UNetConfig
+    from oracle.vae import VaeConfig
+    ucfg = UNetConfig.tiny(sample_size=IMAGE_LATENT)
+    vcfg = VaeConfig.tiny()
+    vcfg.use_shortcuts = use_shortcuts
+    flags = synth.ModelFlags(use_adain=use_adain, train_input=train_input)
+    if RefUNet is not None:
+        latent = build_pipeline(RefUNet, ref_ap, ucfg, flags, lora_unet)
+    else:
+        unet = synth.make_unet(ucfg, seed=0, lora_rank=lora_unet)
+        orig = synth.make_unet(ucfg, seed=0)
+        latent = LatentRestorePipeline(unet, orig, synth.caption_embedding(ucfg.cross_attention_dim), flags)
+    vae = synth.make_vae(vcfg, seed=100, lora_rank=lora_vae)
+    ovae = synth.make_vae(VaeConfig.tiny(), seed=100)
+    if reference_forwards:
+        bind_reference_vae_forwards(vae)
+        bind_reference_vae_forwards(ovae)
+        ovae.decoder.ignore_skip = True
+    return ImageRestorePipeline(latent, vae, ovae)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-full", action="store_true")
@@ -131,6 +176,25 @@ def main():
         np.savez_compressed(GOLDEN / f"{name}.npz", x0=out.numpy(),
                             meta=np.array([batch, n_ref, int(use_adain), int(train_input), lora_rank]),
                             valid=np.array(valid if valid is not None else [n_ref] * batch))
+        print(name, tuple(out.shape), float(out.std()))
+
+    # 3b) VAE alone through the reference's own patched forwards (models/model.py:15-63), and the whole image pipeline
+    from oracle.vae import VaeConfig
+    for name, use_shortcuts, lora_rank in VAE_CASES:
+        vcfg = VaeConfig.tiny()
+        vcfg.use_shortcuts = use_shortcuts
+        vae = bind_reference_vae_forwards(synth.make_vae(vcfg, seed=100, lora_rank=lora_rank))
+        c_t, _, eps_main, _, _, _ = synth.images(2, 1, IMAGE_SIZE, IMAGE_LATENT)
+        with torch.no_grad():
+            z = vae.encode_sample(c_t, eps_main) * vcfg.scaling_factor
+            vae.decoder.incoming_skip_acts = vae.encoder.current_down_blocks
+            y = vae.decode(z / vcfg.scaling_factor).clamp(-1, 1)
+        np.savez_compressed(GOLDEN / f"{name}.npz", latent=z.numpy(), image=y.numpy().astype(np.float16))
+        print(name, tuple(z.shape), float(z.std()), tuple(y.shape), float(y.std()))
+    for name, batch, n_ref, use_adain, train_input, lora_unet, lora_vae, use_shortcuts in IMAGE_CASES:
+        pipe = tiny_image_models(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, True, RefUNet, ref_ap)
+        out = pipe.forward(*synth.images(batch, n_ref, IMAGE_SIZE, IMAGE_LATENT))
+        np.savez_compressed(GOLDEN / f"{name}.npz", image=out.numpy().astype(np.float16))
         print(name, tuple(out.shape), float(out.std()))
 
     # 4) full-width SD-Turbo geometry, released "final model" flags (AdaIN on, refs-only KV), B=1, N=4

@@ -69,3 +69,29 @@ class LatentRestorePipeline:
                          cross_attention_kwargs={"ref_keys": keys, "ref_values": values})
         pred = getattr(pred, "sample", pred)
         return self.sched.pred_original_sample(pred, self.noise_timestep, noisy)
+
+
+class ImageRestorePipeline:
+    """ORACLE: the whole reference forward on images (face_replace/models/pix2pix_turbo.py:281-343 with
+    get_conditioning_keys_values :242-279): VAE-encode the degraded image (:291) and the reference images (:245),
+    run the latent pipeline above, decode with the skip activations of the degraded-image encode (:332-333) and clamp
+    to [-1, 1]. The two posterior draws are injected (`eps_main`, `eps_ref`). The reference also decodes the reference
+    latents (:277-278); that output is unused at inference (test.py:100-105) and is not computed here."""
+
+    def __init__(self, latent_pipeline: LatentRestorePipeline, vae, original_vae):
+        self.latent = latent_pipeline
+        self.vae, self.original_vae = vae, original_vae
+
+    @torch.no_grad()
+    def forward(self, c_t, conditioning_images, eps_main, eps_ref, noise_main, noise_ref, valid_indices=None):
+        sf = self.vae.config.scaling_factor
+        enc = self.vae.encode_sample(c_t, eps_main) * sf
+        ref_lat = None
+        if conditioning_images is not None and self.latent.flags.use_shared_attention:
+            b, n = conditioning_images.shape[:2]
+            cond = conditioning_images.reshape(b * n, *conditioning_images.shape[2:])
+            ref_lat = (self.original_vae.encode_sample(cond, eps_ref) * self.original_vae.config.scaling_factor)
+            ref_lat = ref_lat.reshape(b, n, *ref_lat.shape[1:])
+        x0 = self.latent.forward_latents(enc, ref_lat, noise_main, noise_ref, valid_indices)
+        self.vae.decoder.incoming_skip_acts = self.vae.encoder.current_down_blocks
+        return self.vae.decode(x0 / sf).clamp(-1, 1)

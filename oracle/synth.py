@@ -79,3 +79,39 @@ def latents(batch: int, n_ref: int, size: int, seed: int = 1234):
     noise_main = torch.randn(batch, 4, size, size, generator=g)
     noise_ref = torch.randn(batch * n_ref, 4, size, size, generator=g)
     return enc, refs, noise_main, noise_ref
+
+
+def make_vae(cfg=None, seed: int = 100, lora_rank: int = 0, lora_b_std: float = 0.02):
+    """Seeded AutoencoderKL restatement; lora_rank > 0 wraps it with the 'vae_skip' adapter (pix2pix_turbo.py:150-162)."""
+    from .vae import VAE_LORA_TARGETS, AutoencoderKL, VaeConfig
+    cfg = cfg or VaeConfig()
+    vae = AutoencoderKL(cfg)
+    seeded_init_(vae, seed)
+    with torch.no_grad():   # keep the posterior std moderate: logvar head (second half of conv_out/quant_conv) damped
+        vae.quant_conv.weight[cfg.latent_channels:] *= 0.1
+        vae.quant_conv.bias[cfg.latent_channels:] = -3.0
+        vae.decoder.conv_out.weight *= 0.5     # keep most decoded pixels inside (-1, 1) so the final clamp hides little
+    if lora_rank > 0:
+        g = torch.Generator().manual_seed(seed + 1000)
+        targets = list(VAE_LORA_TARGETS) + (["skip_conv_1", "skip_conv_2", "skip_conv_3", "skip_conv_4"] if cfg.use_shortcuts else [])
+        add_lora(vae, targets, r=lora_rank, alpha=lora_rank // 2, adapter="vae_skip", generator=g, b_std=lora_b_std)
+    return vae.eval().requires_grad_(False)
+
+
+def images(batch: int, n_ref: int, size: int, latent: int, seed: int = 4321):
+    """Degraded image, reference images in [-1, 1] (smooth random fields), and the four normal draws."""
+    g = torch.Generator().manual_seed(seed)
+
+    def img(*lead):
+        low = torch.randn(*lead, 3, size // 8, size // 8, generator=g)
+        x = torch.nn.functional.interpolate(low.flatten(0, -4), size=(size, size), mode="bilinear", align_corners=False)
+        x = x + 0.1 * torch.randn(x.shape, generator=g)
+        return (0.6 * x).clamp(-1, 1).reshape(*lead, 3, size, size)
+
+    c_t = img(batch)
+    cond = img(batch, n_ref)
+    eps_main = torch.randn(batch, 4, latent, latent, generator=g)
+    eps_ref = torch.randn(batch * n_ref, 4, latent, latent, generator=g)
+    noise_main = torch.randn(batch, 4, latent, latent, generator=g)
+    noise_ref = torch.randn(batch * n_ref, 4, latent, latent, generator=g)
+    return c_t, cond, eps_main, eps_ref, noise_main, noise_ref

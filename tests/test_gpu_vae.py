@@ -1,0 +1,194 @@
+"""GPU parity of the VAE side (§8f row 1) and of the whole image-level forward / Predictor entry (a6, a12) against the
+golden vectors produced through the reference's own models/model.py forwards, and against the oracle.
+Tolerances: images live in [-1, 1] after the clamp, so errors are reported as relative L2 over the whole image;
+VAE alone <= 2e-3, full image pipeline <= 3e-3, and never worse than 1.5x the reference's own fp16-autocast error."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from instantrestore_b200 import _lib
+    assert _lib.load().ir_check_device() == 0
+    return _lib
+
+
+def _gen(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("B,H,Ci,Co", [(1, 64, 64, 64), (2, 32, 128, 128), (1, 256, 128, 128), (3, 8, 64, 192)])
+def test_conv3x3_stride2_pad_hi_only(L, B, H, Ci, Co):
+    """diffusers Downsample2D(padding=0): F.pad(x, (0,1,0,1)) then a valid 3x3 stride-2 conv (VAE encoder)."""
+    g = _gen(41)
+    x = torch.randn(B, Ci, H, H, device="cuda", generator=g).half()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / (9 * Ci) ** 0.5).half()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    ref = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), w.float(), bias, stride=2).permute(0, 2, 3, 1).reshape(-1, Co)
+    a = x.permute(0, 2, 3, 1).contiguous().reshape(-1, Ci)
+    wk = w.permute(0, 2, 3, 1).contiguous().reshape(Co, 9 * Ci)
+    out = L.conv_gemm(a, wk, batch=B, h_in=H, w_in=H, c_in=Ci, ksize=3, stride=2, bias=bias, pad_hi_only=True)
+    assert rel_l2(out, ref) <= 1e-3
+
+
+@pytest.mark.parametrize("rows,cols", [(4096, 4096), (64, 64), (256, 256), (300, 8192), (17, 1024)])
+def test_softmax_rows(L, rows, cols):
+    g = _gen(42)
+    x = (torch.randn(rows, cols, device="cuda", generator=g) * 6).half()
+    ref = torch.softmax(x.float() * 0.0442, -1)
+    out = L.softmax_rows(x.clone(), 0.0442)
+    assert rel_l2(out, ref) <= 1e-3
+    assert float((out.float().sum(-1) - 1).abs().max()) <= 2e-3
+
+
+def test_image_in_out_and_vae_sample(L):
+    g = _gen(43)
+    for dt in (torch.float16, torch.float32):
+        x = torch.rand(2, 3, 16, 24, device="cuda", generator=g).to(dt) * 2 - 1
+        cl = L.image_in(x)
+        ref = torch.zeros(2, 16 * 24, 64, device="cuda")
+        ref[..., :3] = x.float().permute(0, 2, 3, 1).reshape(2, -1, 3)
+        assert torch.equal(cl.view(2, -1, 64).float(), ref.half().float())
+    y = (torch.randn(2 * 384, 8, device="cuda", generator=g) * 1.5).half()
+    out = L.image_out(y, batch=2, c=3, h=16, w=24)
+    ref = y[:, :3].float().clamp(-1, 1).view(2, 16, 24, 3).permute(0, 3, 1, 2)
+    assert torch.equal(out.float(), ref.half().float())
+    mom = torch.randn(2 * 64, 8, device="cuda", generator=g).half()
+    mom[:, 4:] *= 20                                         # exercises the logvar clamp
+    eps = torch.randn(2, 4, 8, 8, device="cuda", generator=g)
+    z = L.vae_sample(mom, eps, 0.18215, batch=2, c=4, h=8, w=8)
+    m = mom.float().view(2, 64, 8).permute(0, 2, 1).reshape(2, 8, 8, 8)
+    ref = (m[:, :4] + torch.exp(0.5 * m[:, 4:].clamp(-30, 20)) * eps) * 0.18215
+    assert rel_l2(z, ref) <= 1e-5
+    assert rel_l2(L.vae_sample(mom, None, 1.0, batch=2, c=4, h=8, w=8), m[:, :4]) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ VAE engine
+def _vae_cases():
+    from oracle.make_golden import VAE_CASES
+    return VAE_CASES
+
+
+@pytest.mark.parametrize("case", _vae_cases(), ids=[c[0] for c in _vae_cases()])
+def test_vae_engine_vs_reference_golden(case, golden):
+    from instantrestore_b200.vae_engine import VaeEngine
+    from oracle import synth
+    from oracle.make_golden import IMAGE_LATENT, IMAGE_SIZE
+    from oracle.vae import VaeConfig
+    name, use_shortcuts, lora_rank = case
+    vcfg = VaeConfig.tiny()
+    vcfg.use_shortcuts = use_shortcuts
+    vae = synth.make_vae(vcfg, seed=100, lora_rank=lora_rank)
+    eng = VaeEngine(vae.state_dict(), "cuda:0", block_out_channels=vcfg.block_out_channels, use_shortcuts=use_shortcuts)
+    c_t, _, eps_main, _, _, _ = synth.images(2, 1, IMAGE_SIZE, IMAGE_LATENT)
+    z = eng.encode(c_t.cuda(), eps_main.cuda())
+    y = eng.decode(z)
+    g = golden(name)
+    # the reference's precision contract on the same GPU (fp32 weights, fp16 autocast)
+    vae_c = vae.cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        z_ac = vae_c.encode_sample(c_t.cuda(), eps_main.cuda()) * vcfg.scaling_factor
+        vae_c.decoder.incoming_skip_acts = vae_c.encoder.current_down_blocks
+        y_ac = vae_c.decode(z_ac.float() / vcfg.scaling_factor).clamp(-1, 1)
+    ez, ez_ac = rel_l2(z, torch.as_tensor(g["latent"])), rel_l2(z_ac.float(), torch.as_tensor(g["latent"]))
+    ey, ey_ac = rel_l2(y.float(), torch.as_tensor(g["image"]).float()), rel_l2(y_ac.float(), torch.as_tensor(g["image"]).float())
+    print(f"{name}: latent ours {ez:.3e} autocast {ez_ac:.3e} | image ours {ey:.3e} autocast {ey_ac:.3e}")
+    assert ez <= 2e-3 and ez <= 1.5 * ez_ac + 2e-4
+    assert ey <= 2e-3 and ey <= 1.5 * ey_ac + 3e-4
+
+
+def _image_cases():
+    from oracle.make_golden import IMAGE_CASES
+    return IMAGE_CASES
+
+
+def _tiny_pipeline(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, graph):
+    from instantrestore_b200.pipeline import ModelFlags, RestorePipeline
+    from instantrestore_b200.unet_engine import UNetSpec
+    from oracle import synth
+    from oracle.make_golden import IMAGE_LATENT
+    from oracle.unet import UNetConfig
+    from oracle.vae import VaeConfig
+    ucfg = UNetConfig.tiny(sample_size=IMAGE_LATENT)
+    vcfg = VaeConfig.tiny()
+    vcfg.use_shortcuts = use_shortcuts
+    unet, orig = synth.make_unet(ucfg, seed=0, lora_rank=lora_unet), synth.make_unet(ucfg, seed=0)
+    vae, ovae = synth.make_vae(vcfg, seed=100, lora_rank=lora_vae), synth.make_vae(VaeConfig.tiny(), seed=100)
+    spec = UNetSpec(block_out_channels=tuple(ucfg.block_out_channels), attention_head_dim=tuple(ucfg.attention_head_dim),
+                    cross_attention_dim=ucfg.cross_attention_dim)
+    pipe = RestorePipeline(unet.state_dict(), orig.state_dict(), vae.state_dict(), ovae.state_dict(),
+                           synth.caption_embedding(ucfg.cross_attention_dim), ModelFlags(use_adain=use_adain, train_input=train_input),
+                           spec=spec, vae_block_out_channels=vcfg.block_out_channels, use_shortcuts=use_shortcuts,
+                           use_cuda_graph=graph)
+    return pipe
+
+
+@pytest.mark.parametrize("case", _image_cases(), ids=[c[0] for c in _image_cases()])
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cudagraph"])
+def test_image_pipeline_vs_reference_golden(case, graph, golden):
+    from oracle import synth
+    from oracle.make_golden import IMAGE_LATENT, IMAGE_SIZE, tiny_image_models
+    name, batch, n_ref, use_adain, train_input, lora_unet, lora_vae, use_shortcuts = case
+    pipe = _tiny_pipeline(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, graph)
+    c_t, cond, eps_main, eps_ref, noise_main, noise_ref = synth.images(batch, n_ref, IMAGE_SIZE, IMAGE_LATENT)
+    out, x_conds, maps = pipe.forward(c_t.cuda().half(), conditioning_images=cond.cuda().half(), valid_indices=[n_ref] * batch,
+                                      eps_main=eps_main, eps_ref=eps_ref, noise_main=noise_main, noise_ref=noise_ref)
+    assert x_conds is None and maps is None and out.shape == c_t.shape
+    gold = torch.as_tensor(golden(name)["image"]).float()
+    err = rel_l2(out.float(), gold)
+    if graph:
+        out2, _, _ = pipe.forward(c_t.cuda().half(), conditioning_images=cond.cuda().half(), eps_main=eps_main, eps_ref=eps_ref,
+                                  noise_main=noise_main, noise_ref=noise_ref)
+        assert torch.equal(out2, out)
+    ref = tiny_image_models(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, reference_forwards=False)
+    for m in (ref.latent.unet, ref.latent.original_unet, ref.vae, ref.original_vae):
+        m.cuda()
+    ref.latent.caption_enc = ref.latent.caption_enc.cuda()
+    with torch.autocast("cuda", dtype=torch.float16):
+        ac = ref.forward(c_t.cuda(), cond.cuda(), eps_main.cuda(), eps_ref.cuda(), noise_main.cuda(), noise_ref.cuda())
+    ac_err = rel_l2(ac.float(), gold)
+    print(f"{name}: ours {err:.3e}  reference-autocast {ac_err:.3e}")
+    assert err <= 3e-3
+    assert err <= 1.5 * ac_err + 3e-4
+
+
+def test_predictor_entry_on_a_synthetic_checkpoint(tmp_path):
+    """test.py entry: torch.save({'state_dict': net.*, 'cfg': ...}) -> Predictor(path).predict(PIL, [PIL...])."""
+    from PIL import Image
+    from instantrestore_b200 import inference
+    from instantrestore_b200.synthetic import (synthetic_caption, synthetic_unet_state_dict, synthetic_vae_state_dict)
+    from instantrestore_b200.unet_engine import UNetSpec
+    spec = UNetSpec(block_out_channels=(64, 128, 256, 256), attention_head_dim=(1, 2, 4, 4), cross_attention_dim=128)
+    sd = {}
+    for part, d in (("unet", synthetic_unet_state_dict(spec, seed=0, lora_rank=4)), ("original_unet", synthetic_unet_state_dict(spec, seed=0)),
+                    ("vae", synthetic_vae_state_dict((64, 64, 128, 128), lora_rank=4)), ("original_vae", synthetic_vae_state_dict((64, 64, 128, 128)))):
+        sd.update({f"net.module.{part}.{k}" if part == "vae" else f"net.{part}.{k}": v.to(torch.bfloat16) for k, v in d.items()})
+    ckpt = {"state_dict": sd, "cfg": {"model": {"use_adain": True, "train_input": False, "lora_rank_unet": 4, "lora_rank_vae": 4},
+                                      "data": {"max_conditioning_images": 2}}, "caption_enc": synthetic_caption(128)}
+    path = tmp_path / "ckpt.pt"
+    torch.save(ckpt, path)
+    # reduced geometry: patch the defaults the Predictor would use for the released SD-Turbo / sd-vae-ft-mse models
+    orig_init = inference.RestorePipeline.__init__
+
+    def tiny_init(self, *a, **k):
+        k.update(spec=spec, vae_block_out_channels=(64, 64, 128, 128))
+        return orig_init(self, *a, **k)
+
+    inference.RestorePipeline.__init__ = tiny_init
+    try:
+        pred = inference.Predictor(path)
+    finally:
+        inference.RestorePipeline.__init__ = orig_init
+    rng = np.random.default_rng(0)
+    mk = lambda: Image.fromarray((rng.random((512, 512, 3)) * 255).astype("uint8"))
+    img, vis, probs = pred.predict(mk(), [mk(), mk()], target_img=mk())
+    assert img.size == (512, 512) and vis.size == (512, 1536) and probs is None
+    arr = np.asarray(img).astype(np.float32)
+    assert np.isfinite(arr).all() and arr.std() > 1.0

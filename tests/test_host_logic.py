@@ -110,3 +110,55 @@ def test_shard_ranges_partition_identities():
         assert seen == list(range(n))
         sizes = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
         assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("use_shortcuts,lora_rank", [(False, 0), (True, 4)])
+def test_synthetic_vae_checkpoint_has_reference_key_layout(use_shortcuts, lora_rank):
+    from instantrestore_b200.synthetic import synthetic_vae_state_dict
+    from oracle.diffusers024 import add_lora
+    from oracle.vae import VAE_LORA_TARGETS, AutoencoderKL, VaeConfig
+    cfg = VaeConfig.tiny()
+    cfg.use_shortcuts = use_shortcuts
+    m = AutoencoderKL(cfg)
+    if lora_rank:
+        extra = ["skip_conv_1", "skip_conv_2", "skip_conv_3", "skip_conv_4"] if use_shortcuts else []
+        add_lora(m, list(VAE_LORA_TARGETS) + extra, r=lora_rank, alpha=lora_rank // 2, adapter="vae_skip")
+    m.load_state_dict(synthetic_vae_state_dict(cfg.block_out_channels, lora_rank=lora_rank, use_shortcuts=use_shortcuts), strict=True)
+
+
+def test_full_size_vae_parameter_count():
+    from instantrestore_b200.synthetic import vae_parameter_shapes
+    n = sum(math.prod(s[1]) * (1 if s[2] == "conv_nobias" else 1) + (s[1][0] if s[2] in ("conv", "linear", "norm") else 0)
+            for s in vae_parameter_shapes())
+    assert 83.5e6 < n < 83.8e6                                  # sd-vae-ft-mse: 83.65 M parameters
+
+
+def test_checkpoint_splitting_and_cfg_decoding():
+    from instantrestore_b200.inference import decode_cfg, split_state_dict
+    sd = {"net.unet.conv_in.weight": 1, "net.module.vae.encoder.conv_in.weight": 2, "net.original_unet.a.b": 3,
+          "net.original_vae.quant_conv.bias": 4, "net.text_encoder.x": 5}
+    parts = split_state_dict(sd)
+    assert set(parts) == {"unet", "vae", "original_unet", "original_vae", "text_encoder"}
+    assert parts["vae"] == {"encoder.conv_in.weight": 2} and parts["unet"] == {"conv_in.weight": 1}
+    cfg = decode_cfg({"model": {"use_adain": True, "train_input": False, "lora_rank_unet": 32}, "data": {"max_conditioning_images": 4, "x": 1}})
+    assert cfg.model.use_adain and not cfg.model.train_input and cfg.model.use_shared_attention
+    assert cfg.data.max_conditioning_images == 4
+    assert decode_cfg(None).model.train_input is True          # ModelConfig defaults (train_config.py:118-147)
+
+
+def test_image_transform_matches_reference_transform():
+    """test.py:54-59: Resize(512, LANCZOS) + CenterCrop(512) + ToTensor + Normalize(0.5, 0.5)."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from instantrestore_b200.inference import image_to_tensor, tensor2im
+    tf = transforms.Compose([transforms.Resize(512, interpolation=transforms.InterpolationMode.LANCZOS),
+                             transforms.CenterCrop(512), transforms.ToTensor(),
+                             transforms.Normalize([0.5, 0.5, 0.5], [0.5, 0.5, 0.5])])
+    rng = np.random.default_rng(0)
+    for (h, w) in [(512, 512), (300, 400), (700, 600), (1024, 512)]:
+        im = Image.fromarray((rng.random((h, w, 3)) * 255).astype("uint8"))
+        assert torch.equal(image_to_tensor(im), tf(im))
+    x = torch.rand(3, 8, 8) * 2.4 - 1.2
+    ref = ((x * 0.5 + 0.5).clamp(0, 1) * 255).permute(1, 2, 0).numpy().astype("uint8")     # vis_utils.py:14-23
+    assert np.array_equal(np.asarray(tensor2im(x, unnorm=True)), ref)

@@ -130,3 +130,42 @@ def test_full_width_pipeline_matches_reference(golden):
     enc, refs, nm, nr = synth.latents(1, 4, full.sample_size)
     out = pipe.forward_latents(enc, refs, nm, nr)
     _close(out, golden("unet_full_final_n4")["x0"], tol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ VAE + image pipeline
+def _vae_cases():
+    from oracle.make_golden import VAE_CASES
+    return VAE_CASES
+
+
+@pytest.mark.parametrize("case", _vae_cases(), ids=[c[0] for c in _vae_cases()])
+def test_vae_oracle_matches_reference_forwards(case, golden):
+    """oracle/vae.py forwards == the reference's my_vae_encoder_fwd / my_vae_decoder_fwd (models/model.py:15-63)."""
+    from oracle.make_golden import IMAGE_LATENT, IMAGE_SIZE
+    from oracle.vae import VaeConfig
+    name, use_shortcuts, lora_rank = case
+    vcfg = VaeConfig.tiny()
+    vcfg.use_shortcuts = use_shortcuts
+    vae = synth.make_vae(vcfg, seed=100, lora_rank=lora_rank)
+    c_t, _, eps_main, _, _, _ = synth.images(2, 1, IMAGE_SIZE, IMAGE_LATENT)
+    with torch.no_grad():
+        z = vae.encode_sample(c_t, eps_main) * vcfg.scaling_factor
+        vae.decoder.incoming_skip_acts = vae.encoder.current_down_blocks
+        y = vae.decode(z / vcfg.scaling_factor).clamp(-1, 1)
+    g = golden(name)
+    _close(z, g["latent"])
+    assert float((y - torch.as_tensor(g["image"]).float()).abs().max()) <= 1e-3     # golden images are stored as fp16
+
+
+def _image_cases():
+    from oracle.make_golden import IMAGE_CASES
+    return IMAGE_CASES
+
+
+@pytest.mark.parametrize("case", _image_cases(), ids=[c[0] for c in _image_cases()])
+def test_image_pipeline_oracle_matches_reference(case, golden):
+    from oracle.make_golden import IMAGE_LATENT, IMAGE_SIZE, tiny_image_models
+    name, batch, n_ref, use_adain, train_input, lora_unet, lora_vae, use_shortcuts = case
+    pipe = tiny_image_models(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, reference_forwards=False)
+    out = pipe.forward(*synth.images(batch, n_ref, IMAGE_SIZE, IMAGE_LATENT))
+    assert float((out - torch.as_tensor(golden(name)["image"]).float()).abs().max()) <= 1e-3
