@@ -5,9 +5,10 @@
         bench.py --gpus N --steps K --warmup W
 
 A "step" = one pass of the hot path over one batch of B identities per GPU (default B=1: BASELINE configs[1],
-"single 512x512 + 4 refs, final_model flags (AdaIN on, refs-only KV), 1xB200"): N_ref reference-UNet passes that
-produce the 9 key/value pairs, then the main UNet with the shared-image attention + AdaIN, at the latent boundary
-(64x64x4 latents of 512x512 images). Identities are independent, so ranks shard them with no collective on the data
+"single 512x512 + 4 refs, final_model flags (AdaIN on, refs-only KV), 1xB200"): the reference's
+`Pix2Pix_Turbo.forward` on images — VAE-encode the degraded image and the N_ref reference images, N_ref reference-UNet
+passes that produce the 9 key/value pairs, the main UNet with the shared-image attention + AdaIN, scheduler step,
+VAE decode + clamp (`--latent-only` restricts the step to the two UNet stages). Identities are independent, so ranks shard them with no collective on the data
 path (scaling = weak: B identities per GPU per step); weights are broadcast once from rank 0 at start-up.
 
 Prints ONE JSON line (rank 0). `value` = identities/s with inputs resident in HBM (CUDA-graph replay, CUDA events,
@@ -49,15 +50,23 @@ def parse_args():
     ap.add_argument("--no-trace", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu launch lists)")
     ap.add_argument("--trace-out", default="", help="write the per-shape kernel table (JSON) here")
+    ap.add_argument("--latent-only", action="store_true", help="UNet stages only (latents in, latent out); no VAE")
+    ap.add_argument("--lora-rank-vae", type=int, default=32)
     return ap.parse_args()
 
 
 def workload_name(a) -> str:
     mode = "own+refs KV" if a.train_input else "refs-only KV"
-    return (f"single-step restore at the latent boundary, 512x512 (64x64x4 latents), B={a.batch} identity/GPU/step, "
-            f"N_ref={a.n_ref}: {a.n_ref} reference-UNet passes (KV extraction) + main UNet (shared attention, "
-            f"{'AdaIN, ' if not a.no_adain else ''}{mode}, LoRA r={a.lora_rank} merged); SD-Turbo geometry, "
-            "seeded synthetic weights; VAE encode/decode not yet on this path")
+    if a.latent_only:
+        return (f"single-step restore at the latent boundary, 512x512 (64x64x4 latents), B={a.batch} identity/GPU/step, "
+                f"N_ref={a.n_ref}: {a.n_ref} reference-UNet passes (KV extraction) + main UNet (shared attention, "
+                f"{'AdaIN, ' if not a.no_adain else ''}{mode}, LoRA r={a.lora_rank} merged); SD-Turbo geometry, "
+                "seeded synthetic weights; VAE stages excluded (--latent-only)")
+    return (f"single-step restore, 512x512 images in -> 512x512 image out, B={a.batch} identity/GPU/step, N_ref={a.n_ref}: "
+            f"VAE encode x(1+{a.n_ref}), {a.n_ref} reference-UNet passes (KV extraction), main UNet (shared attention, "
+            f"{'AdaIN, ' if not a.no_adain else ''}{mode}, LoRA r={a.lora_rank} merged), scheduler step, VAE decode + clamp; "
+            "SD-Turbo + sd-vae-ft-mse geometry, seeded synthetic weights (the reference's unused decode of the reference "
+            "latents, pix2pix_turbo.py:277-278, is not executed by either arm)")
 
 
 # --------------------------------------------------------------------------------------------------- clocks
@@ -141,7 +150,18 @@ def build_oracle(sd_main, sd_ref, cap, a):
     return LatentRestorePipeline(unet, orig, cap, flags)
 
 
-def cpu_baseline_sample(sd_main, sd_ref, cap, a):
+def build_oracle_vaes(sd_vae, sd_ovae, a):
+    from oracle.diffusers024 import add_lora
+    from oracle.vae import VAE_LORA_TARGETS, AutoencoderKL, VaeConfig
+    vae, ovae = AutoencoderKL(VaeConfig()), AutoencoderKL(VaeConfig())
+    if a.lora_rank_vae:
+        add_lora(vae, list(VAE_LORA_TARGETS), r=a.lora_rank_vae, alpha=a.lora_rank_vae // 2, adapter="vae_skip")
+    vae.load_state_dict(sd_vae, strict=True)
+    ovae.load_state_dict(sd_ovae, strict=True)
+    return vae.eval().requires_grad_(False), ovae.eval().requires_grad_(False)
+
+
+def cpu_baseline_sample(sd_main, sd_ref, cap, a, sd_vae=None, sd_ovae=None):
     """Bounded sample: ONE identity with ONE reference-UNet pass timed + the main-UNet pass with all N_ref K/V sets
     (the N_ref reference passes are identical work, so images/s = 1 / (N_ref * t_ref + t_main))."""
     import torch
@@ -161,10 +181,27 @@ def cpu_baseline_sample(sd_main, sd_ref, cap, a):
     with torch.no_grad():
         pipe.unet(noisy, t, encoder_hidden_states=pipe.caption_enc, cross_attention_kwargs={"ref_keys": keys, "ref_values": values})
     t_main = time.perf_counter() - t0
-    total = a.n_ref * t_ref + t_main
+    if a.latent_only or sd_vae is None:
+        total = a.n_ref * t_ref + t_main
+        return {"value": 1.0 / total, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"1 identity: 1 of {a.n_ref} reference-UNet passes ({t_ref:.2f} s) + the main-UNet pass ({t_main:.2f} s), "
+                          f"fp32 torch CPU, {cores} threads, no warm-up; images/s = 1/({a.n_ref}*t_ref + t_main)"}
+    from instantrestore_b200.synthetic import synthetic_images
+    vae, _ = build_oracle_vaes(sd_vae, sd_ovae, a)
+    c_t, _ = synthetic_images(1, 1, 512)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        z = vae.encode_sample(c_t.float(), torch.zeros(1, 4, 64, 64))
+    t_enc = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        vae.decode(z)
+    t_dec = time.perf_counter() - t0
+    total = (1 + a.n_ref) * t_enc + a.n_ref * t_ref + t_main + t_dec
     return {"value": 1.0 / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 identity: 1 of {a.n_ref} reference-UNet passes ({t_ref:.2f} s) + the main-UNet pass ({t_main:.2f} s), "
-                      f"fp32 torch CPU, {cores} threads, no warm-up; images/s = 1/({a.n_ref}*t_ref + t_main)"}
+            "sample": f"1 identity, each stage timed once: VAE encode of one 512x512 image ({t_enc:.2f} s, x{1 + a.n_ref}), one "
+                      f"reference-UNet pass ({t_ref:.2f} s, x{a.n_ref}), the main-UNet pass ({t_main:.2f} s), VAE decode ({t_dec:.2f} s); "
+                      f"fp32 torch CPU, {cores} threads, no warm-up; images/s = 1/sum"}
 
 
 def run_reference_arm(a):
@@ -182,19 +219,31 @@ def run_reference_arm(a):
     cap = synthetic_caption()
     pipe = build_oracle(sd_main, sd_ref, cap, a)
     enc, refs, nm, nr = synthetic_latents(a.batch, a.n_ref, 64)
+    if a.latent_only:
+        step = lambda: pipe.forward_latents(enc, refs, nm, nr)
+    else:
+        from instantrestore_b200.synthetic import synthetic_images, synthetic_vae_state_dict
+        from oracle.pipeline import ImageRestorePipeline
+        vae, ovae = build_oracle_vaes(synthetic_vae_state_dict(seed=100, lora_rank=a.lora_rank_vae), synthetic_vae_state_dict(seed=100), a)
+        ipipe = ImageRestorePipeline(pipe, vae, ovae)
+        c_t, cond = synthetic_images(a.batch, a.n_ref, 512)
+        c_t, cond = c_t.float(), cond.float()
+        g = torch.Generator().manual_seed(7)
+        eps_m, eps_r = torch.randn(a.batch, 4, 64, 64, generator=g), torch.randn(a.batch * a.n_ref, 4, 64, 64, generator=g)
+        step = lambda: ipipe.forward(c_t, cond, eps_m, eps_r, nm, nr)
     budget_s = 240.0
     t0 = time.perf_counter()
-    pipe.forward_latents(enc, refs, nm, nr)                      # warm-up step, also sizes the run
+    step()                                                       # warm-up step, also sizes the run
     t_one = time.perf_counter() - t0
     warm_done = 1
     steps = max(1, min(a.steps, int((budget_s - t_one) / max(t_one, 1e-6))))
     extra_warm = max(0, min(a.warmup - 1, int((budget_s - t_one * (1 + steps)) / max(t_one, 1e-6))))
     for _ in range(extra_warm):
-        pipe.forward_latents(enc, refs, nm, nr)
+        step()
         warm_done += 1
     t0 = time.perf_counter()
     for _ in range(steps):
-        pipe.forward_latents(enc, refs, nm, nr)
+        step()
     dt = (time.perf_counter() - t0) / steps
     val = a.batch / dt
     sample = (f"{steps} timed step(s) of {a.batch} identity x {a.n_ref} refs (requested {a.steps}; bounded to ~{int(budget_s)} s), "
@@ -213,8 +262,9 @@ def run_ours(a):
     import torch
     from instantrestore_b200 import _lib as L
     from instantrestore_b200 import dist as D
-    from instantrestore_b200.pipeline import ModelFlags, RestoreEngine
-    from instantrestore_b200.synthetic import synthetic_caption, synthetic_latents, synthetic_unet_state_dict
+    from instantrestore_b200.pipeline import ModelFlags, RestoreEngine, RestorePipeline
+    from instantrestore_b200.synthetic import (synthetic_caption, synthetic_images, synthetic_latents,
+                                               synthetic_unet_state_dict, synthetic_vae_state_dict)
 
     rank, world, local = D.init_from_env()
     if not torch.cuda.is_available():
@@ -227,32 +277,49 @@ def run_ours(a):
     t0 = time.perf_counter()
     sd_main = synthetic_unet_state_dict(seed=0, lora_rank=a.lora_rank) if rank == 0 else None
     sd_ref = synthetic_unet_state_dict(seed=0) if rank == 0 else None
+    sd_vae = sd_ovae = None
+    if not a.latent_only and rank == 0:
+        sd_vae = synthetic_vae_state_dict(seed=100, lora_rank=a.lora_rank_vae)
+        sd_ovae = synthetic_vae_state_dict(seed=100)
     t_bcast = time.perf_counter()
     sd_main = D.broadcast_state_dict(sd_main, src=0)
     sd_ref = D.broadcast_state_dict(sd_ref, src=0)
+    if not a.latent_only:
+        sd_vae = D.broadcast_state_dict(sd_vae, src=0)
+        sd_ovae = D.broadcast_state_dict(sd_ovae, src=0)
     t_bcast = time.perf_counter() - t_bcast
     cap = synthetic_caption()
     flags = ModelFlags(use_adain=not a.no_adain, train_input=bool(a.train_input), lora_rank_unet=a.lora_rank)
-    eng = RestoreEngine(sd_main, sd_ref, cap, flags, device=dev, use_cuda_graph=not a.no_graph)
-    t_setup = time.perf_counter() - t0
-
     B, N = a.batch, a.n_ref
     lo = rank * B    # weak scaling: rank r owns identities [r*B, (r+1)*B)
     enc, refs, nm, nr = synthetic_latents(B, N, 64, seed=1234 + lo)
-    host = [t.pin_memory() for t in (enc, refs, nm, nr)]
+    if a.latent_only:
+        eng = RestoreEngine(sd_main, sd_ref, cap, flags, device=dev, use_cuda_graph=not a.no_graph)
+        host = [t.pin_memory() for t in (enc, refs, nm, nr)]
+        host_out = torch.empty(B, 4, 64, 64, dtype=torch.float32).pin_memory()
+        call = lambda ins: eng.forward_latents(*ins)
+    else:
+        eng = RestorePipeline(sd_main, sd_ref, sd_vae, sd_ovae, cap, flags, device=dev, use_cuda_graph=not a.no_graph)
+        c_t, cond = synthetic_images(B, N, 512, seed=4321 + lo)
+        g = torch.Generator().manual_seed(99 + lo)
+        eps_m, eps_r = torch.randn(B, 4, 64, 64, generator=g), torch.randn(B * N, 4, 64, 64, generator=g)
+        host = [t.pin_memory() for t in (c_t, cond, eps_m, eps_r, nm, nr)]
+        host_out = torch.empty(B, 3, 512, 512, dtype=torch.float16).pin_memory()
+        call = lambda ins: eng.forward(ins[0], conditioning_images=ins[1], eps_main=ins[2], eps_ref=ins[3],
+                                       noise_main=ins[4], noise_ref=ins[5])[0]
+    t_setup = time.perf_counter() - t0
     dev_in = [t.to(dev) for t in host]
-    host_out = torch.empty(B, 4, 64, 64, dtype=torch.float32).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = host_out.numel() * host_out.element_size()
 
     # warm-up (first call captures the CUDA graph)
     n0 = L.launch_count()
     for _ in range(max(a.warmup, 3)):
-        out = eng.forward_latents(*dev_in)
+        out = call(dev_in)
     torch.cuda.synchronize()
     if a.no_graph:
         launches_per_step = (L.launch_count() - n0) // max(a.warmup, 3)
-        replay = lambda: eng.forward_latents(*dev_in)
+        replay = lambda: call(dev_in)
     else:   # capture runs the step twice (warm-up + capture); replays add none
         launches_per_step = (L.launch_count() - n0) // 2
         replay = eng._graphs[next(iter(eng._graphs))]["graph"].replay
@@ -276,7 +343,7 @@ def run_ours(a):
     e0.record()
     for _ in range(a.steps):
         ins = [t.to(dev, non_blocking=True) for t in host]
-        out = eng.forward_latents(*ins)
+        out = call(ins)
         host_out.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller consumes the result before the next request
     e1.record()
@@ -294,7 +361,7 @@ def run_ours(a):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
         "config": {"workload": workload_name(a), "identities_per_gpu_per_step": B, "n_ref": N,
-                   "l2": "no explicit flush: each step streams 3.5 GB of weights + activations through the 126 MB L2",
+                   "l2": "no explicit flush: each step streams >3.5 GB of weights + activations through the 126 MB L2",
                    "cuda_graph": not a.no_graph, "setup_s": round(t_setup, 1), "weight_broadcast_s": round(t_bcast, 2)},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -303,9 +370,9 @@ def run_ours(a):
         "gpu_launches_per_step": launches_per_step,
     }
     if rank == 0 and not a.no_trace:
-        result.update(trace_roofline(eng, dev_in, a, ms_step))
+        result.update(trace_roofline(eng, call, dev_in, a, ms_step))
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        result["cpu_baseline"] = cpu_baseline_sample(sd_main, sd_ref, cap, a)
+        result["cpu_baseline"] = cpu_baseline_sample(sd_main, sd_ref, cap, a, sd_vae, sd_ovae)
     if rank == 0:
         print(json.dumps(result), flush=True)
     if world > 1:
@@ -313,20 +380,20 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def trace_roofline(eng, dev_in, a, ms_step):
+def trace_roofline(eng, call, dev_in, a, ms_step):
     """One eager (non-graph) instrumented step: every C-ABI call bracketed by CUDA events on the launching stream."""
     import torch
     from instantrestore_b200 import _lib as L
     peaks = measured_peaks()
     eng.use_cuda_graph = False
     try:
-        eng.forward_latents(*dev_in)           # eager warm-up
+        call(dev_in)                           # eager warm-up
         torch.cuda.synchronize()
         # head start: a spin kernel keeps the GPU busy while the CPU enqueues the ~850 launches of the step, so every
         # event pair brackets back-to-back device execution and not the CPU's launch latency
         torch.cuda._sleep(int(0.06 * 1.9e9))
         with L.Trace() as tr:
-            eng.forward_latents(*dev_in)
+            call(dev_in)
         rows = tr.summary()
     finally:
         eng.use_cuda_graph = not a.no_graph

@@ -15,7 +15,7 @@ tests)
 bench)
   nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > $OUT/${TAG}_clocks.csv 2>/dev/null &
   SMI=$!
-  timeout 900 python bench.py --steps 20 --warmup 3 --trace-out $OUT/${TAG}_kernels.json > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
+  timeout 1200 python bench.py --steps 20 --warmup 3 --trace-out $OUT/${TAG}_kernels.json > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
   kill $SMI 2>/dev/null
   cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
   timeout 600 python bench.py --steps 10 --warmup 3 --batch 8 --no-cpu-baseline --trace-out $OUT/${TAG}_kernels_b8.json > $OUT/${TAG}_bench_b8.json 2> $OUT/${TAG}_bench_b8.err; echo "bench b8 rc=$?"
