@@ -162,11 +162,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
   const long total_vec = static_cast<long>(hw) * vec_per_row;
   const __half* xb = x + static_cast<size_t>(b) * hw * x_stride;
   __half* ob = out + static_cast<size_t>(b) * hw * out_stride;
-  for (long v = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; v < total_vec;
-       v += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long rowi = v / vec_per_row;
-    const int c0 = static_cast<int>(v - rowi * vec_per_row) << 3;
-    const uint4 u = *reinterpret_cast<const uint4*>(xb + rowi * x_stride + c0);
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+  auto apply8 = [&](const uint4& u, int c0) -> uint4 {
     const __half2* h2 = reinterpret_cast<const __half2*>(&u);
     float f[8];
 #pragma unroll
@@ -182,8 +179,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
       if (silu) y = y / (1.0f + __expf(-y));
       f[j] = y;
     }
-    *reinterpret_cast<uint4*>(ob + rowi * out_stride + c0) =
-        make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
+    return make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
+  };
+  long v = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  // 4 independent 16-byte loads in flight per thread
+  for (; v + 3 * stride < total_vec; v += 4 * stride) {
+    uint4 u[4];
+    long rowi[4];
+    int c0[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long vv = v + k * stride;
+      rowi[k] = vv / vec_per_row;
+      c0[k] = static_cast<int>(vv - rowi[k] * vec_per_row) << 3;
+      u[k] = *reinterpret_cast<const uint4*>(xb + rowi[k] * x_stride + c0[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(ob + rowi[k] * out_stride + c0[k]) = apply8(u[k], c0[k]);
+  }
+  for (; v < total_vec; v += stride) {
+    const long rowi = v / vec_per_row;
+    const int c0 = static_cast<int>(v - rowi * vec_per_row) << 3;
+    const uint4 u = *reinterpret_cast<const uint4*>(xb + rowi * x_stride + c0);
+    *reinterpret_cast<uint4*>(ob + rowi * out_stride + c0) = apply8(u, c0);
   }
 }
 
@@ -249,7 +267,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 static void gn_plan(int batch, int hw, int* slabs, int* rows_per_slab) {
   // <= 32 slabs per batch entry: the apply kernel's prologue merges them (8 lanes x 4 dependent steps); even at
   // batch 1 thirty-two CTAs pull a <= 8 MB activation out of L2/HBM in a couple of microseconds.
-  int want = hw >= 65536 ? 256 : (hw >= 16384 ? 128 : 32);   // VAE-resolution tensors need more CTAs to reach HBM speed
+  int want = hw >= 65536 ? 256 : (hw >= 16384 ? 128 : 32);   // x batch CTAs   // VAE-resolution tensors need more CTAs to reach HBM speed
   int max_slabs = hw / 8 > 0 ? hw / 8 : 1;         // >= 8 rows per slab
   if (want > max_slabs) want = max_slabs;
   (void)batch;

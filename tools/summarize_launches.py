@@ -12,9 +12,12 @@ def main():
     with open(src) as f:
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
-    li = [i for i, r in enumerate(rows) if r["Kernel Name"].startswith(("latent_in", "ir::latent_in"))]
-    # a step = [ref latent_in, main latent_in, ...]; steps start at every second latent_in
-    starts = li[0::2]
+    ii = [i for i, r in enumerate(rows) if "image_in_kernel" in r["Kernel Name"]]
+    if ii:      # image pipeline: a step = [image_in (refs), image_in (degraded), ...]
+        starts = ii[0::2]
+    else:       # latent pipeline: a step = [ref latent_in, main latent_in, ...]
+        li = [i for i, r in enumerate(rows) if r["Kernel Name"].startswith(("latent_in", "ir::latent_in"))]
+        starts = li[0::2]
     s, e = (starts[-2], starts[-1]) if len(starts) >= 2 else (0, len(rows))
     step = rows[s:e]
     with open(out + "_step.csv", "w", newline="") as f:
@@ -38,9 +41,9 @@ def main():
         for n, t in byname.most_common():
             f.write(f"| {n} | {t:.1f} | {t / tot * 100:.1f}% |\n")
         f.write("\n| kernel | grid | launches | us total | us/launch |\n|---|---|---|---|---|\n")
-        for (n, g), (c, t) in sorted(bygrid.items(), key=lambda kv: -kv[1][1])[:40]:
+        for (n, g), (c, t) in sorted(bygrid.items(), key=lambda kv: -kv[1][1])[:60]:
             f.write(f"| {n} | {g} | {c} | {t:.1f} | {t / c:.1f} |\n")
-    print(open(out + ".md").read()[:1500])
+    print(open(out + ".md").read())
 
 
 if __name__ == "__main__":
