@@ -110,29 +110,32 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __half* __restric
   }
 }
 
-// ---- GroupNorm pass B: merge the slab moments of this batch entry (prologue), fold them with gamma/beta into a
-// per-channel affine in shared memory, then y = a[c] * x + b[c] (+ SiLU); 8 channels (16 B) per thread.
-// grid = (blocks_per_batch, batch).
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, int x_stride, int hw, int channels,
-                                                       int groups, int slabs, int rows_per_slab, float eps,
-                                                       const float2* __restrict__ partial, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, int silu, __half* __restrict__ out,
-                                                       int out_stride) {
-  extern __shared__ float sm[];                 // [channels][2] (a, b) then [groups][2] (mean, rstd)
-  float* ab = sm;
-  float* st = sm + 2 * channels;
-  const int b = blockIdx.y;
-  const int cpg = channels / groups;
-  // 8 threads per group merge slabs/8 partials each, then a 3-step shuffle merge
+// ---- GroupNorm pass A2: merge the slab moments (Chan) into per-(batch, group) mean / rstd. One CTA per batch entry,
+// 8 lanes per group, loads issued in independent batches of 8 ahead of the (sequential, cheap) merge arithmetic.
+__global__ void __launch_bounds__(256) gn_merge_kernel(const float2* __restrict__ partial, int groups, int slabs,
+                                                       int rows_per_slab, int hw, int cpg, float eps,
+                                                       float2* __restrict__ stats) {
+  const int b = blockIdx.x;
   for (int g0 = 0; g0 < groups; g0 += 32) {
     const int g = g0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
     float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
     if (g < groups) {
-      for (int sl = sub; sl < slabs; sl += 8) {
-        const float2 pm = __ldg(&partial[(static_cast<size_t>(b) * slabs + sl) * groups + g]);
-        const float n_b = static_cast<float>(min(rows_per_slab, hw - sl * rows_per_slab)) * cpg;
-        if (n_a == 0.f) { n_a = n_b; mean_a = pm.x; m2_a = pm.y; }
-        else merge_moments(n_a, mean_a, m2_a, n_b, pm.x, pm.y);
+      for (int sl0 = sub; sl0 < slabs; sl0 += 64) {
+        float2 pm[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int sl = sl0 + 8 * k;
+          pm[k] = sl < slabs ? __ldg(&partial[(static_cast<size_t>(b) * slabs + sl) * groups + g]) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int sl = sl0 + 8 * k;
+          if (sl < slabs) {
+            const float n_b = static_cast<float>(min(rows_per_slab, hw - sl * rows_per_slab)) * cpg;
+            if (n_a == 0.f) { n_a = n_b; mean_a = pm[k].x; m2_a = pm[k].y; }
+            else merge_moments(n_a, mean_a, m2_a, n_b, pm[k].x, pm[k].y);
+          }
+        }
       }
     }
 #pragma unroll
@@ -145,67 +148,73 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
         else merge_moments(n_a, mean_a, m2_a, n_b, mean_b, m2_b);
       }
     }
-    if (g < groups && sub == 0) {
-      st[2 * g] = mean_a;
-      st[2 * g + 1] = rsqrtf(m2_a / n_a + eps);
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < channels; c += blockDim.x) {
-    const int g = c / cpg;
-    const float a = st[2 * g + 1] * __ldg(gamma + c);
-    ab[2 * c] = a;
-    ab[2 * c + 1] = fmaf(-st[2 * g], a, __ldg(beta + c));
-  }
-  __syncthreads();
-  const int vec_per_row = channels >> 3;
-  const long total_vec = static_cast<long>(hw) * vec_per_row;
-  const __half* xb = x + static_cast<size_t>(b) * hw * x_stride;
-  __half* ob = out + static_cast<size_t>(b) * hw * out_stride;
-  const long stride = static_cast<long>(gridDim.x) * blockDim.x;
-  auto apply8 = [&](const uint4& u, int c0) -> uint4 {
-    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = __half22float2(h2[j]);
-      f[2 * j] = t.x;
-      f[2 * j + 1] = t.y;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 cf = *reinterpret_cast<const float2*>(&ab[2 * (c0 + j)]);
-      float y = fmaf(f[j], cf.x, cf.y);
-      if (silu) y = y / (1.0f + __expf(-y));
-      f[j] = y;
-    }
-    return make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
-  };
-  long v = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
-  // 4 independent 16-byte loads in flight per thread
-  for (; v + 3 * stride < total_vec; v += 4 * stride) {
-    uint4 u[4];
-    long rowi[4];
-    int c0[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long vv = v + k * stride;
-      rowi[k] = vv / vec_per_row;
-      c0[k] = static_cast<int>(vv - rowi[k] * vec_per_row) << 3;
-      u[k] = *reinterpret_cast<const uint4*>(xb + rowi[k] * x_stride + c0[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(ob + rowi[k] * out_stride + c0[k]) = apply8(u[k], c0[k]);
-  }
-  for (; v < total_vec; v += stride) {
-    const long rowi = v / vec_per_row;
-    const int c0 = static_cast<int>(v - rowi * vec_per_row) << 3;
-    const uint4 u = *reinterpret_cast<const uint4*>(xb + rowi * x_stride + c0);
-    *reinterpret_cast<uint4*>(ob + rowi * out_stride + c0) = apply8(u, c0);
+    if (g < groups && sub == 0) stats[b * groups + g] = make_float2(mean_a, rsqrtf(m2_a / n_a + eps));
   }
 }
 
-// ---- LayerNorm: one warp per row.
+// ---- GroupNorm pass B: y = a[c] * x + b[c] (+ SiLU) with a = rstd * gamma, b = beta - mean * a. Every thread owns
+// fixed 8-channel vectors (its 16 affine coefficients live in registers) and walks the rows of its CTA's row range
+// with 4 sixteen-byte loads in flight: no per-element index math, no shared-memory lookups.
+// grid = (row blocks, batch).
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, int x_stride, int hw, int channels,
+                                                       int groups, int rows_per_block, const float2* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int silu, __half* __restrict__ out, int out_stride) {
+  const int b = blockIdx.y;
+  const int cpg = channels / groups;
+  const int vpr = channels >> 3;
+  const int lanes = vpr < 256 ? vpr : 256;
+  const int rgroups = 256 / lanes;
+  const int vec0 = threadIdx.x % lanes, rg = threadIdx.x / lanes;
+  if (rg >= rgroups) return;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, hw);
+  const __half* xb = x + static_cast<size_t>(b) * hw * x_stride;
+  __half* ob = out + static_cast<size_t>(b) * hw * out_stride;
+  for (int v = vec0; v < vpr; v += lanes) {
+    const int c0 = v << 3;
+    float ca[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 st = __ldg(&stats[b * groups + (c0 + j) / cpg]);
+      ca[j] = st.y * __ldg(gamma + c0 + j);
+      cb[j] = fmaf(-st.x, ca[j], __ldg(beta + c0 + j));
+    }
+    auto apply8 = [&](const uint4& u) -> uint4 {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(h2[j]);
+        f[2 * j] = fmaf(t.x, ca[2 * j], cb[2 * j]);
+        f[2 * j + 1] = fmaf(t.y, ca[2 * j + 1], cb[2 * j + 1]);
+      }
+      if (silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + fast_exp2(-1.4426950408889634f * f[j]));
+      }
+      return make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
+    };
+    int r = r0 + rg;
+    for (; r + 3 * rgroups < r1; r += 4 * rgroups) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        u[k] = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r + k * rgroups) * x_stride + c0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<uint4*>(ob + static_cast<size_t>(r + k * rgroups) * out_stride + c0) = apply8(u[k]);
+    }
+    for (; r < r1; r += rgroups) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r) * x_stride + c0);
+      *reinterpret_cast<uint4*>(ob + static_cast<size_t>(r) * out_stride + c0) = apply8(u);
+    }
+  }
+}
+
+// ---- LayerNorm: one warp per row; the row (<= 2560 channels = 10 sixteen-byte vectors per lane) is read from
+// global memory once and stays in registers for the mean, the centred variance and the affine.
+template <int kMaxVec>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int x_stride, int rows, int channels,
                                                         float eps, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __half* __restrict__ out,
@@ -215,69 +224,80 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   if (row >= rows) return;
   const __half* xr = x + static_cast<size_t>(row) * x_stride;
   const int nvec = channels >> 3;
+  uint4 u[kMaxVec];
   float s = 0.f;
-  for (int v = lane; v < nvec; v += 32) {
-    const uint4 u = *reinterpret_cast<const uint4*>(xr + (v << 3));
-    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = __half22float2(h2[j]);
-      s += t.x + t.y;
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+      u[k] = *reinterpret_cast<const uint4*>(xr + (v << 3));
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(h2[j]);
+        s += t.x + t.y;
+      }
     }
   }
   const float mean = warp_sum(s) / channels;
   float q = 0.f;
-  for (int v = lane; v < nvec; v += 32) {
-    const uint4 u = *reinterpret_cast<const uint4*>(xr + (v << 3));
-    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = __half22float2(h2[j]);
-      q += (t.x - mean) * (t.x - mean) + (t.y - mean) * (t.y - mean);
+  for (int k = 0; k < kMaxVec; ++k) {
+    if (lane + 32 * k < nvec) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(h2[j]);
+        q += (t.x - mean) * (t.x - mean) + (t.y - mean) * (t.y - mean);
+      }
     }
   }
   const float rstd = rsqrtf(warp_sum(q) / channels + eps);
   __half* orow = out + static_cast<size_t>(row) * out_stride;
-  for (int v = lane; v < nvec; v += 32) {
-    const int c0 = v << 3;
-    const uint4 u = *reinterpret_cast<const uint4*>(xr + c0);
-    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-    float f[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = __half22float2(h2[j]);
-      f[2 * j] = t.x;
-      f[2 * j + 1] = t.y;
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+      const int c0 = v << 3;
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(h2[j]);
+        f[2 * j] = (t.x - mean) * rstd * gg[2 * j] + bb[2 * j];
+        f[2 * j + 1] = (t.y - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1];
+      }
+      *reinterpret_cast<uint4*>(orow + c0) =
+          make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
     }
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * gg[j] + bb[j];
-    *reinterpret_cast<uint4*>(orow + c0) =
-        make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
   }
 }
 
 }  // namespace ir
 
+constexpr int kGnMaxSlabs = 1024;
+
 static void gn_plan(int batch, int hw, int* slabs, int* rows_per_slab) {
-  // <= 32 slabs per batch entry: the apply kernel's prologue merges them (8 lanes x 4 dependent steps); even at
-  // batch 1 thirty-two CTAs pull a <= 8 MB activation out of L2/HBM in a couple of microseconds.
-  int want = hw >= 65536 ? 256 : (hw >= 16384 ? 128 : 32);   // x batch CTAs   // VAE-resolution tensors need more CTAs to reach HBM speed
-  int max_slabs = hw / 8 > 0 ? hw / 8 : 1;         // >= 8 rows per slab
+  // enough CTAs for ~10 MB of loads in flight (592 = 4 per SM), >= 8 rows per slab
+  int want = (592 + batch - 1) / batch;
+  if (want < 32) want = 32;
+  if (want > kGnMaxSlabs) want = kGnMaxSlabs;
+  int max_slabs = hw / 8 > 0 ? hw / 8 : 1;
   if (want > max_slabs) want = max_slabs;
-  (void)batch;
   const int rps = (hw + want - 1) / want;
   *rows_per_slab = rps;
   *slabs = (hw + rps - 1) / rps;
 }
 
 extern "C" size_t ir_groupnorm_workspace_bytes(int batch, int groups) {
-  return static_cast<size_t>(batch) * 256 * groups * sizeof(float2);   // up to 256 slabs per batch entry
+  // per-(batch, slab, group) partial moments + per-(batch, group) mean / rstd
+  return static_cast<size_t>(batch) * (kGnMaxSlabs + 1) * groups * sizeof(float2);
 }
 
 extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
@@ -291,6 +311,7 @@ extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
   if (p->batch <= 0 || p->hw <= 0) return set_error(IR_ERR_SHAPE, "ir_groupnorm: non-positive dims");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   float2* partial = static_cast<float2*>(p->workspace);
+  float2* stats = partial + static_cast<size_t>(p->batch) * kGnMaxSlabs * p->groups;
   int slabs, rps;
   gn_plan(p->batch, p->hw, &slabs, &rps);
   const int vpr = p->channels >> 3;
@@ -298,15 +319,17 @@ extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
   gn_partial_kernel<<<dim3(slabs, p->batch), 256, static_cast<size_t>(rgroups) * p->channels * 2 * sizeof(float), stream>>>(
       static_cast<const __half*>(p->x), p->x_row_stride, p->hw, p->channels, p->groups, rps, partial);
   IR_CUDA_LAUNCH_CHECK("gn_partial launch");
-  const long total_vec = static_cast<long>(p->hw) * (p->channels >> 3);
-  long blocks = (total_vec + 256 * 4 - 1) / (256 * 4);                   // ~4 vectors per thread
-  const long cap = (148 * 8 + p->batch - 1) / p->batch;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  const size_t smem = (static_cast<size_t>(p->channels) * 2 + p->groups * 2) * sizeof(float);
-  gn_apply_kernel<<<dim3(static_cast<unsigned>(blocks), p->batch), 256, smem, stream>>>(
-      static_cast<const __half*>(p->x), p->x_row_stride, p->hw, p->channels, p->groups, slabs, rps, p->eps, partial,
-      p->gamma, p->beta, p->silu, static_cast<__half*>(p->out), p->out_row_stride);
+  gn_merge_kernel<<<p->batch, 256, 0, stream>>>(partial, p->groups, slabs, rps, p->hw, p->channels / p->groups, p->eps, stats);
+  IR_CUDA_LAUNCH_CHECK("gn_merge launch");
+  // apply: ~8 CTAs per SM in total, >= 4 * rgroups rows per CTA so the unrolled loop is used
+  int row_blocks = (148 * 8 + p->batch - 1) / p->batch;
+  int min_rows = 4 * rgroups;
+  int rpb = (p->hw + row_blocks - 1) / row_blocks;
+  if (rpb < min_rows) rpb = min_rows;
+  row_blocks = (p->hw + rpb - 1) / rpb;
+  gn_apply_kernel<<<dim3(row_blocks, p->batch), 256, 0, stream>>>(
+      static_cast<const __half*>(p->x), p->x_row_stride, p->hw, p->channels, p->groups, rpb, stats, p->gamma, p->beta, p->silu,
+      static_cast<__half*>(p->out), p->out_row_stride);
   IR_CUDA_LAUNCH_CHECK("gn_apply launch");
   return 0;
 }
@@ -315,15 +338,22 @@ extern "C" int ir_layernorm(const ir_layernorm_params* p, ir_stream_t stream_) {
   using namespace ir;
   if (!p || !p->x || !p->out || !p->gamma || !p->beta) return set_error(IR_ERR_ARG, "ir_layernorm: NULL argument");
   if (int rc = check_arch()) return rc;
-  if (p->channels % 8 != 0 || p->channels <= 0 || p->rows <= 0) return set_error(IR_ERR_SHAPE, "ir_layernorm: rows=%d channels=%d", p->rows, p->channels);
+  if (p->channels % 8 != 0 || p->channels <= 0 || p->channels > 2560 || p->rows <= 0)
+    return set_error(IR_ERR_SHAPE, "ir_layernorm: rows=%d channels=%d (channels %% 8 == 0, <= 2560)", p->rows, p->channels);
   if (p->x_row_stride % 8 || p->out_row_stride % 8 || (reinterpret_cast<uintptr_t>(p->x) & 15) || (reinterpret_cast<uintptr_t>(p->out) & 15) ||
       (reinterpret_cast<uintptr_t>(p->gamma) & 15) || (reinterpret_cast<uintptr_t>(p->beta) & 15))
     return set_error(IR_ERR_ALIGN, "ir_layernorm: pointers/strides must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int rows_per_block = 8;
-  layernorm_kernel<<<(p->rows + rows_per_block - 1) / rows_per_block, 256, 0, stream>>>(
-      static_cast<const __half*>(p->x), p->x_row_stride, p->rows, p->channels, p->eps, p->gamma, p->beta,
-      static_cast<__half*>(p->out), p->out_row_stride);
+  const int blocks = (p->rows + rows_per_block - 1) / rows_per_block;
+  const __half* xp = static_cast<const __half*>(p->x);
+  __half* op = static_cast<__half*>(p->out);
+  if (p->channels <= 512)
+    layernorm_kernel<2><<<blocks, 256, 0, stream>>>(xp, p->x_row_stride, p->rows, p->channels, p->eps, p->gamma, p->beta, op, p->out_row_stride);
+  else if (p->channels <= 1280)
+    layernorm_kernel<5><<<blocks, 256, 0, stream>>>(xp, p->x_row_stride, p->rows, p->channels, p->eps, p->gamma, p->beta, op, p->out_row_stride);
+  else
+    layernorm_kernel<10><<<blocks, 256, 0, stream>>>(xp, p->x_row_stride, p->rows, p->channels, p->eps, p->gamma, p->beta, op, p->out_row_stride);
   IR_CUDA_LAUNCH_CHECK("layernorm launch");
   return 0;
 }
