@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--trace-out", default="", help="write the per-shape kernel table (JSON) here")
     ap.add_argument("--latent-only", action="store_true", help="UNet stages only (latents in, latent out); no VAE")
     ap.add_argument("--lora-rank-vae", type=int, default=32)
+    ap.add_argument("--streams", type=int, default=2,
+                    help="independent requests kept in flight on separate CUDA streams (each its own graph instance)")
     return ap.parse_args()
 
 
@@ -297,7 +299,7 @@ def run_ours(a):
         eng = RestoreEngine(sd_main, sd_ref, cap, flags, device=dev, use_cuda_graph=not a.no_graph)
         host = [t.pin_memory() for t in (enc, refs, nm, nr)]
         host_out = torch.empty(B, 4, 64, 64, dtype=torch.float32).pin_memory()
-        call = lambda ins: eng.forward_latents(*ins)
+        call = lambda ins, slot=0: eng.forward_latents(*ins)
     else:
         eng = RestorePipeline(sd_main, sd_ref, sd_vae, sd_ovae, cap, flags, device=dev, use_cuda_graph=not a.no_graph)
         c_t, cond = synthetic_images(B, N, 512, seed=4321 + lo)
@@ -305,54 +307,79 @@ def run_ours(a):
         eps_m, eps_r = torch.randn(B, 4, 64, 64, generator=g), torch.randn(B * N, 4, 64, 64, generator=g)
         host = [t.pin_memory() for t in (c_t, cond, eps_m, eps_r, nm, nr)]
         host_out = torch.empty(B, 3, 512, 512, dtype=torch.float16).pin_memory()
-        call = lambda ins: eng.forward(ins[0], conditioning_images=ins[1], eps_main=ins[2], eps_ref=ins[3],
-                                       noise_main=ins[4], noise_ref=ins[5])[0]
+        call = lambda ins, slot=0: eng.forward(ins[0], conditioning_images=ins[1], eps_main=ins[2], eps_ref=ins[3],
+                                               noise_main=ins[4], noise_ref=ins[5], slot=slot)[0]
     t_setup = time.perf_counter() - t0
     dev_in = [t.to(dev) for t in host]
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = host_out.numel() * host_out.element_size()
 
-    # warm-up (first call captures the CUDA graph)
+    # warm-up (first call of a slot captures its CUDA graph)
+    n_streams = 1 if (a.latent_only or a.no_graph) else max(1, a.streams)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
     n0 = L.launch_count()
     for _ in range(max(a.warmup, 3)):
-        out = call(dev_in)
+        out = call(dev_in, 0)
     torch.cuda.synchronize()
     if a.no_graph:
         launches_per_step = (L.launch_count() - n0) // max(a.warmup, 3)
-        replay = lambda: call(dev_in)
+        replays = [lambda: call(dev_in)]
     else:   # capture runs the step twice (warm-up + capture); replays add none
         launches_per_step = (L.launch_count() - n0) // 2
-        replay = eng._graphs[next(iter(eng._graphs))]["graph"].replay
+        for sl in range(1, n_streams):
+            for _ in range(2):
+                call(dev_in, sl)
+        torch.cuda.synchronize()
+        graphs = list(eng._graphs.values())
+        replays = [g["graph"].replay for g in graphs[:n_streams]]
+    cur = torch.cuda.current_stream(dev)
+
+    def run_steps(k):
+        """k independent requests, round-robin over the streams; joined back into the current stream."""
+        for st in streams:
+            st.wait_stream(cur)
+        for i in range(k):
+            with torch.cuda.stream(streams[i % n_streams]):
+                replays[i % n_streams]()
+        for st in streams:
+            cur.wait_stream(st)
 
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- device-resident throughput: K graph replays between two events
+    # ---- device-resident throughput: K requests between two events
     D.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
-        replay()
+    run_steps(a.steps)
     e1.record()
     torch.cuda.synchronize()
     D.barrier()
     ms_total = D.max_over_ranks(e0.elapsed_time(e1), dev)
     # ---- end to end through the public API: pinned host -> device, step, device -> pinned host, every step.
-    # Two requests are kept in flight (the host enqueues request i+1 while the GPU runs request i, and consumes
-    # result i-1 from its own pinned buffer), as a serving loop would.
-    host_outs = [host_out, torch.empty_like(host_out).pin_memory()]
-    done = [torch.cuda.Event(), torch.cuda.Event()]
+    # `n_streams` requests are kept in flight (the host enqueues request i+1 while the GPU runs request i and
+    # consumes each result from its own pinned buffer), as a serving loop would.
+    n_fly = max(2, n_streams)
+    host_outs = [torch.empty_like(host_out).pin_memory() for _ in range(n_fly)]
+    done = [torch.cuda.Event() for _ in range(n_fly)]
     D.barrier()
     torch.cuda.synchronize()
     e0.record()
+    for st in streams:
+        st.wait_stream(cur)
     for i in range(a.steps):
-        ins = [t.to(dev, non_blocking=True) for t in host]
-        out = call(ins)
-        host_outs[i & 1].copy_(out, non_blocking=True)
-        done[i & 1].record()
-        if i > 0:
-            done[(i - 1) & 1].synchronize()            # result i-1 is on the host
-    done[(a.steps - 1) & 1].synchronize()
+        k = i % n_fly
+        if i >= n_fly:
+            done[k].synchronize()                      # result i - n_fly is on the host; its buffers are free again
+        with torch.cuda.stream(streams[i % n_streams]):
+            ins = [t.to(dev, non_blocking=True) for t in host]
+            out = call(ins, i % n_streams)
+            host_outs[k].copy_(out, non_blocking=True)
+            done[k].record()
+    for ev in done:
+        ev.synchronize()
+    for st in streams:
+        cur.wait_stream(st)
     e1.record()
     torch.cuda.synchronize()
     D.barrier()
@@ -369,10 +396,10 @@ def run_ours(a):
         "data": "synthetic",
         "config": {"workload": workload_name(a), "identities_per_gpu_per_step": B, "n_ref": N,
                    "l2": "no explicit flush: each step streams >3.5 GB of weights + activations through the 126 MB L2",
-                   "cuda_graph": not a.no_graph, "setup_s": round(t_setup, 1), "weight_broadcast_s": round(t_bcast, 2)},
+                   "cuda_graph": not a.no_graph, "requests_in_flight": n_streams, "setup_s": round(t_setup, 1), "weight_broadcast_s": round(t_bcast, 2)},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / a.steps, "requests_in_flight": 2},
+                "ms_per_step": ms_e2e / a.steps, "requests_in_flight": n_fly},
         "gpu_launches": launches_per_step * a.steps,
         "gpu_launches_per_step": launches_per_step,
     }

@@ -196,12 +196,30 @@ def _f(t: torch.Tensor | None, name: str) -> torch.Tensor | None:
 
 
 _scratch_bufs: dict = {}
+_scratch_ns = 0
+
+
+class scratch_namespace:
+    """Scratch buffers requested inside this context belong to `ns` (e.g. one CUDA-graph instance): graphs that may
+    replay concurrently on different streams must not share split-KV scratch."""
+
+    def __init__(self, ns):
+        self.ns = ns
+
+    def __enter__(self):
+        global _scratch_ns
+        self.prev, _scratch_ns = _scratch_ns, self.ns
+        return self
+
+    def __exit__(self, *exc):
+        global _scratch_ns
+        _scratch_ns = self.prev
 
 
 def _scratch(device, nbytes: int) -> torch.Tensor:
-    """Per-device scratch for split-KV partials. Kernels of one stream run in order, so one buffer serves every
-    layer; it only grows, and superseded buffers stay alive because captured CUDA graphs hold their addresses."""
-    bufs = _scratch_bufs.setdefault(str(device), [])
+    """Per-(device, stream) scratch for split-KV partials. Kernels of one stream run in order, so one buffer serves
+    every layer launched on it; it only grows, and superseded buffers stay alive because captured CUDA graphs hold their addresses."""
+    bufs = _scratch_bufs.setdefault((_scratch_ns, str(device), torch.cuda.current_stream(device).cuda_stream), [])
     if not bufs or bufs[-1].numel() < nbytes:
         bufs.append(torch.empty(nbytes, dtype=torch.uint8, device=device))
     return bufs[-1]

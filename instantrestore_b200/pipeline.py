@@ -64,6 +64,14 @@ class RestoreEngine:
     # ------------------------------------------------------------------------------------------ eager step
     def _step(self, enc, refs, noise_main, noise_ref, valid: Optional[Sequence[int]]):
         B, _, H, W = enc.shape
+        cur = torch.cuda.current_stream(self.dev)
+        # main path prefix (noise, conv_in, down blocks, mid block) does not depend on the references: fork it onto a
+        # second stream so its small (batch B) grids fill the SMs the reference pass (batch B*N) leaves idle
+        side = self._side_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            x = L.latent_in(enc, noise_main, self.a_main, self.s_main)
+            state = self.main.forward_down_mid(x, B, H, W)
         ref_kv = None
         if self.ref is not None and refs is not None:
             N = refs.shape[1]
@@ -77,9 +85,16 @@ class RestoreEngine:
                         if nv < N:
                             rows[b, nv:, :, cap.k_off:].zero_()     # K and V columns of the padded slots
                 ref_kv.append(RefKV(buf=cap.buf, k_off=cap.k_off, v_off=cap.v_off, n_ref=N, s_ref=cap.s_ref))
-        x = L.latent_in(enc, noise_main, self.a_main, self.s_main)
-        eps = self.main.forward(x, B, H, W, ref_kv=ref_kv)
+        cur.wait_stream(side)                                       # join: the up blocks need both paths
+        for t in (x, state[0], *[sk[0] for sk in state[1]]):
+            t.record_stream(cur)
+        eps = self.main.forward_up(state, ref_kv=ref_kv)
         return L.latent_out(eps, enc, noise_main, self.a_main, self.s_main)
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        return self._side
 
     # ------------------------------------------------------------------------------------------ public
     @torch.no_grad()
@@ -158,20 +173,44 @@ class RestorePipeline:
 
     def _step(self, c_t, cond, eps_main, eps_ref, noise_main, noise_ref, valid):
         B = c_t.shape[0]
-        ref_lat = None
+        eng = self.engine
+        cur = torch.cuda.current_stream(self.dev)
+        # fork: degraded-image encode + main-UNet prefix on the side stream, reference encode + reference UNet here
+        side = eng._side_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            enc = self.vae.encode(c_t, eps_main)             # records the skip activations for the decoder
+            skips = self.vae.skip_acts
+            _, _, H, W = enc.shape
+            x = L.latent_in(enc, noise_main, eng.a_main, eng.s_main)
+            state = eng.main.forward_down_mid(x, B, H, W)
+        ref_kv = None
         if cond is not None and self.original_vae is not None:
             N = cond.shape[1]
             lat = self.original_vae.encode(cond.reshape(B * N, *cond.shape[2:]), eps_ref)
-            ref_lat = lat.view(B, N, *lat.shape[1:])
-        enc = self.vae.encode(c_t, eps_main)                 # records the skip activations for the decoder
-        skips = self.vae.skip_acts
-        x0 = self.engine._step(enc, ref_lat, noise_main, noise_ref, valid)
+            rin = L.latent_in(lat, noise_ref, eng.a_ref, eng.s_ref)
+            eng.ref.forward(rin, B * N, lat.shape[2], lat.shape[3])
+            ref_kv = []
+            for cap in eng.ref.captured:
+                if valid is not None:
+                    rows = cap.buf.view(B, N, cap.s_ref, -1)
+                    for b, nv in enumerate(valid):
+                        if nv < N:
+                            rows[b, nv:, :, cap.k_off:].zero_()
+                ref_kv.append(RefKV(buf=cap.buf, k_off=cap.k_off, v_off=cap.v_off, n_ref=N, s_ref=cap.s_ref))
+        cur.wait_stream(side)                                # join
+        for t in (enc, x, state[0], *[sk[0] for sk in state[1]], *[sk[0] for sk in skips]):
+            t.record_stream(cur)
+        eps = eng.main.forward_up(state, ref_kv=ref_kv)
+        x0 = L.latent_out(eps, enc, noise_main, eng.a_main, eng.s_main)
         return self.vae.decode(x0, skip_acts=skips, dtype=self.out_dtype)
 
     @torch.no_grad()
     def forward(self, c_t: torch.Tensor, face_embeds=None, conditioning_images: Optional[torch.Tensor] = None,
                 valid_indices=None, mask=None, return_self_attention_maps: bool = False, *, eps_main=None, eps_ref=None,
-                noise_main=None, noise_ref=None):
+                noise_main=None, noise_ref=None, slot: int = 0):
+        """`slot` selects one of several independent CUDA-graph instances (own static buffers and scratch), so that a
+        serving loop can keep requests in flight on different streams; results of a slot stay valid until its next call."""
         if face_embeds is not None:
             raise NotImplementedError("condition_on_face_embeds is False in the released configs")
         if return_self_attention_maps:
@@ -204,10 +243,11 @@ class RestorePipeline:
         if not self.use_cuda_graph:
             out = self._step(ins["c_t"], ins["cond"], ins["eps_main"], ins["eps_ref"], ins["noise_main"], ins["noise_ref"], valid)
             return out, None, None
-        key = (tuple(c_t.shape), c_t.dtype, None if cond is None else tuple(cond.shape), tuple(valid) if valid else None)
+        key = (tuple(c_t.shape), c_t.dtype, None if cond is None else tuple(cond.shape), tuple(valid) if valid else None, slot)
         g = self._graphs.get(key)
         if g is None:
-            g = self._capture(ins, valid)
+            with L.scratch_namespace(("graph", id(self), len(self._graphs))):
+                g = self._capture(ins, valid)
             self._graphs[key] = g
         for k, v in ins.items():
             if v is not None:

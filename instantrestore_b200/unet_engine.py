@@ -228,8 +228,12 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, B: int, H: int, W: int, ref_kv: Optional[Sequence[RefKV]] = None) -> torch.Tensor:
         """x: fp16 channel-last latent [B*H*W, 64] (4 real channels). Returns the model output [B*H*W, 4] fp16."""
+        return self.forward_up(self.forward_down_mid(x, B, H, W), ref_kv)
+
+    def forward_down_mid(self, x: torch.Tensor, B: int, H: int, W: int):
+        """conv_in, down blocks and mid block (reference unet.py:1042-1121): independent of the reference K/V, so the
+        pipeline runs it on a second stream while the reference UNet is still working."""
         self.captured = []
-        shared_idx = 0
         dbg = self.debug
         h = self._conv(x, self.conv_in, B, H, W)
         if dbg is not None:
@@ -257,6 +261,14 @@ class UNetEngine:
         h = self._resnet(h, r1, B, H, W)
         if dbg is not None:
             dbg["mid_block"] = h
+        return h, skips, B, H, W
+
+    def forward_up(self, state, ref_kv: Optional[Sequence[RefKV]] = None) -> torch.Tensor:
+        """up blocks (shared attention against the reference K/V), conv_norm_out, conv_out (unet.py:1135-1170)."""
+        h, skips, B, H, W = state
+        skips = list(skips)
+        shared_idx = 0
+        dbg = self.debug
         for i, (layers, us) in enumerate(self.up):
             bscale, sscale = 1.0, 1.0
             if self.freeu is not None and i < 2:
