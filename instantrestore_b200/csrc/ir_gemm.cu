@@ -12,6 +12,12 @@
 // Two CTAs are resident per SM (<= 113 KB smem, <= 256 TMEM columns each) so one CTA's epilogue overlaps the
 // other's main loop.
 //
+// Persistent variant (conv_gemm_persistent_kernel, used whenever K is not split): one CTA per SM loops over output
+// tiles; the TMEM accumulator is double-buffered (2 x BN columns) and a dedicated epilogue warpgroup pair (8 warps)
+// drains tile i while the producer / MMA warps are already deep into tile i+1, so the epilogue (bias, fp16 round,
+// residual, GEGLU with a polynomial erf) and the per-CTA set-up (barrier init, TMEM allocation, pipeline fill)
+// disappear from the critical path of short-K layers (VAE 128-channel convolutions, K = 320 linears, GEGLU).
+//
 // Split-K over a thread-block cluster (small-M layers: 8x8 / 16x16 resolution convs and the B=1 linears launch only
 // 10-80 output tiles on 148 SMs and are weight-bandwidth bound): gridDim.z = cluster size S in {2,4,8}; CTA z
 // accumulates K-blocks [z*kb, (z+1)*kb) in its own TMEM, then the S partial tiles are reduce-scattered through
@@ -39,6 +45,7 @@ struct GemmKParams {
   int bw, bh, bn;
   int8_t tap_map[9], tap_dx[9], tap_dy[9];
   int split, kb_per_split;
+  int m_tiles;
   const float* bias;
   const __half* residual;
   int res_stride;
@@ -49,6 +56,17 @@ struct GemmKParams {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// gelu_erf with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below one fp16 ulp): 2 MUFU + ~12 FMA
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * fast_exp2(-1.4426950408889634f * z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 
 
@@ -295,6 +313,203 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------------ persistent kernel
+constexpr int kPersistThreads = 320;   // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue (two warps per TMEM lane quarter)
+
+// GEGLU epilogue for 32 outputs: values at accumulator columns vcol.., gates 64 columns further
+__device__ __forceinline__ void geglu_store32(uint32_t taddr_v, const GemmKParams& p, long grow, int wcol, int ocol, bool row_ok) {
+  uint32_t rv[32], rg[32];
+  tmem_ld32(taddr_v, rv);
+  tmem_ld32(taddr_v + 64, rg);
+  tmem_ld_wait();
+  if (!row_ok) return;
+  uint32_t packed[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float v0 = __uint_as_float(rv[i]), v1 = __uint_as_float(rv[i + 1]);
+    float g0 = __uint_as_float(rg[i]), g1 = __uint_as_float(rg[i + 1]);
+    if (p.bias) {
+      v0 += __ldg(p.bias + wcol + i);
+      v1 += __ldg(p.bias + wcol + i + 1);
+      g0 += __ldg(p.bias + wcol + 64 + i);
+      g1 += __ldg(p.bias + wcol + 64 + i + 1);
+    }
+    v0 = round_h(v0); v1 = round_h(v1); g0 = round_h(g0); g1 = round_h(g1);
+    packed[i / 2] = pack_half2(v0 * round_h(gelu_erf_fast(g0)), v1 * round_h(gelu_erf_fast(g1)));
+  }
+  uint4* dst = reinterpret_cast<uint4*>(p.out + grow * p.out_stride + ocol);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kernel(const __grid_constant__ GemmKParams p) {
+  constexpr int B_BYTES = BN * kBK * 2;
+  constexpr int STAGE_BYTES = kABytes + B_BYTES;
+  constexpr uint32_t ACC_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // columns per accumulator stage
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  constexpr uint32_t IDESC = umma_idesc_f16(kBM, BN, 0, 0);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;    // accumulator stage ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;        // accumulator stage drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles_n = (p.N + BN - 1) / BN;
+  const int total_tiles = p.m_tiles * n_tiles_n;
+  const int num_k = p.taps * p.kc_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a[0]);
+    tma_prefetch_desc(&p.tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;   // running k-block counter across tiles (stage ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles_n, nt = tile - mt * n_tiles_n;
+        const int w0 = (mt % p.tiles_w) * p.bw;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+        int tap = 0, kc = 0;
+        for (int ks = 0; ks < num_k; ++ks, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_4d(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], &full_bar[s], kc * kBK, w0 + p.tap_dx[tap],
+                      h0 + p.tap_dy[tap], n0);
+          tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], ks * kBK, nt * BN);
+          if (++kc == p.kc_per_tap) {
+            kc = 0;
+            ++tap;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        mbar_wait(&tempty_bar[as], ((local >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+        for (int ks = 0; ks < num_k; ++ks, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * kABytes);
+          const uint32_t b_base = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adesc = umma_smem_desc(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(b_base + k * 32, 16, 1024);
+            umma_f16_ss(d_tmem, adesc, bdesc, IDESC, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (thread == row, half the columns)
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which half of the tile's columns
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int mt = tile / n_tiles_n, nt = tile - mt * n_tiles_n;
+      const int as = local & 1;
+      mbar_wait(&tfull_bar[as], (local >> 1) & 1);
+      tc_fence_after();
+      const long grow = static_cast<long>(mt) * kBM + row;
+      const bool row_ok = grow < p.M;
+      const uint32_t taddr = tmem_base + as * ACC_COLS + lane_addr;
+      if (p.act == IR_ACT_GEGLU) {
+        if constexpr (BN % 128 == 0) {
+#pragma unroll 1
+          for (int blk = 0; blk < BN / 128; ++blk) {
+            const int wcol = nt * BN + blk * 128 + half * 32;            // weight-row index of the value columns
+            const int ocol = (nt * BN + blk * 128) / 2 + half * 32;      // output column
+            geglu_store32(taddr + blk * 128 + half * 32, p, grow, wcol, ocol, row_ok);
+          }
+        }
+      } else {
+        // BN = 160 splits 96 | 64 so both halves work in 32-column chunks
+        const int c_begin = half == 0 ? 0 : (BN == 160 ? 96 : BN / 2);
+        const int c_end = half == 0 ? (BN == 160 ? 96 : BN / 2) : BN;
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            epilogue_store<32>(v, p, grow, nt * BN + c0);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES>
+static int launch_persistent(const GemmKParams& kp, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 1024 + 256;
+  static bool attr_done = false;  // benign race: idempotent
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm_persistent<%d>): %s", BN, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const long tiles = static_cast<long>(kp.m_tiles) * ((kp.N + BN - 1) / BN);
+  const int grid = static_cast<int>(tiles < 148 ? tiles : 148);
+  conv_gemm_persistent_kernel<BN, STAGES><<<grid, kPersistThreads, smem, stream>>>(kp);
+  IR_CUDA_LAUNCH_CHECK("conv_gemm_persistent launch");
+  return 0;
+}
+
 template <int BN, int STAGES>
 static int launch(const GemmKParams& kp, int m_tiles, cudaStream_t stream) {
   constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 1024 + 256;
@@ -485,6 +700,25 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
     if (int rc = make_tmap_f16(&kp.tma_b, p->w, 2, dims, str, box)) return rc;
   }
 
+  kp.m_tiles = m_tiles;
+  // Persistent kernel when the epilogue / per-CTA set-up is a visible fraction of a tile (short K, GEGLU) and the
+  // tile count quantises well over 148 SMs; long-K layers keep two one-tile CTAs per SM (measured: tools/gemm_bench.py).
+  bool persistent = false;
+  if (split == 1 && !p->no_persistent) {
+    const long tiles = static_cast<long>(m_tiles) * ((p->c_out + bn_tile - 1) / bn_tile);
+    const long rounds = (tiles + 147) / 148;
+    const double eff = tiles < 148 ? 1.0 : static_cast<double>(tiles) / (rounds * 148.0);
+    persistent = geglu || (num_k <= 40 && (tiles >= 592 || eff >= 0.85));
+  }
+  if (persistent) {
+    switch (bn_tile) {
+      case 64: return launch_persistent<64, 8>(kp, stream);
+      case 128: return launch_persistent<128, 6>(kp, stream);
+      case 160: return launch_persistent<160, 5>(kp, stream);
+      case 256: return launch_persistent<256, 4>(kp, stream);
+      default: return set_error(IR_ERR_SHAPE, "ir_conv_gemm: tile_n=%d unsupported", bn_tile);
+    }
+  }
   switch (bn_tile) {
     case 64: return launch<64, 4>(kp, m_tiles, stream);
     case 128: return launch<128, 3>(kp, m_tiles, stream);
