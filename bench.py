@@ -420,6 +420,8 @@ def trace_roofline(eng, call, dev_in, a, ms_step):
     from instantrestore_b200 import _lib as L
     peaks = measured_peaks()
     eng.use_cuda_graph = False
+    inner = getattr(eng, "engine", eng)
+    inner.overlap_streams = False          # one stream: every kernel is timed alone
     try:
         call(dev_in)                           # eager warm-up
         torch.cuda.synchronize()
@@ -430,6 +432,7 @@ def trace_roofline(eng, call, dev_in, a, ms_step):
             call(dev_in)
         rows = tr.summary()
     finally:
+        inner.overlap_streams = True
         eng.use_cuda_graph = not a.no_graph
     by_op = {}
     for r in rows:

@@ -59,6 +59,7 @@ class RestoreEngine:
         self.a_main, self.s_main = ddpm_coeffs(noise_timestep)
         self.a_ref, self.s_ref = ddpm_coeffs(ref_timestep)
         self.use_cuda_graph = use_cuda_graph
+        self.overlap_streams = True     # fork the main-path prefix onto a second stream (off for per-kernel tracing)
         self._graphs: Dict[Tuple, dict] = {}
 
     # ------------------------------------------------------------------------------------------ eager step
@@ -92,6 +93,8 @@ class RestoreEngine:
         return L.latent_out(eps, enc, noise_main, self.a_main, self.s_main)
 
     def _side_stream(self):
+        if not self.overlap_streams:
+            return torch.cuda.current_stream(self.dev)
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=self.dev)
         return self._side
