@@ -247,7 +247,8 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
         pad_hi_only=int(pad_hi_only), no_persistent=int(no_persistent))
     k_tot = ksize * ksize * c_in
     _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks{ksize}s{stride}", 2.0 * m * k_tot * c_out,
-         2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out),
+         2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out
+                + (m * n_out if residual is not None else 0)),
          load().ir_conv_gemm, C.byref(p), stream_ptr())
     return out
 

@@ -31,7 +31,10 @@ def timeit(f, n=10):
 
 def main():
     g = torch.Generator(device="cuda").manual_seed(0)
-    for kind, B, H, Ci, Co in SHAPES:
+    shapes = SHAPES
+    if len(sys.argv) >= 6:      # one shape from the command line: kind B H Cin Cout
+        shapes = [(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))]
+    for kind, B, H, Ci, Co in shapes:
         if kind == "conv3":
             a = torch.randn(B * H * H, Ci, device="cuda", generator=g).half()
             w = (torch.randn(Co, 9 * Ci, device="cuda", generator=g) / math.sqrt(9 * Ci)).half()

@@ -7,8 +7,13 @@ cap() {  # name regex skip
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_full_$1.log 2>&1
   echo "$1 rc=$?"
 }
-cap conv_persistent_128 "conv_gemm_persistent_kernel<128" 4
+WHAT=${2:-all}
+if [ "$WHAT" = all ] || [ "$WHAT" = conv ]; then
+cap conv_persistent "conv_gemm_persistent_kernel" 1     # VAE encoder resnet conv 128->128 @512^2, 4 reference images
+cap conv_onetile "^conv_gemm_kernel" 0
+fi
+if [ "$WHAT" = all ] || [ "$WHAT" = rest ]; then
 cap attn "shared_attn_kernel" 0
 cap gn_apply "gn_apply_kernel" 2
-cap conv_onetile_128 "conv_gemm_kernel<128" 6
+fi
 ls -la $OUT/${TAG}_full_*.ncu-rep
