@@ -101,8 +101,9 @@ int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
  *         pix2pix_turbo.py:269-273): they still receive softmax mass.
  * adain_scale/shift: fp32 [batch, n_ref, heads*64] or NULL.
  * out:    fp16 [batch, s_q, heads*64] (row stride out_row_stride).
- * chunk_mass: optional fp32 [batch, heads, n_chunks] — attention probability mass per KV chunk averaged over
- *         queries (what gradio_demo.py:118-133 derives from the dense matrix). NULL to skip.
+ * chunk_mass: optional fp32 [batch, heads, n_chunks] — attention probability mass per KV chunk ([own], ref 0, ...)
+ *         averaged over queries (what gradio_demo.py:118-133 derives from the dense matrix). NULL to skip. Needs
+ *         n_ref > 0 and `workspace` of batch*heads*ceil(s_q/256)*256*(n_chunks+1)*8 bytes; disables KV splitting.
  * When batch * heads * ceil(s_q / 256) cannot fill the 148 SMs (a single identity), the KV sequence is split into
  * ranges handled by separate CTAs; partial (O, max, sum) land in `workspace` and are merged in split order.
  */

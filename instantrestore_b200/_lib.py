@@ -258,7 +258,7 @@ def shared_attn(q: torch.Tensor, *, heads: int, scale: float, batch: int, s_q: i
                 own_shared: bool = False, q_col_off: int = 0, k_own_col_off: int = 0, v_own_col_off: int = 0,
                 k_ref: torch.Tensor | None = None, v_ref: torch.Tensor | None = None, n_ref: int = 0, s_ref: int = 0,
                 ref_col_off: int = 0, adain_scale: torch.Tensor | None = None, adain_shift: torch.Tensor | None = None,
-                out: torch.Tensor | None = None, kv_splits: int = 0) -> torch.Tensor:
+                out: torch.Tensor | None = None, kv_splits: int = 0, chunk_mass: bool = False):
     """q: fp16 [batch*s_q, row]; k_own/v_own: fp16 [(batch|1)*s_own, row]; k_ref/v_ref: fp16 [batch*n_ref*s_ref, row]."""
     _h(q, "q")
     if out is None:
@@ -272,10 +272,17 @@ def shared_attn(q: torch.Tensor, *, heads: int, scale: float, batch: int, s_q: i
         adain_scale=ptr(_f(adain_scale, "adain_scale")), adain_shift=ptr(_f(adain_shift, "adain_shift")),
         batch=batch, heads=heads, s_q=s_q, scale=scale, out=ptr(out), out_row_stride=out.stride(-2), chunk_mass=None,
         kv_splits=kv_splits)
-    ws_bytes = load().ir_shared_attn_workspace_bytes(batch, heads, s_q) if kv_splits != 1 else 0
-    if ws_bytes:
-        ws = _scratch(q.device, ws_bytes)
-        p.workspace, p.workspace_bytes = ptr(ws), ws.numel()
+    mass = None
+    if chunk_mass:
+        n_chunks = (1 if k_own is not None else 0) + n_ref
+        mass = torch.empty((batch, heads, n_chunks), dtype=torch.float32, device=q.device)
+        ws = _scratch(q.device, batch * heads * ((s_q + 255) // 256) * 256 * (n_chunks + 1) * 8)
+        p.chunk_mass, p.workspace, p.workspace_bytes, p.kv_splits = ptr(mass), ptr(ws), ws.numel(), 1
+    else:
+        ws_bytes = load().ir_shared_attn_workspace_bytes(batch, heads, s_q) if kv_splits != 1 else 0
+        if ws_bytes:
+            ws = _scratch(q.device, ws_bytes)
+            p.workspace, p.workspace_bytes = ptr(ws), ws.numel()
     if k_own is not None:
         _h(k_own, "k_own"); _h(v_own, "v_own")
         assert k_own.stride(-2) == v_own.stride(-2)
@@ -285,7 +292,7 @@ def shared_attn(q: torch.Tensor, *, heads: int, scale: float, batch: int, s_q: i
     s_kv = (s_own if k_own is not None else 0) + n_ref * s_ref
     _run("ir_shared_attn_fwd", f"b{batch}_h{heads}_sq{s_q}_skv{s_kv}", 4.0 * batch * heads * s_q * s_kv * 64,
          2.0 * batch * heads * 64 * (2 * s_q + 2 * s_kv), load().ir_shared_attn_fwd, C.byref(p), stream_ptr())
-    return out
+    return (out, mass) if chunk_mass else out
 
 
 def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch: int, hw: int, groups: int = 32,

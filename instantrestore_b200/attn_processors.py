@@ -15,10 +15,14 @@ reference keys/values consumed in their native (B, N, S, C) layout (no head spli
 into the kernel through ir_adain_coeffs. Inputs must be CUDA tensors on a B200; there is no CPU path here (the CPU
 restatement lives in oracle/ and is test infrastructure).
 
+`save_self_attentions=True` keeps the reference behaviour of exposing `self.attention_probs` (B, H, S, S_k) after a
+forward (:258-260); the fused kernel never builds that matrix, so it is recomputed by a GEMM + row softmax
+(attn_probs.py) — diagnostic use only. `save_reference_mass=True` (new, cheap) stores `self.reference_mass`
+(B, H, n_chunks): the softmax mass per KV chunk averaged over queries, which is what gradio_demo.py:118-133 derives
+from the dense matrix.
+
 Not provided on this path: attention masks, attn.group_norm / spatial_norm / norm_cross (all None for the SD-Turbo
-UNet), FaceIDAttnProcessor (condition_on_face_embeds=False in the released configs), and the dense
-`attention_probs` tensor (save_self_attentions=True raises; the per-reference mass read-out is the planned
-replacement).
+UNet) and FaceIDAttnProcessor (condition_on_face_embeds=False in the released configs).
 """
 from __future__ import annotations
 
@@ -139,13 +143,14 @@ class SharedAttnProcessor(nn.Module):
         self.save_self_attentions = save_self_attentions
         self.use_adain = use_adain
         self.train_input = train_input
+        self.save_reference_mass = False
+        self.attention_probs = None
+        self.reference_mass = None
         self._cache = _ProjCache()
 
     def forward(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, ref_keys=None,
                 ref_values=None):
         _check(attn, hidden_states, attention_mask)
-        if self.save_self_attentions:
-            raise NotImplementedError("the fused kernel never materialises attention_probs (save_self_attentions=True)")
         residual, dtype = hidden_states, hidden_states.dtype
         x, b, s, c, shape4 = _as_tokens(hidden_states)
         is_self = encoder_hidden_states is None
@@ -160,18 +165,28 @@ class SharedAttnProcessor(nn.Module):
             ctx = ctx.reshape(-1, ctx.shape[-1]).contiguous()
             q, k, v = _project(x, w["q"], w["qb"]), _project(ctx, w["k"], w["kb"]), _project(ctx, w["v"], w["vb"])
         kw = dict(k_own=k, v_own=v, s_own=s_kv)
+        chunks = [(k, 0, s_kv, s_kv, 0)]
+        has_refs = False
         if self.self_attn_idx is not None and ref_keys is not None and ref_values is not None:
+            has_refs = True
             rk = ref_keys[self.self_attn_idx].to(torch.float16).contiguous()        # (B, N, S_ref, C)
             rv = ref_values[self.self_attn_idx].to(torch.float16).contiguous()
             n_ref, s_ref = rk.shape[1], rk.shape[2]
             rk2, rv2 = rk.view(-1, inner), rv.view(-1, inner)
             if not self.train_input:
-                kw = {}
+                kw, chunks = {}, []
             kw.update(k_ref=rk2, v_ref=rv2, n_ref=n_ref, s_ref=s_ref)
+            chunks += [(rk2, 0, s_ref, n_ref * s_ref, r * s_ref) for r in range(n_ref)]
             if self.use_adain:
                 sc, sh = L.adain_coeffs(v, rv2, batch=b, s_own=s_kv, n_ref=n_ref, s_ref=s_ref, channels=inner, eps=ADAIN_EPS)
                 kw.update(adain_scale=sc, adain_shift=sh)
-        o = L.shared_attn(q, heads=attn.heads, scale=attn.scale, batch=b, s_q=s, **kw)
+        if self.save_reference_mass and has_refs:
+            o, self.reference_mass = L.shared_attn(q, heads=attn.heads, scale=attn.scale, batch=b, s_q=s, chunk_mass=True, **kw)
+        else:
+            o = L.shared_attn(q, heads=attn.heads, scale=attn.scale, batch=b, s_q=s, **kw)
+        if self.save_self_attentions:                                                  # reference :258-260
+            from .attn_probs import dense_attention_probs
+            self.attention_probs = dense_attention_probs(q, 0, chunks, batch=b, heads=attn.heads, s_q=s, scale=attn.scale)
         return _finish(attn, o, w, b, s, residual, shape4, dtype)
 
 

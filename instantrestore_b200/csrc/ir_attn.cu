@@ -52,6 +52,8 @@ struct AttnKParams {
   int out_stride;
   int own_tiles, ref_tiles, total_tiles;
   int n_splits, tiles_per_split;
+  float2* mass_ws;    // [batch, heads, q tiles * 128, n_chunks + 1] (row sum, reference max) per chunk, then the row total
+  int n_chunks;
   float* part_o;      // [batch, heads, q tiles, n_splits, 128, 64] fp32 un-normalised partial outputs
   float2* part_ml;    // [batch, heads, q tiles, n_splits, 128] (running max in log2 units, row sum)
 };
@@ -233,8 +235,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     for (int i = threadIdx.x; i < p.n_ref * kD; i += blockDim.x) {
       const int r = i / kD, d = i % kD;
       const size_t g = (static_cast<size_t>(b) * p.n_ref + r) * C + head * kD + d;
-      sAd[(r * 2 + 0) * kD + d] = p.adain_scale[g];
-      sAd[(r * 2 + 1) * kD + d] = p.adain_shift[g];
+      sAd[(r * 2 + 0) * kD + d] = p.adain_scale ? p.adain_scale[g] : 1.0f;   // identity affine: per-chunk bookkeeping only
+      sAd[(r * 2 + 1) * kD + d] = p.adain_scale ? p.adain_shift[g] : 0.0f;
     }
   }
   tc_fence_before();
@@ -395,6 +397,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
         tmem_st_wait();
         tc_fence_before();
         acc_valid = true;
+        if (p.mass_ws) {
+          const int n_qrows = 2 * (gridDim.x / p.n_splits) * kQT;
+          p.mass_ws[((static_cast<size_t>(b) * p.heads + head) * n_qrows + (2 * pair + i) * kQT + row) * (p.n_chunks + 1) + tr.chunk] =
+              make_float2(l_seg, m_ref);
+        }
         l_tot += l_seg;
         l_seg = 0.f;
       }
@@ -409,6 +416,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
       }
       const uint32_t t_src = ADAIN ? t_A : t_O;
       const float l = ADAIN ? l_tot : l_seg;
+      if (ADAIN && p.mass_ws) {
+        const int n_qrows = 2 * (gridDim.x / p.n_splits) * kQT;
+        p.mass_ws[((static_cast<size_t>(b) * p.heads + head) * n_qrows + (2 * pair + i) * kQT + row) * (p.n_chunks + 1) + p.n_chunks] =
+            make_float2(l, m_ref);
+      }
       if (p.n_splits == 1) {
         const float inv = 1.0f / l;
         __half* op = p.out + (static_cast<size_t>(b) * p.s_q + qrow) * p.out_stride + head * kD;
@@ -490,6 +502,31 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restri
                    pack_half2(acc[q * 8 + 4] * inv, acc[q * 8 + 5] * inv), pack_half2(acc[q * 8 + 6] * inv, acc[q * 8 + 7] * inv));
 }
 
+// chunk_mass[b, h, c] = mean over queries of the softmax mass that lands on KV chunk c (what gradio_demo.py:118-133
+// derives from the dense attention_probs). grid = (heads, batch), block = 256; fixed-order block reduction.
+__global__ void __launch_bounds__(256) attn_mass_kernel(const float2* __restrict__ ws, int n_qrows, int s_q, int n_chunks,
+                                                        int heads, float* __restrict__ mass) {
+  __shared__ float red[256];
+  const int head = blockIdx.x, b = blockIdx.y;
+  const float2* base = ws + (static_cast<size_t>(b) * heads + head) * n_qrows * (n_chunks + 1);
+  for (int c = 0; c < n_chunks; ++c) {
+    float acc = 0.f;
+    for (int q = threadIdx.x; q < s_q; q += 256) {
+      const float2 tot = base[static_cast<size_t>(q) * (n_chunks + 1) + n_chunks];
+      const float2 seg = base[static_cast<size_t>(q) * (n_chunks + 1) + c];
+      acc += seg.x * fast_exp2(seg.y - tot.y) / tot.x;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) mass[(static_cast<size_t>(b) * heads + head) * n_chunks + c] = red[0] / s_q;
+    __syncthreads();
+  }
+}
+
 // Split-KV plan: the number of KV ranges that minimises (rounds over 148 SMs) x (tiles per range), with a small
 // charge per split for the partial write + combine.
 static int plan_splits(long units, int total_tiles, int requested) {
@@ -527,7 +564,6 @@ extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t st
   if (has_own && p->s_own <= 0) return set_error(IR_ERR_SHAPE, "ir_shared_attn_fwd: s_own=%d", p->s_own);
   if (p->batch <= 0 || p->heads <= 0 || p->s_q <= 0) return set_error(IR_ERR_SHAPE, "ir_shared_attn_fwd: non-positive dims");
   if ((p->adain_scale == nullptr) != (p->adain_shift == nullptr)) return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: adain scale/shift mismatch");
-  if (p->chunk_mass) return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: chunk_mass output not implemented yet");
   if (p->q_row_stride < p->q_col_off + p->heads * kD || (has_own && p->own_row_stride < p->heads * kD) ||
       (p->n_ref && p->ref_row_stride < p->ref_col_off + p->heads * kD))
     return set_error(IR_ERR_SHAPE, "ir_shared_attn_fwd: row stride smaller than heads*64 columns");
@@ -575,9 +611,11 @@ extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t st
   kp.s_q = p->s_q;
   kp.heads = p->heads;
   kp.scale_log2 = p->scale * 1.4426950408889634f;
-  const bool adain = p->n_ref > 0 && p->adain_scale != nullptr;
-  kp.adain_scale = adain ? p->adain_scale : nullptr;
-  kp.adain_shift = adain ? p->adain_shift : nullptr;
+  const bool want_mass = p->chunk_mass != nullptr;
+  const bool adain = p->n_ref > 0 && (p->adain_scale != nullptr || want_mass);   // per-chunk segments (identity affine for mass only)
+  kp.adain_scale = (p->n_ref > 0) ? p->adain_scale : nullptr;
+  kp.adain_shift = (p->n_ref > 0) ? p->adain_shift : nullptr;
+  kp.n_chunks = (has_own ? 1 : 0) + p->n_ref;
   kp.out = static_cast<__half*>(p->out);
   kp.out_stride = p->out_row_stride;
   kp.own_tiles = has_own ? (p->s_own + kKT - 1) / kKT : 0;
@@ -585,7 +623,15 @@ extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t st
   kp.total_tiles = kp.own_tiles + p->n_ref * (p->n_ref > 0 ? kp.ref_tiles : 0);
 
   const int pairs = (p->s_q + 2 * kQT - 1) / (2 * kQT);
-  int n_splits = plan_splits(static_cast<long>(pairs) * p->heads * p->batch, kp.total_tiles, p->kv_splits);
+  if (want_mass) {
+    if (p->n_ref == 0) return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: chunk_mass needs reference chunks");
+    const size_t need = static_cast<size_t>(p->batch) * p->heads * (2 * pairs * kQT) * (kp.n_chunks + 1) * sizeof(float2);
+    if (!p->workspace || p->workspace_bytes < need)
+      return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: chunk_mass needs %zu bytes of workspace", need);
+    if (p->kv_splits > 1) return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: chunk_mass and kv_splits > 1 are exclusive");
+    kp.mass_ws = static_cast<float2*>(p->workspace);
+  }
+  int n_splits = want_mass ? 1 : plan_splits(static_cast<long>(pairs) * p->heads * p->batch, kp.total_tiles, p->kv_splits);
   if (n_splits > 1 && !p->workspace) {
     if (p->kv_splits > 1) return set_error(IR_ERR_ARG, "ir_shared_attn_fwd: kv_splits=%d needs a workspace", p->kv_splits);
     n_splits = 1;
@@ -612,6 +658,10 @@ extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t st
   if (adain) shared_attn_kernel<true><<<grid, kAttnThreads, kAttnSmem, stream>>>(kp);
   else shared_attn_kernel<false><<<grid, kAttnThreads, kAttnSmem, stream>>>(kp);
   IR_CUDA_LAUNCH_CHECK("shared_attn launch");
+  if (want_mass) {
+    attn_mass_kernel<<<dim3(p->heads, p->batch), 256, 0, stream>>>(kp.mass_ws, 2 * pairs * kQT, p->s_q, kp.n_chunks, p->heads, p->chunk_mass);
+    IR_CUDA_LAUNCH_CHECK("attn_mass launch");
+  }
   if (n_splits > 1) {
     attn_combine_kernel<<<dim3(2 * pairs, p->heads, p->batch), 128, 0, stream>>>(kp.part_o, kp.part_ml, n_splits, 2 * pairs, p->heads,
                                                                                  p->s_q, kp.out, kp.out_stride);

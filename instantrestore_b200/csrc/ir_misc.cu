@@ -332,6 +332,71 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
   }
 }
 
+// Row softmax for rows longer than 8192 columns: three passes over global memory (max, sum, write).
+__global__ void __launch_bounds__(256) softmax_rows_long_kernel(__half* __restrict__ x, int cols, int row_stride, float scale_log2) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  __half* xr = x + static_cast<size_t>(blockIdx.x) * row_stride;
+  const int nvec = cols >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + (i << 3));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      mx = fmaxf(mx, fmaxf(f.x, f.y));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    bc = m;
+  }
+  __syncthreads();
+  const float m = bc * scale_log2;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + (i << 3));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      sum += fast_exp2(fmaf(f.x, scale_log2, -m)) + fast_exp2(fmaf(f.y, scale_log2, -m));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    bc = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = bc;
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + (i << 3));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+    float e[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      e[2 * j] = fast_exp2(fmaf(f.x, scale_log2, -m)) * inv;
+      e[2 * j + 1] = fast_exp2(fmaf(f.y, scale_log2, -m)) * inv;
+    }
+    *reinterpret_cast<uint4*>(xr + (i << 3)) =
+        make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
+  }
+}
+
 template <typename T>
 __global__ void image_in_kernel(const T* __restrict__ x, __half* __restrict__ out, int c, int hw, int c_pad, long total_px) {
   // one thread per pixel: reads c planes (coalesced across threads), writes c_pad halfs (16-byte stores)
@@ -493,11 +558,15 @@ extern "C" int ir_softmax_rows(void* x, int rows, int cols, int row_stride, floa
   using namespace ir;
   if (!x) return set_error(IR_ERR_ARG, "ir_softmax_rows: NULL argument");
   if (int rc = check_arch()) return rc;
-  if (rows <= 0 || cols <= 0 || cols % 8 != 0 || cols > 8192 || row_stride % 8 != 0 || row_stride < cols)
-    return set_error(IR_ERR_SHAPE, "ir_softmax_rows: rows=%d cols=%d stride=%d (cols %% 8 == 0, cols <= 8192)", rows, cols, row_stride);
+  if (rows <= 0 || cols <= 0 || cols % 8 != 0 || row_stride % 8 != 0 || row_stride < cols)
+    return set_error(IR_ERR_SHAPE, "ir_softmax_rows: rows=%d cols=%d stride=%d (cols %% 8 == 0)", rows, cols, row_stride);
   if (reinterpret_cast<uintptr_t>(x) & 15) return set_error(IR_ERR_ALIGN, "ir_softmax_rows: pointer not 16-byte aligned");
-  softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<__half*>(x), cols, row_stride,
-                                                                            scale * 1.4426950408889634f);
+  if (cols <= 8192)
+    softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<__half*>(x), cols, row_stride,
+                                                                              scale * 1.4426950408889634f);
+  else
+    softmax_rows_long_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<__half*>(x), cols, row_stride,
+                                                                                   scale * 1.4426950408889634f);
   IR_CUDA_LAUNCH_CHECK("softmax_rows launch");
   return 0;
 }

@@ -134,12 +134,12 @@ class Predictor:
 
     def _forward_batch(self, input_images: torch.Tensor, conditioning_images: torch.Tensor, face_embeds=None,
                        calc_attn_probs: bool = False):
-        if calc_attn_probs:
-            raise NotImplementedError("attention_probs are never materialised by the fused kernel")
         valid_indices = torch.ones(input_images.size(0), dtype=torch.int64) * self.max_conditioning_images
-        x_pred, _, _ = self.net.forward(input_images.to(self.device, self.dtype),
-                                        conditioning_images=conditioning_images.to(self.device, self.dtype),
-                                        valid_indices=valid_indices)
+        x_pred, _, maps = self.net.forward(input_images.to(self.device, self.dtype),
+                                           conditioning_images=conditioning_images.to(self.device, self.dtype),
+                                           valid_indices=valid_indices, return_self_attention_maps=calc_attn_probs)
+        if calc_attn_probs:                                         # test.py:107-110
+            return x_pred, [p.float().cpu().detach() for p in maps]
         return x_pred, None
 
     def prepare_conditioning_images(self, cond_imgs: List[Image.Image]):

@@ -216,8 +216,6 @@ class RestorePipeline:
         serving loop can keep requests in flight on different streams; results of a slot stay valid until its next call."""
         if face_embeds is not None:
             raise NotImplementedError("condition_on_face_embeds is False in the released configs")
-        if return_self_attention_maps:
-            raise NotImplementedError("the fused attention kernel never materialises attention maps")
         dev = self.dev
         c_t = c_t.to(dev)
         if c_t.dtype not in (torch.float16, torch.float32):
@@ -243,9 +241,17 @@ class RestorePipeline:
                 valid = None
         ins = dict(c_t=c_t.contiguous(), cond=None if cond is None else cond.contiguous(), eps_main=eps_main.contiguous(),
                    eps_ref=eps_ref, noise_main=noise_main.contiguous(), noise_ref=noise_ref)
-        if not self.use_cuda_graph:
-            out = self._step(ins["c_t"], ins["cond"], ins["eps_main"], ins["eps_ref"], ins["noise_main"], ins["noise_ref"], valid)
-            return out, None, None
+        if return_self_attention_maps or not self.use_cuda_graph:
+            # attention maps: eager (no graph), the 9 shared layers also build the dense (B, H, S, S_k) softmax matrix the
+            # reference exposes as SharedAttnProcessor.attention_probs (pix2pix_turbo.py:338-341)
+            main = self.engine.main
+            main.save_attention_probs = bool(return_self_attention_maps)
+            try:
+                out = self._step(ins["c_t"], ins["cond"], ins["eps_main"], ins["eps_ref"], ins["noise_main"], ins["noise_ref"], valid)
+                maps = list(main.attention_probs) if return_self_attention_maps else None
+            finally:
+                main.save_attention_probs = False
+            return out, None, maps
         key = (tuple(c_t.shape), c_t.dtype, None if cond is None else tuple(cond.shape), tuple(valid) if valid else None, slot)
         g = self._graphs.get(key)
         if g is None:

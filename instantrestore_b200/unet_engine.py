@@ -90,6 +90,11 @@ class UNetEngine:
         self.freeu = freeu
         self.captured: List[RefKV] = []
         self.debug: Optional[dict] = None     # set to {} to record per-module outputs (tools/debug_engine.py)
+        # opt-in by-products of the 9 shared-attention layers (reference attn_processors.py:258-260; gradio_demo.py:118-133)
+        self.save_attention_probs = False     # dense (B, H, S, S_k) per layer -> self.attention_probs
+        self.save_reference_mass = False      # (B, H, n_chunks) per layer -> self.reference_mass
+        self.attention_probs: List[torch.Tensor] = []
+        self.reference_mass: List[torch.Tensor] = []
         dev = self.dev
         boc = spec.block_out_channels
         cap = caption_enc.detach().to(torch.float32).cpu()
@@ -202,7 +207,8 @@ class UNetEngine:
             self.captured.append(RefKV(buf=qkv, k_off=C, v_off=2 * C, n_ref=0, s_ref=S))
         kw = {}
         own = True
-        if self.consume_refs and ref is not None:
+        shared_layer = self.consume_refs and ref is not None
+        if shared_layer:
             kw.update(k_ref=ref.buf[:, ref.k_off:], v_ref=ref.buf[:, ref.v_off:], n_ref=ref.n_ref, s_ref=ref.s_ref)
             if self.use_adain:
                 sc, sh = L.adain_coeffs(qkv[:, 2 * C:], ref.buf[:, ref.v_off:], batch=B, s_own=S, n_ref=ref.n_ref,
@@ -211,7 +217,16 @@ class UNetEngine:
             own = self.train_input
         if own:
             kw.update(k_own=qkv[:, C:], v_own=qkv[:, 2 * C:], s_own=S)
-        a = L.shared_attn(qkv, heads=heads, scale=scale, batch=B, s_q=S, **kw)
+        if shared_layer and self.save_reference_mass:
+            a, mass = L.shared_attn(qkv, heads=heads, scale=scale, batch=B, s_q=S, chunk_mass=True, **kw)
+            self.reference_mass.append(mass)
+        else:
+            a = L.shared_attn(qkv, heads=heads, scale=scale, batch=B, s_q=S, **kw)
+        if shared_layer and self.save_attention_probs:
+            from .attn_probs import dense_attention_probs
+            chunks = [(qkv, C, S, S, 0)] if own else []
+            chunks += [(ref.buf, ref.k_off, ref.s_ref, ref.n_ref * ref.s_ref, r * ref.s_ref) for r in range(ref.n_ref)]
+            self.attention_probs.append(dense_attention_probs(qkv, 0, chunks, batch=B, heads=heads, s_q=S, scale=scale))
         h = self._lin(a, p["out1"], residual=h)
         # --- attn2: cross attention against the constant caption K/V
         n = L.layernorm(h, p["ln2"].g, p["ln2"].b)
@@ -268,6 +283,7 @@ class UNetEngine:
         h, skips, B, H, W = state
         skips = list(skips)
         shared_idx = 0
+        self.attention_probs, self.reference_mass = [], []
         dbg = self.debug
         for i, (layers, us) in enumerate(self.up):
             bscale, sscale = 1.0, 1.0

@@ -176,3 +176,27 @@ def test_identity_result_is_independent_of_batch_position():
         one = eng.forward_latents(enc[i:i + 1].contiguous(), refs[i:i + 1].contiguous(), nm[i:i + 1].contiguous(),
                                   nr3[i].contiguous())
         assert rel_l2(one[0], full[i]) <= 1e-3, i
+
+
+# ------------------------------------------------------------------------------------------------ attention by-products
+@pytest.mark.parametrize("case", [c for c in _processor_cases() if c[3] > 0], ids=[c[0] for c in _processor_cases() if c[3] > 0])
+def test_attention_probs_and_reference_mass_vs_reference_golden(case, golden):
+    """save_self_attentions keeps exposing `attention_probs` (reference :258-260); `reference_mass` equals the per-chunk
+    column mass of the reference's dense matrix averaged over queries (what gradio_demo.py:118-133 computes)."""
+    from instantrestore_b200.attn_processors import SharedAttnProcessor
+    from oracle.make_golden import attn_inputs
+    name, heads, s, n_ref, use_adain, train_input, zeroed = case
+    attn, hidden, rk, rv = attn_inputs(heads, s, n_ref, zeroed)
+    proc = SharedAttnProcessor(self_attn_idx=0, save_self_attentions=True, use_adain=use_adain, train_input=train_input)
+    proc.save_reference_mass = True
+    out = proc(attn.cuda(), hidden.cuda(), ref_keys=[rk.cuda()], ref_values=[rv.cuda()])
+    g = golden(name)
+    assert rel_l2(out, torch.as_tensor(g["out"])) <= OP_TOL
+    colsum = torch.as_tensor(g["probs_colsum"])                        # (B, H, S_k): sum over queries
+    n_chunks = n_ref + (1 if train_input else 0)
+    assert proc.attention_probs.shape == (2, heads, s, n_chunks * s)
+    assert rel_l2(proc.attention_probs.float().sum(dim=2), colsum) <= 2e-3
+    want_mass = colsum.view(2, heads, n_chunks, s).sum(-1) / s
+    assert proc.reference_mass.shape == (2, heads, n_chunks)
+    assert float((proc.reference_mass.cpu() - want_mass).abs().max()) <= 2e-3
+    assert float((proc.reference_mass.sum(-1) - 1).abs().max()) <= 1e-3

@@ -193,3 +193,7 @@ def test_predictor_entry_on_a_synthetic_checkpoint(tmp_path):
     assert img.size == (512, 512) and vis.size == (512, 1536) and probs is None
     arr = np.asarray(img).astype(np.float32)
     assert np.isfinite(arr).all() and arr.std() > 1.0
+    # calc_attn_probs=True (test.py:93-108): one dense map per shared layer, (B, H, S, N_ref * S), rows sum to 1
+    img2, _, probs = pred.predict(mk(), [mk(), mk()], calc_attn_probs=True)
+    assert len(probs) == 9 and probs[0].shape == (1, 4, 256, 2 * 256) and probs[-1].shape == (1, 1, 4096, 2 * 4096)
+    assert float((probs[3].sum(-1) - 1).abs().max()) <= 2e-3
