@@ -21,8 +21,12 @@ forward (:258-260); the fused kernel never builds that matrix, so it is recomput
 (B, H, n_chunks): the softmax mass per KV chunk averaged over queries, which is what gradio_demo.py:118-133 derives
 from the dense matrix.
 
+`FaceIDAttnProcessor(hidden_size, self_attn_idx=None, cross_attention_dim=None, embed_dim=512)` (:100-180) is provided
+as a drop-in too (face embeddings -> face_projection -> to_k/to_v_face_embed -> attention), although every released
+config keeps condition_on_face_embeds False and the whole-step engine (pipeline.py) does not take face embeddings.
+
 Not provided on this path: attention masks, attn.group_norm / spatial_norm / norm_cross (all None for the SD-Turbo
-UNet) and FaceIDAttnProcessor (condition_on_face_embeds=False in the released configs).
+UNet).
 """
 from __future__ import annotations
 
@@ -135,6 +139,44 @@ class AttnProcessor(nn.Module):
         return _finish(attn, o, w, b, s, residual, shape4, dtype)
 
 
+class FaceIDAttnProcessor(nn.Module):
+    """Reference :100-180: keys/values come from face-recognition embeddings (B, n_faces, embed_dim) through
+    face_projection -> to_k_face_embed / to_v_face_embed; the parameters live on the processor (state_dict keys
+    `<attn>.processor.{face_projection,to_k_face_embed,to_v_face_embed}.*`)."""
+
+    def __init__(self, hidden_size, self_attn_idx=None, cross_attention_dim=None, embed_dim: int = 512):
+        super().__init__()
+        self.hidden_size, self.cross_attention_dim, self.self_attn_idx = hidden_size, cross_attention_dim, self_attn_idx
+        width = cross_attention_dim or hidden_size
+        self.face_projection = nn.Linear(embed_dim, width)
+        self.to_k_face_embed = nn.Linear(width, hidden_size, bias=False)
+        self.to_v_face_embed = nn.Linear(width, hidden_size, bias=False)
+        self._cache = _ProjCache()
+        self.reset()
+
+    def reset(self):
+        self.keys, self.values, self.is_self_attn = None, None, None
+
+    def forward(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, ref_keys=None,
+                ref_values=None):
+        _check(attn, hidden_states, attention_mask)
+        residual, dtype = hidden_states, hidden_states.dtype
+        x, b, s, c, shape4 = _as_tokens(hidden_states)
+        self.is_self_attn = encoder_hidden_states is None
+        w = self._cache.get(attn, False)
+        ctx = (hidden_states if self.is_self_attn else encoder_hidden_states).to(torch.float16)
+        s_kv = ctx.shape[1]
+        ctx = ctx.reshape(-1, ctx.shape[-1]).contiguous()
+        h = lambda t: t.detach().to(torch.float16).contiguous()
+        f = lambda t: None if t is None else t.detach().float().contiguous()
+        q = _project(x, w["q"], w["qb"])
+        face = _project(ctx, h(self.face_projection.weight), f(self.face_projection.bias))
+        k = _project(face, h(self.to_k_face_embed.weight), None)
+        v = _project(face, h(self.to_v_face_embed.weight), None)
+        o = L.shared_attn(q, heads=attn.heads, scale=attn.scale, batch=b, s_q=s, k_own=k, v_own=v, s_own=s_kv)
+        return _finish(attn, o, w, b, s, residual, shape4, dtype)
+
+
 class SharedAttnProcessor(nn.Module):
     def __init__(self, self_attn_idx: int = None, save_self_attentions: bool = False, use_adain: bool = False,
                  train_input: bool = True):
@@ -201,11 +243,14 @@ def _hidden_size(unet, name):
 
 def register_attention_processor(unet, cfg, save_self_attentions: bool = False):
     """Same numbering as the reference (:282-321): only `up_blocks.*.attn1` get a self_attn_idx (0..8, module order)."""
-    if getattr(cfg, "condition_on_face_embeds", False):
-        raise NotImplementedError("FaceIDAttnProcessor is not provided (condition_on_face_embeds=False in released configs)")
     procs, idx = {}, 0
     for name in unet.attn_processors.keys():
         shared_layer = name.endswith("attn1.processor") and name.startswith("up_blocks")
+        if not name.endswith("attn1.processor") and getattr(cfg, "condition_on_face_embeds", False):   # :296-300
+            procs[name] = FaceIDAttnProcessor(self_attn_idx=None, hidden_size=_hidden_size(unet, name),
+                                              cross_attention_dim=unet.config.cross_attention_dim, embed_dim=512
+                                              ).to(unet.device, dtype=unet.dtype)
+            continue
         procs[name] = SharedAttnProcessor(self_attn_idx=idx if shared_layer else None,
                                           save_self_attentions=save_self_attentions and name.endswith("attn1.processor"),
                                           use_adain=cfg.use_adain, train_input=cfg.train_input)

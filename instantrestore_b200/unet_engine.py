@@ -89,6 +89,10 @@ class UNetEngine:
         self.consume_refs, self.capture_kv = consume_refs, capture_kv
         self.freeu = freeu
         self.captured: List[RefKV] = []
+        # The reference UNet is only run for its 9 captured K/V projections (reference pix2pix_turbo.py:255-266; the
+        # prediction itself feeds an image decode nobody reads, :277-278): stop right after the last projection and skip
+        # that block's attention / cross-attention / feed-forward, conv_norm_out and conv_out.
+        self.stop_after_last_kv = capture_kv
         self.debug: Optional[dict] = None     # set to {} to record per-module outputs (tools/debug_engine.py)
         # opt-in by-products of the 9 shared-attention layers (reference attn_processors.py:258-260; gradio_demo.py:118-133)
         self.save_attention_probs = False     # dense (B, H, S, S_k) per layer -> self.attention_probs
@@ -195,7 +199,7 @@ class UNetEngine:
         skip = x if p["shortcut"] is None else self._lin(x, p["shortcut"])
         return self._conv(t, p["conv2"], B, H, W, residual=skip)
 
-    def _transformer(self, x, p, B, S, ref: Optional[RefKV] = None, capture: bool = False):
+    def _transformer(self, x, p, B, S, ref: Optional[RefKV] = None, capture: bool = False, stop_after_kv: bool = False):
         C, heads = p["ch"], p["heads"]
         scale = 0.125  # head_dim ** -0.5, head_dim == 64
         t = self._gn(x, p["norm"], B, S, 1e-6, False)
@@ -205,6 +209,8 @@ class UNetEngine:
         qkv = self._lin(n, p["qkv"])                                   # [B*S, 3C]: q | k | v
         if capture:
             self.captured.append(RefKV(buf=qkv, k_off=C, v_off=2 * C, n_ref=0, s_ref=S))
+            if stop_after_kv:
+                return None        # nothing downstream of the last captured K/V is ever read (see forward_up)
         kw = {}
         own = True
         shared_layer = self.consume_refs and ref is not None
@@ -300,7 +306,10 @@ class UNetEngine:
                 if tr is not None:
                     ref = ref_kv[shared_idx] if (self.consume_refs and ref_kv is not None) else None
                     shared_idx += 1
-                    h = self._transformer(h, tr, B, H * W, ref, capture=self.capture_kv)
+                    last_kv = self.capture_kv and self.stop_after_last_kv and i == len(self.up) - 1 and j == len(layers) - 1
+                    h = self._transformer(h, tr, B, H * W, ref, capture=self.capture_kv, stop_after_kv=last_kv)
+                    if last_kv:
+                        return None
                     if dbg is not None:
                         dbg[f"up_blocks.{i}.attentions.{j}"] = h
             if us is not None:

@@ -63,6 +63,21 @@ def attn_inputs(heads, s, n_ref, zeroed, seed=7):
     return attn, hidden, rk, rv
 
 
+def faceid_case(proc_cls, device="cpu"):
+    """FaceIDAttnProcessor(hidden 128, cross_attention_dim 256, embed_dim 512) on 4 face embeddings per sample."""
+    from oracle.diffusers024 import Attention
+    from oracle.synth import seeded_init_
+    g = torch.Generator().manual_seed(17)
+    attn = seeded_init_(Attention(query_dim=128, cross_attention_dim=256, heads=2, dim_head=64), 17).eval().requires_grad_(False)
+    proc = seeded_init_(proc_cls(hidden_size=128, cross_attention_dim=256, embed_dim=512), 18).eval().requires_grad_(False)
+    hidden = torch.randn(2, 64, 128, generator=g)
+    faces = torch.randn(2, 4, 512, generator=g)
+    attn, proc = attn.to(device), proc.to(device)
+    with torch.no_grad():
+        out = proc(attn, hidden.to(device), encoder_hidden_states=faces.to(device))
+    return out, proc
+
+
 def build_pipeline(RefUNet, ref_ap, cfg, flags, lora_rank, seed=0):
     """Reference UNet classes + reference processors, weights copied from the seeded oracle models."""
     from oracle import synth
@@ -157,6 +172,10 @@ def main():
     with torch.no_grad():
         out = cap_proc(attn, hidden)
     np.savez_compressed(GOLDEN / "attn_kv_capture.npz", out=out.numpy(), keys=cap_proc.keys.numpy(), values=cap_proc.values.numpy())
+
+    # the face-embedding cross-attention processor (reference attn_processors.py:100-180)
+    out, _ = faceid_case(ref_ap.FaceIDAttnProcessor)
+    np.savez_compressed(GOLDEN / "attn_faceid.npz", out=out.numpy())
 
     # 2) FreeU (reference block.py:3495-3520 on top of the restated fourier_filter)
     g = torch.Generator().manual_seed(11)

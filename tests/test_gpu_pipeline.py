@@ -200,3 +200,12 @@ def test_attention_probs_and_reference_mass_vs_reference_golden(case, golden):
     assert proc.reference_mass.shape == (2, heads, n_chunks)
     assert float((proc.reference_mass.cpu() - want_mass).abs().max()) <= 2e-3
     assert float((proc.reference_mass.sum(-1) - 1).abs().max()) <= 1e-3
+
+
+def test_faceid_processor_vs_reference_golden(golden):
+    from instantrestore_b200.attn_processors import FaceIDAttnProcessor
+    from oracle.make_golden import faceid_case
+    out, proc = faceid_case(FaceIDAttnProcessor, device="cuda")
+    assert rel_l2(out, torch.as_tensor(golden("attn_faceid")["out"])) <= OP_TOL
+    assert sorted(k for k in proc.state_dict()) == ["face_projection.bias", "face_projection.weight", "to_k_face_embed.weight",
+                                                    "to_v_face_embed.weight"]

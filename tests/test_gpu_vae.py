@@ -197,3 +197,30 @@ def test_predictor_entry_on_a_synthetic_checkpoint(tmp_path):
     img2, _, probs = pred.predict(mk(), [mk(), mk()], calc_attn_probs=True)
     assert len(probs) == 9 and probs[0].shape == (1, 4, 256, 2 * 256) and probs[-1].shape == (1, 1, 4096, 2 * 4096)
     assert float((probs[3].sum(-1) - 1).abs().max()) <= 2e-3
+
+
+def test_concurrent_graph_slots_match_sequential():
+    """Two graph instances (slots) replayed concurrently on two streams give exactly the results of sequential calls:
+    per-slot static buffers and split-KV scratch do not alias."""
+    from oracle import synth
+    from oracle.make_golden import IMAGE_LATENT, IMAGE_SIZE
+    pipe = _tiny_pipeline(True, False, 4, 4, False, True)
+    c_t, cond, eps_main, eps_ref, noise_main, noise_ref = synth.images(2, 2, IMAGE_SIZE, IMAGE_LATENT)
+    mk = lambda i: dict(conditioning_images=cond[i:i + 1].cuda().half(), eps_main=eps_main[i:i + 1], eps_ref=eps_ref[2 * i:2 * i + 2],
+                        noise_main=noise_main[i:i + 1], noise_ref=noise_ref[2 * i:2 * i + 2])
+    want = [pipe.forward(c_t[i:i + 1].cuda().half(), slot=0, **mk(i))[0].clone() for i in range(2)]
+    for i in range(2):                                     # capture slot 1, warm slot 0
+        pipe.forward(c_t[i:i + 1].cuda().half(), slot=i, **mk(i))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for _ in range(3):
+        outs = []
+        for i in range(2):
+            streams[i].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(streams[i]):
+                outs.append(pipe.forward(c_t[i:i + 1].cuda().half(), slot=i, **mk(i))[0])
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        for i in range(2):
+            assert torch.equal(outs[i], want[i]), i

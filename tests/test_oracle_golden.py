@@ -169,3 +169,10 @@ def test_image_pipeline_oracle_matches_reference(case, golden):
     pipe = tiny_image_models(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, reference_forwards=False)
     out = pipe.forward(*synth.images(batch, n_ref, IMAGE_SIZE, IMAGE_LATENT))
     assert float((out - torch.as_tensor(golden(name)["image"]).float()).abs().max()) <= 1e-3
+
+
+def test_faceid_processor_matches_reference(golden):
+    from oracle.make_golden import faceid_case
+    out, proc = faceid_case(oap.FaceIDAttnProcessor)
+    _close(out, golden("attn_faceid")["out"])
+    assert proc.is_self_attn is False
