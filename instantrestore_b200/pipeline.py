@@ -31,6 +31,16 @@ class ModelFlags:
     lora_rank_unet: int = 32
 
 
+@dataclass
+class RefCache:
+    """Keys/values of one batch of identities' reference images for the 9 shared-attention layers, kept on the device
+    so that many degraded frames of the same people (video, albums) amortise the reference pass.
+    The reference redraws the reference-latent noise on every call (pix2pix_turbo.py:245-248); a cache fixes that draw."""
+    kv: list            # 9 x RefKV over persistent buffers
+    batch: int
+    n_ref: int
+
+
 def ddpm_coeffs(t: int, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012):
     """sqrt(alpha_bar_t), sqrt(1 - alpha_bar_t) of the sd-turbo scaled-linear schedule (reference models/model.py:4-12)."""
     betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
@@ -189,18 +199,7 @@ class RestorePipeline:
             state = eng.main.forward_down_mid(x, B, H, W)
         ref_kv = None
         if cond is not None and self.original_vae is not None:
-            N = cond.shape[1]
-            lat = self.original_vae.encode(cond.reshape(B * N, *cond.shape[2:]), eps_ref)
-            rin = L.latent_in(lat, noise_ref, eng.a_ref, eng.s_ref)
-            eng.ref.forward(rin, B * N, lat.shape[2], lat.shape[3])
-            ref_kv = []
-            for cap in eng.ref.captured:
-                if valid is not None:
-                    rows = cap.buf.view(B, N, cap.s_ref, -1)
-                    for b, nv in enumerate(valid):
-                        if nv < N:
-                            rows[b, nv:, :, cap.k_off:].zero_()
-                ref_kv.append(RefKV(buf=cap.buf, k_off=cap.k_off, v_off=cap.v_off, n_ref=N, s_ref=cap.s_ref))
+            ref_kv = self._reference_kv(cond, eps_ref, noise_ref, valid, B)
         cur.wait_stream(side)                                # join
         for t in (enc, x, state[0], *[sk[0] for sk in state[1]], *[sk[0] for sk in skips]):
             t.record_stream(cur)
@@ -208,12 +207,73 @@ class RestorePipeline:
         x0 = L.latent_out(eps, enc, noise_main, eng.a_main, eng.s_main)
         return self.vae.decode(x0, skip_acts=skips, dtype=self.out_dtype)
 
+    # ------------------------------------------------------------------------------------------ reference K/V cache
+    def _reference_kv(self, cond, eps_ref, noise_ref, valid, B):
+        """Reference path of the step: VAE-encode the reference images, run the reference UNet, zero padded slots."""
+        eng = self.engine
+        N = cond.shape[1]
+        lat = self.original_vae.encode(cond.reshape(B * N, *cond.shape[2:]), eps_ref)
+        rin = L.latent_in(lat, noise_ref, eng.a_ref, eng.s_ref)
+        eng.ref.forward(rin, B * N, lat.shape[2], lat.shape[3])
+        ref_kv = []
+        for cap in eng.ref.captured:
+            if valid is not None:
+                rows = cap.buf.view(B, N, cap.s_ref, -1)
+                for b, nv in enumerate(valid):
+                    if nv < N:
+                        rows[b, nv:, :, cap.k_off:].zero_()
+            ref_kv.append(RefKV(buf=cap.buf, k_off=cap.k_off, v_off=cap.v_off, n_ref=N, s_ref=cap.s_ref))
+        return ref_kv
+
+    @torch.no_grad()
+    def extract_reference_kv(self, conditioning_images: torch.Tensor, valid_indices=None, *, eps_ref=None, noise_ref=None) -> RefCache:
+        """Runs get_conditioning_keys_values (pix2pix_turbo.py:242-279) once and keeps the 9 K/V pairs on the device;
+        pass the result as `ref_cache=` to forward() for every degraded image of the same identities."""
+        if self.original_vae is None:
+            raise RuntimeError("use_shared_attention is False: there are no reference keys/values")
+        dev = self.dev
+        cond = conditioning_images.to(dev)
+        if cond.dtype not in (torch.float16, torch.float32):
+            cond = cond.float()
+        B, N, _, H, W = cond.shape
+        h, w = H // 8, W // 8
+        rnd = lambda *s: torch.randn(*s, device=dev, dtype=torch.float32, generator=self._gen)
+        eps_ref = rnd(B * N, 4, h, w) if eps_ref is None else eps_ref.to(dev, torch.float32)
+        noise_ref = rnd(B * N, 4, h, w) if noise_ref is None else noise_ref.to(dev, torch.float32)
+        valid = None
+        if valid_indices is not None:
+            valid = [int(v) for v in valid_indices]
+            if all(v >= N for v in valid):
+                valid = None
+        kv = self._reference_kv(cond.contiguous(), eps_ref.contiguous(), noise_ref.contiguous(), valid, B)
+        # keep only the K | V columns ([B*N*S, 2C]) in buffers the cache owns
+        kept = []
+        for r in kv:
+            c = r.v_off - r.k_off
+            buf = r.buf[:, r.k_off:r.k_off + 2 * c].contiguous()
+            kept.append(RefKV(buf=buf, k_off=0, v_off=c, n_ref=r.n_ref, s_ref=r.s_ref))
+        return RefCache(kv=kept, batch=B, n_ref=N)
+
+    def _step_cached(self, c_t, eps_main, noise_main, cache: RefCache):
+        eng = self.engine
+        B = c_t.shape[0]
+        enc = self.vae.encode(c_t, eps_main)
+        skips = self.vae.skip_acts
+        _, _, H, W = enc.shape
+        x = L.latent_in(enc, noise_main, eng.a_main, eng.s_main)
+        eps = eng.main.forward(x, B, H, W, ref_kv=cache.kv)
+        x0 = L.latent_out(eps, enc, noise_main, eng.a_main, eng.s_main)
+        return self.vae.decode(x0, skip_acts=skips, dtype=self.out_dtype)
+
     @torch.no_grad()
     def forward(self, c_t: torch.Tensor, face_embeds=None, conditioning_images: Optional[torch.Tensor] = None,
                 valid_indices=None, mask=None, return_self_attention_maps: bool = False, *, eps_main=None, eps_ref=None,
-                noise_main=None, noise_ref=None, slot: int = 0):
+                noise_main=None, noise_ref=None, slot: int = 0, ref_cache: Optional[RefCache] = None):
         """`slot` selects one of several independent CUDA-graph instances (own static buffers and scratch), so that a
-        serving loop can keep requests in flight on different streams; results of a slot stay valid until its next call."""
+        serving loop can keep requests in flight on different streams; results of a slot stay valid until its next call.
+        `ref_cache` (from extract_reference_kv) replaces `conditioning_images`: the reference path is skipped."""
+        if ref_cache is not None:
+            return self._forward_cached(c_t, ref_cache, eps_main, noise_main, slot)
         if face_embeds is not None:
             raise NotImplementedError("condition_on_face_embeds is False in the released configs")
         dev = self.dev
@@ -265,6 +325,41 @@ class RestorePipeline:
         return g["out"], None, None
 
     __call__ = forward
+
+    def _forward_cached(self, c_t, cache: RefCache, eps_main, noise_main, slot):
+        dev = self.dev
+        c_t = c_t.to(dev)
+        if c_t.dtype not in (torch.float16, torch.float32):
+            c_t = c_t.float()
+        B, _, H, W = c_t.shape
+        if B != cache.batch:
+            raise ValueError(f"ref_cache holds {cache.batch} identities, got a batch of {B}")
+        rnd = lambda *s: torch.randn(*s, device=dev, dtype=torch.float32, generator=self._gen)
+        eps_main = rnd(B, 4, H // 8, W // 8) if eps_main is None else eps_main.to(dev, torch.float32)
+        noise_main = rnd(B, 4, H // 8, W // 8) if noise_main is None else noise_main.to(dev, torch.float32)
+        if not self.use_cuda_graph:
+            return self._step_cached(c_t.contiguous(), eps_main.contiguous(), noise_main.contiguous(), cache), None, None
+        key = ("cached", tuple(c_t.shape), c_t.dtype, id(cache), slot)
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(c_t=c_t.clone(), eps_main=eps_main.clone(), noise_main=noise_main.clone(), cache=cache)
+            with L.scratch_namespace(("graph", id(self), len(self._graphs))):
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    self._step_cached(st["c_t"], st["eps_main"], st["noise_main"], cache)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    st["out"] = self._step_cached(st["c_t"], st["eps_main"], st["noise_main"], cache)
+            st["graph"] = graph
+            g = self._graphs[key] = st
+        g["c_t"].copy_(c_t, non_blocking=True)
+        g["eps_main"].copy_(eps_main, non_blocking=True)
+        g["noise_main"].copy_(noise_main, non_blocking=True)
+        g["graph"].replay()
+        return g["out"], None, None
 
     def _capture(self, ins, valid):
         st = {k: (None if v is None else v.clone()) for k, v in ins.items()}

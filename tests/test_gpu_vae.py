@@ -224,3 +224,26 @@ def test_concurrent_graph_slots_match_sequential():
         torch.cuda.synchronize()
         for i in range(2):
             assert torch.equal(outs[i], want[i]), i
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cudagraph"])
+def test_reference_kv_cache_matches_uncached(graph):
+    """extract_reference_kv + forward(ref_cache=...) == forward(conditioning_images=...) with the same draws, and the
+    cache serves further degraded images of the same identities."""
+    from oracle import synth
+    from oracle.make_golden import IMAGE_LATENT, IMAGE_SIZE
+    pipe = _tiny_pipeline(True, False, 4, 4, False, graph)
+    c_t, cond, eps_main, eps_ref, noise_main, noise_ref = synth.images(2, 3, IMAGE_SIZE, IMAGE_LATENT)
+    valid = [3, 2]
+    want, _, _ = pipe.forward(c_t.cuda().half(), conditioning_images=cond.cuda().half(), valid_indices=valid, eps_main=eps_main,
+                              eps_ref=eps_ref, noise_main=noise_main, noise_ref=noise_ref)
+    want = want.clone()
+    cache = pipe.extract_reference_kv(cond.cuda().half(), valid, eps_ref=eps_ref, noise_ref=noise_ref)
+    assert len(cache.kv) == 9 and cache.n_ref == 3
+    got, _, _ = pipe.forward(c_t.cuda().half(), ref_cache=cache, eps_main=eps_main, noise_main=noise_main)
+    assert rel_l2(got.float(), want.float()) <= 1e-3        # different attention split plans may differ in the last bit
+    c2 = c_t.flip(0).contiguous()
+    a, _, _ = pipe.forward(c2.cuda().half(), ref_cache=cache, eps_main=eps_main, noise_main=noise_main)
+    a = a.clone()
+    b, _, _ = pipe.forward(c2.cuda().half(), ref_cache=cache, eps_main=eps_main, noise_main=noise_main)
+    assert torch.equal(a, b) and not torch.equal(a, got)
