@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--lora-rank-vae", type=int, default=32)
     ap.add_argument("--cached-refs", action="store_true",
                     help="extra measurement: reference K/V extracted once and reused (video / album use case)")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=3,
                     help="independent requests kept in flight on separate CUDA streams (each its own graph instance)")
     return ap.parse_args()
 

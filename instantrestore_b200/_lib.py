@@ -229,7 +229,7 @@ def _scratch(device, nbytes: int) -> torch.Tensor:
 def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: int, c_in: int, ksize: int = 1,
               stride: int = 1, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
               act: int = IR_ACT_NONE, out: torch.Tensor | None = None, tile_n: int = 0, split_k: int = 0,
-              a_row_stride: int | None = None, pad_hi_only: bool = False, no_persistent: bool = False) -> torch.Tensor:
+              a_row_stride: int | None = None, pad_hi_only: bool = False, no_persistent: int = 0) -> torch.Tensor:
     """a: fp16 channel-last [batch*h_in*w_in, >=c_in]; w: fp16 [c_out, ksize*ksize*c_in]."""
     _h(a, "a"); _h(w, "w"); _f(bias, "bias")
     c_out = w.shape[0]

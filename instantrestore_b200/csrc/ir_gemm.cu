@@ -655,9 +655,17 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
 
   // tile-N selection: exact divisors first, fewest wasted columns
   int bn_tile = p->tile_n;
+  bool wide_persistent = false;   // 128 x 256 tiles on the persistent kernel: 96 B/clk of operand reads instead of 128
+  if (bn_tile == 0 && !geglu && p->c_out % 256 == 0 && p->split_k <= 1 && p->no_persistent != 1 &&
+      static_cast<long>(m_tiles) * (p->c_out / 256) >= 64) {
+    bn_tile = 256;
+    wide_persistent = true;
+  }
   if (bn_tile == 0) {
     if (geglu) bn_tile = (p->c_out % 256 == 0 && static_cast<long>(m_tiles) * (p->c_out / 256) >= 296) ? 256 : 128;
     else if (p->c_out <= 64) bn_tile = 64;
+    // 160-wide tiles (115 B/clk of operand reads, fewer A re-reads) when they fill the machine without a K split
+    else if (p->c_out % 160 == 0 && (p->c_out % 128 != 0 || static_cast<long>(m_tiles) * (p->c_out / 160) >= 148)) bn_tile = 160;
     else if (p->c_out % 128 == 0) bn_tile = 128;
     else if (p->c_out % 160 == 0) bn_tile = 160;
     else if (p->c_out % 64 == 0) bn_tile = 64;
@@ -676,11 +684,11 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
     if (!can_split) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: split_k needs c_out %% 64 == 0 and no GEGLU");
     split = p->split_k;
   }
-  if (can_split && (p->split_k == 0 || p->split_k > 1) && p->tile_n == 0) {
+  if (can_split && !wide_persistent && (p->split_k == 0 || p->split_k > 1) && p->tile_n == 0) {
     // narrower N tile first when even 8-way split of 128-wide tiles leaves most SMs idle
     if (static_cast<long>(m_tiles) * ((p->c_out + bn_tile - 1) / bn_tile) * 8 < 148 && bn_tile > 64) bn_tile = 64;
   }
-  if (can_split && p->split_k == 0 && p->c_out % bn_tile == 0 && (bn_tile == 64 || bn_tile == 128)) {
+  if (can_split && !wide_persistent && p->split_k == 0 && p->c_out % bn_tile == 0 && (bn_tile == 64 || bn_tile == 128)) {
     const long tiles = static_cast<long>(m_tiles) * (p->c_out / bn_tile);
     while (split < 8 && tiles * split < 148 && tiles * split * 2 <= 296 && num_k / (split * 2) >= 4) split *= 2;
   }
@@ -704,7 +712,8 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
   // Persistent kernel when the epilogue / per-CTA set-up is a visible fraction of a tile (short K, GEGLU) and the
   // tile count quantises well over 148 SMs; long-K layers keep two one-tile CTAs per SM (measured: tools/gemm_bench.py).
   bool persistent = false;
-  if (split == 1 && !p->no_persistent) {
+  if (split == 1 && (p->no_persistent == 2 || wide_persistent)) persistent = true;
+  else if (split == 1 && !p->no_persistent) {
     const long tiles = static_cast<long>(m_tiles) * ((p->c_out + bn_tile - 1) / bn_tile);
     const long rounds = (tiles + 147) / 148;
     const double eff = tiles < 148 ? 1.0 : static_cast<double>(tiles) / (rounds * 148.0);
