@@ -79,6 +79,7 @@ typedef struct {
   int out_row_stride;
   int tile_n;  /* 0 = auto; else 64, 128, 160 or 256 */
   int split_k; /* 0 = auto; 1 = off; 2, 4, 8 = K split over a thread-block cluster of that size (DSMEM reduce) */
+  int m_sub; /* A-B measurement: 0 = auto, 1 = never stack two M tiles per CTA */
   int no_persistent; /* A-B measurement: 0 = auto, 1 = one tile per CTA, 2 = always the persistent kernel (needs split_k <= 1) */
   int pad_hi_only; /* 3x3 stride 2 only: 0 = zero padding 1 on every side; 1 = one row/column of zeros at the
                       bottom/right only (diffusers Downsample2D(padding=0) of the VAE encoder) */

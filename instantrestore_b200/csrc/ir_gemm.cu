@@ -314,6 +314,39 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
 }
 
 
+// epilogue_store<32> with the residual already in registers (prefetched before the accumulator was ready)
+__device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4 (&res)[4], bool has_res, const GemmKParams& p,
+                                                     long grow, int gcol) {
+  if (p.bias) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + q);
+      v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+    }
+  }
+  if (has_res) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&res[q]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        v[q * 8 + 2 * j] = round_h(v[q * 8 + 2 * j]) + f.x;
+        v[q * 8 + 2 * j + 1] = round_h(v[q * 8 + 2 * j + 1]) + f.y;
+      }
+    }
+  }
+  if (p.act == IR_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = silu(round_h(v[i]));
+  }
+  __half* op = p.out + grow * p.out_stride + gcol;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    reinterpret_cast<uint4*>(op)[q] = make_uint4(pack_half2(v[q * 8], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
+                                                 pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+}
+
 // ------------------------------------------------------------------------------------------------ persistent kernel
 constexpr int kPersistThreads = 320;   // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue (two warps per TMEM lane quarter)
 
@@ -343,18 +376,22 @@ __device__ __forceinline__ void geglu_store32(uint32_t taddr_v, const GemmKParam
   for (int v = 0; v < 4; ++v) dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
 }
 
-template <int BN, int STAGES>
+// MSUB = 2: a CTA tile is two stacked 128-row tiles (256 x BN) that share every weight box: the operand traffic per
+// MMA cycle drops from 128 to 96 B/clk for BN = 128, the width of the 128-channel VAE layers.
+// RESID: the launch carries a residual (and no GEGLU) — its values are prefetched into registers.
+template <int BN, int STAGES, int MSUB, bool RESID>
 __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kernel(const __grid_constant__ GemmKParams p) {
   constexpr int B_BYTES = BN * kBK * 2;
-  constexpr int STAGE_BYTES = kABytes + B_BYTES;
-  constexpr uint32_t ACC_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // columns per accumulator stage
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  constexpr int STAGE_BYTES = MSUB * kABytes + B_BYTES;
+  constexpr uint32_t ACC_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // columns per accumulator
+  constexpr uint32_t TMEM_COLS = 2 * MSUB * ACC_COLS;                    // two stages x MSUB sub-tiles
+  static_assert(TMEM_COLS <= 512, "accumulators do not fit in tensor memory");
   constexpr uint32_t IDESC = umma_idesc_f16(kBM, BN, 0, 0);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * kABytes;
+  uint8_t* sA = smem;                                   // [STAGES][MSUB] x 16 KB
+  uint8_t* sB = smem + STAGES * MSUB * kABytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;    // accumulator stage ready for the epilogue
@@ -364,7 +401,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles_n = (p.N + BN - 1) / BN;
-  const int total_tiles = p.m_tiles * n_tiles_n;
+  const int m_super = (p.m_tiles + MSUB - 1) / MSUB;
+  const int total_tiles = m_super * n_tiles_n;
   const int num_k = p.taps * p.kc_per_tap;
 
   if (warp == 0 && lane == 0) {
@@ -396,17 +434,24 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
     if (lane == 0) {
       int it = 0;   // running k-block counter across tiles (stage ring position)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / n_tiles_n, nt = tile - mt * n_tiles_n;
-        const int w0 = (mt % p.tiles_w) * p.bw;
-        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
-        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+        const int ms = tile / n_tiles_n, nt = tile - ms * n_tiles_n;
+        int w0[MSUB], h0[MSUB], n0[MSUB];
+#pragma unroll
+        for (int sub = 0; sub < MSUB; ++sub) {
+          const int mt = ms * MSUB + sub;       // may run past m_tiles: out-of-range boxes are zero fill
+          w0[sub] = (mt % p.tiles_w) * p.bw;
+          h0[sub] = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+          n0[sub] = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+        }
         int tap = 0, kc = 0;
         for (int ks = 0; ks < num_k; ++ks, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-          tma_load_4d(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], &full_bar[s], kc * kBK, w0 + p.tap_dx[tap],
-                      h0 + p.tap_dy[tap], n0);
+#pragma unroll
+          for (int sub = 0; sub < MSUB; ++sub)
+            tma_load_4d(sA + (s * MSUB + sub) * kABytes, &p.tma_a[p.tap_map[tap]], &full_bar[s], kc * kBK,
+                        w0[sub] + p.tap_dx[tap], h0[sub] + p.tap_dy[tap], n0[sub]);
           tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], ks * kBK, nt * BN);
           if (++kc == p.kc_per_tap) {
             kc = 0;
@@ -424,18 +469,21 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
         const int as = local & 1;
         mbar_wait(&tempty_bar[as], ((local >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+        const uint32_t d_tmem = tmem_base + as * MSUB * ACC_COLS;
         for (int ks = 0; ks < num_k; ++ks, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * kABytes);
           const uint32_t b_base = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t adesc = umma_smem_desc(a_base + k * 32, 16, 1024);
-            const uint64_t bdesc = umma_smem_desc(b_base + k * 32, 16, 1024);
-            umma_f16_ss(d_tmem, adesc, bdesc, IDESC, (ks | k) != 0 ? 1u : 0u);
+          for (int sub = 0; sub < MSUB; ++sub) {
+            const uint32_t a_base = smem_u32(sA + (s * MSUB + sub) * kABytes);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t adesc = umma_smem_desc(a_base + k * 32, 16, 1024);
+              const uint64_t bdesc = umma_smem_desc(b_base + k * 32, 16, 1024);
+              umma_f16_ss(d_tmem + sub * ACC_COLS, adesc, bdesc, IDESC, (ks | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[s]);
         }
@@ -451,36 +499,70 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-      const int mt = tile / n_tiles_n, nt = tile - mt * n_tiles_n;
+      const int ms = tile / n_tiles_n, nt = tile - ms * n_tiles_n;
       const int as = local & 1;
+      // prefetch this thread's residual values while the tile is still being accumulated: a short-K tile would
+      // otherwise pay one HBM round trip per 32-column chunk after the accumulator is ready
+      constexpr int kMaxChunks = (BN == 160 ? 3 : (BN / 2 + 31) / 32);
+      uint4 resid[RESID ? MSUB : 1][RESID ? kMaxChunks : 1][4];
+      if (RESID && p.N % 32 == 0) {
+        const int cb = half == 0 ? 0 : (BN == 160 ? 96 : BN / 2);
+        const int ce = half == 0 ? (BN == 160 ? 96 : BN / 2) : BN;
+#pragma unroll
+        for (int sub = 0; sub < MSUB; ++sub) {
+          const long gr = (static_cast<long>(ms) * MSUB + sub) * kBM + row;
+#pragma unroll
+          for (int ci = 0; ci < kMaxChunks; ++ci) {
+            const int gcol = nt * BN + cb + ci * 32;
+            if (gr < p.M && cb + ci * 32 < ce && gcol < p.N) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + gr * p.res_stride + gcol);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) resid[sub][ci][q] = __ldg(rp + q);
+            }
+          }
+        }
+      }
       mbar_wait(&tfull_bar[as], (local >> 1) & 1);
       tc_fence_after();
-      const long grow = static_cast<long>(mt) * kBM + row;
-      const bool row_ok = grow < p.M;
-      const uint32_t taddr = tmem_base + as * ACC_COLS + lane_addr;
       if (p.act == IR_ACT_GEGLU) {
         if constexpr (BN % 128 == 0) {
 #pragma unroll 1
-          for (int blk = 0; blk < BN / 128; ++blk) {
-            const int wcol = nt * BN + blk * 128 + half * 32;            // weight-row index of the value columns
-            const int ocol = (nt * BN + blk * 128) / 2 + half * 32;      // output column
-            geglu_store32(taddr + blk * 128 + half * 32, p, grow, wcol, ocol, row_ok);
+          for (int sub = 0; sub < MSUB; ++sub) {
+            const long grow = (static_cast<long>(ms) * MSUB + sub) * kBM + row;
+            const uint32_t taddr = tmem_base + (as * MSUB + sub) * ACC_COLS + lane_addr;
+#pragma unroll 1
+            for (int blk = 0; blk < BN / 128; ++blk) {
+              const int wcol = nt * BN + blk * 128 + half * 32;            // weight-row index of the value columns
+              const int ocol = (nt * BN + blk * 128) / 2 + half * 32;      // output column
+              geglu_store32(taddr + blk * 128 + half * 32, p, grow, wcol, ocol, grow < p.M);
+            }
           }
         }
       } else {
         // BN = 160 splits 96 | 64 so both halves work in 32-column chunks
         const int c_begin = half == 0 ? 0 : (BN == 160 ? 96 : BN / 2);
         const int c_end = half == 0 ? (BN == 160 ? 96 : BN / 2) : BN;
-#pragma unroll 1
-        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
-          tmem_ld_wait();
-          if (row_ok) {
-            float v[32];
+        const bool fast = p.N % 32 == 0 && (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            epilogue_store<32>(v, p, grow, nt * BN + c0);
+        for (int sub = 0; sub < MSUB; ++sub) {
+          const long grow = (static_cast<long>(ms) * MSUB + sub) * kBM + row;
+          const bool row_ok = grow < p.M;
+          const uint32_t taddr = tmem_base + (as * MSUB + sub) * ACC_COLS + lane_addr;
+#pragma unroll
+          for (int ci = 0; ci < kMaxChunks; ++ci) {      // fully unrolled: the prefetched residual stays in registers
+            const int c0 = c_begin + ci * 32;
+            if (c0 < c_end) {
+              uint32_t r[32];
+              tmem_ld32(taddr + c0, r);
+              tmem_ld_wait();
+              if (row_ok) {
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                if (fast && nt * BN + c0 < p.N) epilogue_store32_pre(v, resid[RESID ? sub : 0][RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
+                else epilogue_store<32>(v, p, grow, nt * BN + c0);
+              }
+            }
           }
         }
       }
@@ -494,20 +576,27 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES>
-static int launch_persistent(const GemmKParams& kp, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 1024 + 256;
+template <int BN, int STAGES, int MSUB, bool RESID>
+static int launch_persistent_r(const GemmKParams& kp, cudaStream_t stream) {
+  constexpr int smem = STAGES * (MSUB * kABytes + BN * kBK * 2) + 1024 + 256;
   static bool attr_done = false;  // benign race: idempotent
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm_persistent<%d>): %s", BN, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, STAGES, MSUB, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm_persistent<%d,%d>): %s", BN, MSUB, cudaGetErrorString(e));
     attr_done = true;
   }
-  const long tiles = static_cast<long>(kp.m_tiles) * ((kp.N + BN - 1) / BN);
+  const long tiles = static_cast<long>((kp.m_tiles + MSUB - 1) / MSUB) * ((kp.N + BN - 1) / BN);
   const int grid = static_cast<int>(tiles < 148 ? tiles : 148);
-  conv_gemm_persistent_kernel<BN, STAGES><<<grid, kPersistThreads, smem, stream>>>(kp);
+  conv_gemm_persistent_kernel<BN, STAGES, MSUB, RESID><<<grid, kPersistThreads, smem, stream>>>(kp);
   IR_CUDA_LAUNCH_CHECK("conv_gemm_persistent launch");
   return 0;
+}
+
+template <int BN, int STAGES, int MSUB>
+static int launch_persistent(const GemmKParams& kp, cudaStream_t stream) {
+  const bool resid = kp.residual != nullptr && kp.act != IR_ACT_GEGLU && kp.N % 32 == 0 &&
+                     (kp.bias == nullptr || (reinterpret_cast<uintptr_t>(kp.bias) & 15) == 0);
+  return resid ? launch_persistent_r<BN, STAGES, MSUB, true>(kp, stream) : launch_persistent_r<BN, STAGES, MSUB, false>(kp, stream);
 }
 
 template <int BN, int STAGES>
@@ -720,11 +809,13 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
     persistent = geglu || (num_k <= 40 && (tiles >= 592 || eff >= 0.85));
   }
   if (persistent) {
+    // 256 x 128 CTA tiles (two stacked M tiles sharing the weight boxes) when there are plenty of M tiles
+    const bool tall = bn_tile == 128 && !geglu && m_tiles >= 2 * 148 && num_k >= 16 && p->m_sub != 1;
     switch (bn_tile) {
-      case 64: return launch_persistent<64, 8>(kp, stream);
-      case 128: return launch_persistent<128, 6>(kp, stream);
-      case 160: return launch_persistent<160, 5>(kp, stream);
-      case 256: return launch_persistent<256, 4>(kp, stream);
+      case 64: return launch_persistent<64, 8, 1>(kp, stream);
+      case 128: return tall ? launch_persistent<128, 4, 2>(kp, stream) : launch_persistent<128, 6, 1>(kp, stream);
+      case 160: return launch_persistent<160, 5, 1>(kp, stream);
+      case 256: return launch_persistent<256, 4, 1>(kp, stream);
       default: return set_error(IR_ERR_SHAPE, "ir_conv_gemm: tile_n=%d unsupported", bn_tile);
     }
   }

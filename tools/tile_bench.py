@@ -6,7 +6,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from instantrestore_b200 import _lib as L
 from tools.gemm_bench import timeit
 
-SHAPES = [(8, 16, 1280, 1280), (8, 16, 2560, 1280), (8, 32, 1280, 1280), (8, 8, 1280, 1280), (4, 16, 1280, 1280), (8, 32, 640, 640), (8, 32, 1280, 640), (8, 32, 1920, 640), (8, 64, 640, 320), (8, 64, 960, 320), (1, 32, 640, 640), (4, 32, 640, 640)]
+SHAPES = [(8, 512, 128, 128), (1, 512, 128, 128), (4, 512, 128, 128), (8, 256, 128, 128), (1, 256, 128, 128), (8, 512, 64, 128)]
+_OLD2 = [(8, 16, 1280, 1280), (8, 16, 2560, 1280), (8, 32, 1280, 1280), (8, 8, 1280, 1280), (4, 16, 1280, 1280), (8, 32, 640, 640), (8, 32, 1280, 640), (8, 32, 1920, 640), (8, 64, 640, 320), (8, 64, 960, 320), (1, 32, 640, 640), (4, 32, 640, 640)]
 _OLD = [(8, 128, 512, 512), (1, 128, 512, 512), (8, 256, 256, 256), (1, 256, 256, 256), (8, 32, 640, 640), (8, 16, 1280, 1280),
           (8, 64, 320, 320), (8, 32, 1280, 640), (4, 64, 512, 512), (1, 64, 512, 512), (8, 64, 512, 512), (8, 16, 2560, 1280), (8, 32, 1920, 640),
           (8, 256, 128, 256), (8, 128, 256, 512), (8, 512, 128, 128)]
@@ -18,7 +19,10 @@ for B, H, Ci, Co in SHAPES:
     out = torch.empty(B * H * H, Co, device="cuda", dtype=torch.float16)
     flops = 2.0 * B * H * H * 9 * Ci * Co
     res = []
-    for tn in (0, 128, 160, 256):
+    for msub in (1, 0):
+        t = timeit(lambda: L.conv_gemm(a, w, batch=B, h_in=H, w_in=H, c_in=Ci, ksize=3, bias=bias, out=out, m_sub=msub))
+        res.append(f"auto m_sub={msub} {flops / t / 1e6:6.0f}")
+    for tn in ():
         for npers in (1, 2):
             if (tn == 256 and Co % 256) or (tn == 160 and Co % 160):
                 continue
