@@ -83,6 +83,8 @@ typedef struct {
   int no_persistent; /* A-B measurement: 0 = auto, 1 = one tile per CTA, 2 = always the persistent kernel (needs split_k <= 1) */
   int pad_hi_only; /* 3x3 stride 2 only: 0 = zero padding 1 on every side; 1 = one row/column of zeros at the
                       bottom/right only (diffusers Downsample2D(padding=0) of the VAE encoder) */
+  int cta_pair; /* A-B measurement: 0 = auto, 1 = never, 2 = always the CTA-pair (tcgen05 cta_group::2, 256 x 256
+                   tiles over two SMs) kernel; needs c_out % 256 == 0, no K split, >= 2 M tiles */
 } ir_conv_gemm_params;
 int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
 

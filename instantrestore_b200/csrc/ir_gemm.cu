@@ -576,6 +576,203 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair kernel
+// Persistent kernel on tcgen05.mma.cta_group::2: a cluster of two CTAs (one TPC) computes 256 x 256 output tiles as ONE
+// M = 256, N = 256 MMA. CTA r stages its own 128 rows of A and rows [r*128, r*128+128) of the weight tile (32 KB per
+// stage instead of 48 KB), so each SM reads 64 B/clk of operands from shared memory instead of 96 and every weight
+// box is fetched from L2 once per 256 output rows. Accumulator: 128 lanes x 256 fp32 columns in EACH CTA's tensor
+// memory (rows r*128.. of the pair tile), double-buffered (512 columns). Roles per CTA as in the persistent kernel;
+// only the leader's (cluster rank 0) warp 1 issues MMAs; its commits are multicast to both CTAs' barriers. Both
+// CTAs' TMA loads signal the leader's full barrier (expect_tx covers both halves).
+template <int BN, int STAGES, bool RESID>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) conv_gemm_pair_kernel(const __grid_constant__ GemmKParams p) {
+  static_assert(BN == 128 || BN == 256, "pair tile N");
+  constexpr int B_BYTES = (BN / 2) * kBK * 2;   // this CTA's half of the weight box
+  constexpr int STAGE_BYTES = kABytes + B_BYTES;
+  constexpr uint32_t ACC_COLS = BN;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr uint32_t IDESC = umma_idesc_f16(256, BN, 0, 0);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // used in the leader only
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;                                            // used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_tiles_n = p.N / BN;
+  const int m_pairs = (p.m_tiles + 1) / 2;
+  const int total_tiles = m_pairs * n_tiles_n;
+  const int num_k = p.taps * p.kc_per_tap;
+  const int tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a[0]);
+    tma_prefetch_desc(&p.tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 512);           // 256 epilogue threads of each CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();                           // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int mp = tile / n_tiles_n, nt = tile - mp * n_tiles_n;
+        const int mt = mp * 2 + static_cast<int>(rank);      // may run past m_tiles: out-of-range boxes are zero fill
+        const int w0 = (mt % p.tiles_w) * p.bw;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+        const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+        int tap = 0, kc = 0;
+        for (int ks = 0; ks < num_k; ++ks, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          const uint32_t leader_full = dsmem_addr(smem_u32(&full_bar[s]), 0);
+          tma_load_4d_pair(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], leader_full, kc * kBK, w0 + p.tap_dx[tap],
+                           h0 + p.tap_dy[tap], n0);
+          tma_load_2d_pair(sB + s * B_BYTES, &p.tma_b, leader_full, ks * kBK, nt * BN + static_cast<int>(rank) * (BN / 2));
+          if (++kc == p.kc_per_tap) {
+            kc = 0;
+            ++tap;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      int it = 0, local = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++local) {
+        const int as = local & 1;
+        mbar_wait(&tempty_bar[as], ((local >> 1) & 1) ^ 1);       // both CTAs' epilogues have drained this stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+        for (int ks = 0; ks < num_k; ++ks, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * kABytes);
+          const uint32_t b_base = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adesc = umma_smem_desc(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(b_base + k * 32, 16, 1024);
+            umma_f16_ss_pair(d_tmem, adesc, bdesc, IDESC, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[s], 3);
+        }
+        umma_commit_pair(&tfull_bar[as], 3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (thread == row, half the columns)
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const int c_begin = half * (BN / 2);
+    constexpr int kChunks = BN / 2 / 32;          // 4
+    const bool fast = p.N % 32 == 0 && (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    int local = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++local) {
+      const int mp = tile / n_tiles_n, nt = tile - mp * n_tiles_n;
+      const int as = local & 1;
+      const long grow = (static_cast<long>(mp) * 2 + rank) * kBM + row;
+      const bool row_ok = grow < p.M;
+      uint4 resid[RESID ? kChunks : 1][4];
+      if (RESID && row_ok) {
+#pragma unroll
+        for (int ci = 0; ci < kChunks; ++ci) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + nt * BN + c_begin + ci * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) resid[ci][q] = __ldg(rp + q);
+        }
+      }
+      mbar_wait(&tfull_bar[as], (local >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * ACC_COLS + lane_addr;
+      if (p.act == IR_ACT_GEGLU) {
+#pragma unroll 1
+        for (int blk = 0; blk < BN / 128; ++blk) {
+          const int wcol = nt * BN + blk * 128 + half * 32;
+          const int ocol = (nt * BN + blk * 128) / 2 + half * 32;
+          geglu_store32(taddr + blk * 128 + half * 32, p, grow, wcol, ocol, row_ok);
+        }
+      } else {
+#pragma unroll
+        for (int ci = 0; ci < kChunks; ++ci) {
+          const int c0 = c_begin + ci * 32;
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (fast) epilogue_store32_pre(v, resid[RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
+            else epilogue_store<32>(v, p, grow, nt * BN + c0);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(dsmem_addr(smem_u32(&tempty_bar[as]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();     // the leader's MMAs read the peer's shared memory and write its tensor memory until here
+  if (warp == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES, bool RESID>
+static int launch_pair_r(const GemmKParams& kp, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + (BN / 2) * kBK * 2) + 1024 + 256;
+  static bool attr_done = false;  // benign race: idempotent
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<BN, STAGES, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm_pair): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const long tiles = static_cast<long>((kp.m_tiles + 1) / 2) * (kp.N / BN);
+  const int grid = 2 * static_cast<int>(tiles < 74 ? tiles : 74);
+  conv_gemm_pair_kernel<BN, STAGES, RESID><<<grid, kPersistThreads, smem, stream>>>(kp);
+  IR_CUDA_LAUNCH_CHECK("conv_gemm_pair launch");
+  return 0;
+}
+
+static int launch_pair(const GemmKParams& kp, int bn_pair, cudaStream_t stream) {
+  const bool resid = kp.residual != nullptr && kp.act != IR_ACT_GEGLU && kp.N % 32 == 0 &&
+                     (kp.bias == nullptr || (reinterpret_cast<uintptr_t>(kp.bias) & 15) == 0);
+  if (bn_pair == 128) return resid ? launch_pair_r<128, 8, true>(kp, stream) : launch_pair_r<128, 8, false>(kp, stream);
+  return resid ? launch_pair_r<256, 6, true>(kp, stream) : launch_pair_r<256, 6, false>(kp, stream);
+}
+
 template <int BN, int STAGES, int MSUB, bool RESID>
 static int launch_persistent_r(const GemmKParams& kp, cudaStream_t stream) {
   constexpr int smem = STAGES * (MSUB * kABytes + BN * kBK * 2) + 1024 + 256;
@@ -790,14 +987,36 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
     kp.kb_per_split = num_k;
   }
 
+  // CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 or 256 x 128 tiles over the two SMs of a TPC). Measured
+  // (tools/pair_bench.py): ahead of the single-CTA kernels once there are >= 4 tiles per cluster and K >= 1024; behind
+  // them on short-K / GEGLU launches (the accumulator hand-over couples the two epilogues), on few-tile launches and
+  // for 128-wide outputs (256 x 128 pair tiles: 798 vs 905 TFLOP/s of the stacked-M single-CTA kernel) — auto mode
+  // pairs only the 256-wide tiles.
+  int bn_pair = 0;
+  if (p->cta_pair < 0 || p->cta_pair > 2) return set_error(IR_ERR_ARG, "ir_conv_gemm: cta_pair=%d (0 = auto, 1 = off, 2 = force)", p->cta_pair);
+  if (p->cta_pair != 1 && split == 1 && m_tiles >= 2) {
+    int cand = 0;
+    if (p->c_out % 256 == 0 && (p->tile_n == 0 || p->tile_n == 256)) cand = 256;
+    else if (p->c_out % 128 == 0 && (p->tile_n == 0 || p->tile_n == 128)) cand = 128;
+    if (cand) {
+      const long ptiles = static_cast<long>((m_tiles + 1) / 2) * (p->c_out / cand);
+      if (p->cta_pair == 2) bn_pair = cand;
+      else if (!geglu && p->no_persistent != 1 && cand == 256 && bn_tile == 256 && ptiles >= 296 && num_k >= 16) bn_pair = cand;
+    }
+  }
+  if (p->cta_pair == 2 && !bn_pair)
+    return set_error(IR_ERR_SHAPE, "ir_conv_gemm: cta_pair needs c_out %% 128 == 0, no K split, >= 2 M tiles (c_out=%d split=%d m_tiles=%d)", p->c_out, split, m_tiles);
+  const bool use_pair = bn_pair != 0;
+
   {
     uint64_t dims[2] = {static_cast<uint64_t>(taps) * p->c_in, static_cast<uint64_t>(p->c_out)};
     uint64_t str[1] = {static_cast<uint64_t>(taps) * p->c_in * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(bn_tile)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(use_pair ? bn_pair / 2 : bn_tile)};
     if (int rc = make_tmap_f16(&kp.tma_b, p->w, 2, dims, str, box)) return rc;
   }
 
   kp.m_tiles = m_tiles;
+  if (use_pair) return launch_pair(kp, bn_pair, stream);
   // Persistent kernel when the epilogue / per-CTA set-up is a visible fraction of a tile (short K, GEGLU) and the
   // tile count quantises well over 148 SMs; long-K layers keep two one-tile CTAs per SM (measured: tools/gemm_bench.py).
   bool persistent = false;

@@ -117,6 +117,54 @@ def test_conv3x3_split_k_cluster(L, B, H, Ci, Co, stride, split):
     assert rel_l2(out, ref) <= TOL
 
 
+@pytest.mark.parametrize("M,K,N,use_res,geglu", [
+    (4096, 512, 512, True, False), (640, 320, 256, True, False), (1000, 1280, 1280, False, False), (257, 64, 256, True, False),
+    (20000, 640, 1024, True, False), (4096, 320, 2560, False, True), (777, 128, 512, False, True),
+    (5000, 1152, 128, True, False), (900, 64, 640, False, False),
+])
+def test_linear_cta_pair(L, M, K, N, use_res, geglu):
+    """tcgen05 cta_group::2 kernel (256 x 256 tiles over two SMs): odd tile counts, ragged M, residual, GEGLU; must agree
+    with fp32 math and, bit for bit, with the single-CTA kernel (same K order)."""
+    from instantrestore_b200.weights import geglu_interleave_index
+    g = _gen(31)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, N, device="cuda", generator=g).half() if use_res else None
+    h = a.float() @ w.float().T + bias
+    if geglu:
+        idx = geglu_interleave_index(N).cuda()
+        kw = dict(batch=1, h_in=1, w_in=M, c_in=K, bias=bias[idx].contiguous(), act=L.IR_ACT_GEGLU)
+        out = L.conv_gemm(a, w[idx].contiguous(), cta_pair=2, **kw)
+        single = L.conv_gemm(a, w[idx].contiguous(), cta_pair=1, **kw)
+        ref, tol = h[:, : N // 2] * F.gelu(h[:, N // 2:]), 2 * TOL
+    else:
+        kw = dict(batch=1, h_in=1, w_in=M, c_in=K, bias=bias, residual=r, split_k=1)
+        out = L.conv_gemm(a, w, cta_pair=2, **kw)
+        single = L.conv_gemm(a, w, cta_pair=1, **kw)
+        ref, tol = (h.half().float() + r.float() if use_res else h), TOL
+    assert rel_l2(out, ref) <= tol
+    assert rel_l2(out, single) <= 2e-4
+
+
+@pytest.mark.parametrize("B,H,Ci,Co,stride", [
+    (1, 64, 512, 512, 1), (2, 32, 256, 256, 1), (3, 16, 1280, 1280, 1), (5, 8, 128, 256, 1), (1, 64, 128, 256, 2),
+    (2, 128, 64, 256, 1), (2, 128, 64, 128, 1), (3, 32, 128, 128, 2),
+])
+def test_conv3x3_cta_pair(L, B, H, Ci, Co, stride):
+    g = _gen(32)
+    x = torch.randn(B, Ci, H, H, device="cuda", generator=g).half()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Ci)).half()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    ref = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
+    a = x.permute(0, 2, 3, 1).contiguous().reshape(-1, Ci)
+    wk = w.permute(0, 2, 3, 1).contiguous().reshape(Co, 9 * Ci)
+    out = L.conv_gemm(a, wk, batch=B, h_in=H, w_in=H, c_in=Ci, ksize=3, stride=stride, bias=bias, cta_pair=2, split_k=1)
+    assert rel_l2(out, ref) <= TOL
+    again = L.conv_gemm(a, wk, batch=B, h_in=H, w_in=H, c_in=Ci, ksize=3, stride=stride, bias=bias, cta_pair=2, split_k=1)
+    assert torch.equal(out, again)
+
+
 def test_conv_rejects_bad_shapes(L):
     a = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
     w = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
