@@ -85,6 +85,9 @@ typedef struct {
                       bottom/right only (diffusers Downsample2D(padding=0) of the VAE encoder) */
   int cta_pair; /* A-B measurement: 0 = auto, 1 = never, 2 = always the CTA-pair (tcgen05 cta_group::2, 256 x 256
                    tiles over two SMs) kernel; needs c_out % 256 == 0, no K split, >= 2 M tiles */
+  int halo; /* A-B measurement: 0 = auto, 1 = never, 2 = always the halo kernel (3x3 stride 1, w_in % 128 == 0, even
+               h_in, c_out % 128 == 0): each 64-channel input slice is staged once per tile as a (rows+2) x 130 pixel box
+               and the nine taps read shifted views of it */
 } ir_conv_gemm_params;
 int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
 

@@ -31,7 +31,7 @@ class ConvGemmParams(C.Structure):
         ("w", C.c_void_p), ("c_out", C.c_int), ("bias", C.c_void_p), ("residual", C.c_void_p),
         ("res_row_stride", C.c_int), ("act", C.c_int), ("out", C.c_void_p), ("out_row_stride", C.c_int),
         ("tile_n", C.c_int), ("split_k", C.c_int), ("m_sub", C.c_int), ("no_persistent", C.c_int), ("pad_hi_only", C.c_int),
-        ("cta_pair", C.c_int),
+        ("cta_pair", C.c_int), ("halo", C.c_int),
     ]
 
 
@@ -230,7 +230,7 @@ def _scratch(device, nbytes: int) -> torch.Tensor:
 def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: int, c_in: int, ksize: int = 1,
               stride: int = 1, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
               act: int = IR_ACT_NONE, out: torch.Tensor | None = None, tile_n: int = 0, split_k: int = 0,
-              a_row_stride: int | None = None, pad_hi_only: bool = False, no_persistent: int = 0, m_sub: int = 0, cta_pair: int = 0) -> torch.Tensor:
+              a_row_stride: int | None = None, pad_hi_only: bool = False, no_persistent: int = 0, m_sub: int = 0, cta_pair: int = 0, halo: int = 0) -> torch.Tensor:
     """a: fp16 channel-last [batch*h_in*w_in, >=c_in]; w: fp16 [c_out, ksize*ksize*c_in]."""
     _h(a, "a"); _h(w, "w"); _f(bias, "bias")
     c_out = w.shape[0]
@@ -245,7 +245,7 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
         ksize=ksize, stride=stride, w=ptr(w), c_out=c_out, bias=ptr(bias),
         residual=ptr(residual), res_row_stride=residual.stride(-2) if residual is not None else 0,
         act=act, out=ptr(out), out_row_stride=out.stride(-2), tile_n=tile_n, split_k=split_k,
-        pad_hi_only=int(pad_hi_only), no_persistent=int(no_persistent), m_sub=m_sub, cta_pair=cta_pair)
+        pad_hi_only=int(pad_hi_only), no_persistent=int(no_persistent), m_sub=m_sub, cta_pair=cta_pair, halo=halo)
     k_tot = ksize * ksize * c_in
     _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks{ksize}s{stride}", 2.0 * m * k_tot * c_out,
          2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
 
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not lane == 0: TMA / MMA operands then stay in uniform registers (no R2UR loops)
       mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
       tma_load_3d(sQ, &p.tma_q, q_full, p.q_col_off + head * kD, (2 * pair) * kQT, b);
       tma_load_3d(sQ + kTileBytes, &p.tma_q, q_full, p.q_col_off + head * kD, (2 * pair + 1) * kQT, b);
@@ -268,18 +268,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     __syncwarp();
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t IDESC_QK = umma_idesc_f16(128, kKT, 0, 0);   // A = Q (K-major), B = K (K-major)
       constexpr uint32_t IDESC_PV = umma_idesc_f16(128, kD, 0, 1);    // A = P (TMEM), B = V (MN-major)
+      // descriptors are (constant high word, low word = address >> 4 | LBO): stepping K or the stage is an integer add;
+      // the issue loop has to stay far below the 512 clk of tensor work per (KV tile, query tile)
+      const uint32_t q_lo0 = umma_desc_lo(smem_u32(sQ)), k_lo0 = umma_desc_lo(smem_u32(sK)), v_lo0 = umma_desc_lo_mn(smem_u32(sV));
       auto issue_qk = [&](int jj, int i) {
-        const uint32_t k_base = smem_u32(sK + (jj % kKVStages) * kTileBytes);
-        const uint32_t q_base = smem_u32(sQ + i * kTileBytes);
+        const uint32_t k_lo = k_lo0 + (jj % kKVStages) * (kTileBytes >> 4);
+        const uint32_t q_lo = q_lo0 + i * (kTileBytes >> 4);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) {
-          const uint64_t adesc = umma_smem_desc(q_base + k * 32, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc(k_base + k * 32, 16, 1024);
-          umma_f16_ss(tmem_base + kTmemS + i * kKT, adesc, bdesc, IDESC_QK, k != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < kD / 16; ++k)
+          umma_f16_ss_lo(tmem_base + kTmemS + i * kKT, q_lo + 2 * k, k_lo + 2 * k, IDESC_QK, k != 0 ? 1u : 0u);
         umma_commit(&s_full[i]);
       };
       mbar_wait(q_full, 0);
@@ -293,18 +293,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
         const int g = g_begin + jj, s = jj % kKVStages;
         // a segment (AdaIN: one chunk; otherwise the whole range) starts with a fresh accumulator
         const bool fresh = (jj == 0) || (ADAIN && locate_tile(p, g).chunk != locate_tile(p, g - 1).chunk);
-        const uint32_t v_base = smem_u32(sV + s * kTileBytes);
+        const uint32_t v_lo = v_lo0 + s * (kTileBytes >> 4);
         if (jj + 1 < n_tiles) mbar_wait(&kv_full[(jj + 1) % kKVStages], ((jj + 1) / kKVStages) & 1);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           mbar_wait(&p_full[i], jj & 1);
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < kKT / 16; ++kk) {
-            const uint64_t bdesc = umma_smem_desc(v_base + kk * 2048, 1024, 1024);
-            umma_f16_ts(tmem_base + kTmemO + i * kD, tmem_base + kTmemS + i * kKT + kk * 8, bdesc, IDESC_PV,
-                        (kk != 0 || !fresh) ? 1u : 0u);
-          }
+          for (int kk = 0; kk < kKT / 16; ++kk)
+            umma_f16_ts_lo(tmem_base + kTmemO + i * kD, tmem_base + kTmemS + i * kKT + kk * 8, v_lo + kk * (2048 >> 4), IDESC_PV,
+                           (kk != 0 || !fresh) ? 1u : 0u);
           umma_commit(&o_done[i]);
           // tcgen05.mma executes in issue order: the next QK^T refills S_i only after this PV has read P_i out of it
           if (jj + 1 < n_tiles) issue_qk(jj + 1, i);

@@ -46,6 +46,7 @@ struct GemmKParams {
   int8_t tap_map[9], tap_dx[9], tap_dy[9];
   int split, kb_per_split;
   int m_tiles;
+  int img_h, img_w;     // halo kernel: output (= input) image size
   const float* bias;
   const __half* residual;
   int res_stride;
@@ -168,15 +169,15 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
   const int num_k = k_end - k_begin;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync (not lane == 0): the compiler then keeps TMA / MMA operands in uniform registers
       const int w0 = (mt % p.tiles_w) * p.bw;
       const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
       const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
       int tap = k_begin / p.kc_per_tap, kc = k_begin % p.kc_per_tap;
+      int s = 0;
+      uint32_t ph = 1;
       for (int ks = 0; ks < num_k; ++ks) {
-        const int s = ks % STAGES;
-        const uint32_t ph = (ks / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait(&empty_bar[s], ph);
         mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
         tma_load_4d(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], &full_bar[s], kc * kBK, w0 + p.tap_dx[tap],
                     h0 + p.tap_dy[tap], n0);
@@ -185,25 +186,23 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
           kc = 0;
           ++tap;
         }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA)), b_lo0 = umma_desc_lo(smem_u32(sB));
       for (int ks = 0; ks < num_k; ++ks) {
-        const int s = ks % STAGES;
-        const uint32_t ph = (ks / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + s * kABytes);
-        const uint32_t b_base = smem_u32(sB + s * B_BYTES);
+        const uint32_t a_lo = a_lo0 + s * (kABytes >> 4), b_lo = b_lo0 + s * (B_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t adesc = umma_smem_desc(a_base + k * 32, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc(b_base + k * 32, 16, 1024);
-          umma_f16_ss(tmem_base, adesc, bdesc, IDESC, (ks | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < kBK / 16; ++k) umma_f16_ss_lo(tmem_base, a_lo + 2 * k, b_lo + 2 * k, IDESC, (ks | k) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       umma_commit(accum_bar);
     }
@@ -431,8 +430,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int it = 0;   // running k-block counter across tiles (stage ring position)
+    if (elect_one()) {
+      int s = 0;          // stage ring position and phase, carried across tiles
+      uint32_t ph = 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int ms = tile / n_tiles_n, nt = tile - ms * n_tiles_n;
         int w0[MSUB], h0[MSUB], n0[MSUB];
@@ -444,9 +444,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
           n0[sub] = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
         }
         int tap = 0, kc = 0;
-        for (int ks = 0; ks < num_k; ++ks, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        for (int ks = 0; ks < num_k; ++ks) {
+          mbar_wait(&empty_bar[s], ph);
           mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
 #pragma unroll
           for (int sub = 0; sub < MSUB; ++sub)
@@ -457,35 +456,35 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
             kc = 0;
             ++tap;
           }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int it = 0, local = 0;
+    if (elect_one()) {
+      int s = 0, local = 0;
+      uint32_t ph = 0;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA)), b_lo0 = umma_desc_lo(smem_u32(sB));
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         const int as = local & 1;
         mbar_wait(&tempty_bar[as], ((local >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * MSUB * ACC_COLS;
-        for (int ks = 0; ks < num_k; ++ks, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        for (int ks = 0; ks < num_k; ++ks) {
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t b_base = smem_u32(sB + s * B_BYTES);
+          const uint32_t b_lo = b_lo0 + s * (B_BYTES >> 4);
 #pragma unroll
           for (int sub = 0; sub < MSUB; ++sub) {
-            const uint32_t a_base = smem_u32(sA + (s * MSUB + sub) * kABytes);
+            const uint32_t a_lo = a_lo0 + (s * MSUB + sub) * (kABytes >> 4);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t adesc = umma_smem_desc(a_base + k * 32, 16, 1024);
-              const uint64_t bdesc = umma_smem_desc(b_base + k * 32, 16, 1024);
-              umma_f16_ss(d_tmem + sub * ACC_COLS, adesc, bdesc, IDESC, (ks | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_f16_ss_lo(d_tmem + sub * ACC_COLS, a_lo + 2 * k, b_lo + 2 * k, IDESC, (ks | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[as]);
       }
@@ -638,8 +637,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int it = 0;
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 1;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int mp = tile / n_tiles_n, nt = tile - mp * n_tiles_n;
         const int mt = mp * 2 + static_cast<int>(rank);      // may run past m_tiles: out-of-range boxes are zero fill
@@ -647,9 +647,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
         const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
         int tap = 0, kc = 0;
-        for (int ks = 0; ks < num_k; ++ks, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        for (int ks = 0; ks < num_k; ++ks) {
+          mbar_wait(&empty_bar[s], ph);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
           const uint32_t leader_full = dsmem_addr(smem_u32(&full_bar[s]), 0);
           tma_load_4d_pair(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], leader_full, kc * kBK, w0 + p.tap_dx[tap],
@@ -659,32 +658,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
             kc = 0;
             ++tap;
           }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
-      int it = 0, local = 0;
+    if (rank == 0 && elect_one()) {
+      // one elected thread; ring position and phase are carried (no div/mod), descriptors advance by adding to the
+      // low word: the issue loop must stay well under the 512 clk of tensor work per K block
+      int s = 0, local = 0;
+      uint32_t ph = 0;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA)), b_lo0 = umma_desc_lo(smem_u32(sB));
       for (int tile = tile0; tile < total_tiles; tile += tile_step, ++local) {
         const int as = local & 1;
         mbar_wait(&tempty_bar[as], ((local >> 1) & 1) ^ 1);       // both CTAs' epilogues have drained this stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_COLS;
-        for (int ks = 0; ks < num_k; ++ks, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        for (int ks = 0; ks < num_k; ++ks) {
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * kABytes);
-          const uint32_t b_base = smem_u32(sB + s * B_BYTES);
+          const uint32_t a_lo = a_lo0 + s * (kABytes >> 4), b_lo = b_lo0 + s * (B_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t adesc = umma_smem_desc(a_base + k * 32, 16, 1024);
-            const uint64_t bdesc = umma_smem_desc(b_base + k * 32, 16, 1024);
-            umma_f16_ss_pair(d_tmem, adesc, bdesc, IDESC, (ks | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_f16_ss_pair_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, IDESC, (ks | k) != 0 ? 1u : 0u);
           umma_commit_pair(&empty_bar[s], 3);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit_pair(&tfull_bar[as], 3);
       }
@@ -771,6 +771,265 @@ static int launch_pair(const GemmKParams& kp, int bn_pair, cudaStream_t stream) 
                      (kp.bias == nullptr || (reinterpret_cast<uintptr_t>(kp.bias) & 15) == 0);
   if (bn_pair == 128) return resid ? launch_pair_r<128, 8, true>(kp, stream) : launch_pair_r<128, 8, false>(kp, stream);
   return resid ? launch_pair_r<256, 6, true>(kp, stream) : launch_pair_r<256, 6, false>(kp, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ halo kernel
+// 3x3 stride-1 convolutions on images >= 128 pixels wide. ncu on the kernels above shows the big VAE convolutions pinned
+// at ~50 B/clk of L2->SM traffic per SM (l1tex__m_xbar2l1tex_read_bytes ~ 11.4 TB/s over the chip) with the tensor pipe
+// 46 % (128-wide outputs) to 77 % (CTA pair) busy: an im2col-free conv still re-fetches every input pixel nine times,
+// once per tap. Here the 64-channel slice of the input a tile needs is fetched ONCE as a (rows + 2) x 130-pixel halo
+// box (TMA zero fill = padding) and the nine taps are nine shifted views of it: the A descriptor of tap (ky, kx) starts
+// (ky * 130 + kx) * 128 bytes into the box — 128-byte swizzling is a function of the shared-memory address bits, so a
+// view that starts on any 128-byte row reads back exactly what TMA wrote. Weights stream through their own ring
+// (one 128 x 64 box per tap). Bytes into the SM per 64-channel slice and 256 output pixels: 66 KB + 144 KB instead of
+// 288 KB + 144 KB (single CTA, 128-wide outputs, two image rows stacked per CTA), 2 x (50 KB + 144 KB) instead of
+// 2 x (144 KB + 144 KB) for the CTA pair (256-wide N tiles, one image row per CTA).
+// K order: channel slice, then tap (the kernels above run tap, then slice): same products, different fp32 summation
+// order.
+constexpr int kHaloW = 130;
+
+template <int BN, bool PAIR, bool RESID>
+__global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __grid_constant__ GemmKParams p) {
+  static_assert((BN == 128 && !PAIR) || (BN == 256 && PAIR), "halo kernel: 128-wide single CTA or 256-wide CTA pair");
+  constexpr int MSUB = PAIR ? 1 : 2;                       // output image rows per CTA
+  constexpr int HROWS = MSUB + 2;
+  constexpr uint32_t HALO_BYTES = HROWS * kHaloW * 128;    // one 64-channel halo box
+  constexpr int HALO_SLOT = (HALO_BYTES + 1023) / 1024 * 1024;
+  constexpr int NA = 2;
+  constexpr int NB = PAIR ? 7 : 5;
+  constexpr int B_BYTES = 128 * kBK * 2;                   // 128 weight rows of one tap (pair: this CTA's half)
+  constexpr uint32_t STAGE_COLS = 256;                     // accumulator columns per stage (2 x 128 or 1 x 256)
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t IDESC = PAIR ? umma_idesc_f16(256, 256, 0, 0) : umma_idesc_f16(128, 128, 0, 0);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + NA * HALO_SLOT;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + NB * B_BYTES);
+  uint64_t* a_empty = a_full + NA;
+  uint64_t* b_full = a_empty + NA;
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* tfull_bar = b_empty + NB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int tiles_w = p.img_w >> 7;
+  const int per_img = (p.img_h >> 1) * tiles_w;            // tiles of 128 pixels x 2 rows per image
+  const int n_tiles_n = p.N / BN;
+  const int total_tiles = p.bn * per_img * n_tiles_n;      // p.bn carries the batch size here
+  const int chunks = p.kc_per_tap;
+  const int c_in = chunks * kBK;
+  const int tile0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x, tile_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a[0]);
+    tma_prefetch_desc(&p.tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], PAIR ? 512 : 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
+  }
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 1, phb = 1;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int ms = tile / n_tiles_n, nt = tile - ms * n_tiles_n;
+        const int img = ms / per_img, rem = ms - img * per_img;
+        const int h0 = (rem / tiles_w) * 2 + static_cast<int>(rank), w0 = (rem % tiles_w) << 7;
+        for (int c = 0; c < chunks; ++c) {
+          mbar_wait(&a_empty[sa], pha);
+          if (PAIR) {
+            if (rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2 * HALO_BYTES);
+            tma_load_4d_pair(sA + sa * HALO_SLOT, &p.tma_a[0], dsmem_addr(smem_u32(&a_full[sa]), 0), c * kBK, w0 - 1, h0 - 1, img);
+          } else {
+            mbar_arrive_expect_tx(&a_full[sa], HALO_BYTES);
+            tma_load_4d(sA + sa * HALO_SLOT, &p.tma_a[0], &a_full[sa], c * kBK, w0 - 1, h0 - 1, img);
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[sb], phb);
+            if (PAIR) {
+              if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], 2 * B_BYTES);
+              tma_load_2d_pair(sB + sb * B_BYTES, &p.tma_b, dsmem_addr(smem_u32(&b_full[sb]), 0), tap * c_in + c * kBK,
+                               nt * BN + static_cast<int>(rank) * 128);
+            } else {
+              mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
+              tma_load_2d(sB + sb * B_BYTES, &p.tma_b, &b_full[sb], tap * c_in + c * kBK, nt * BN);
+            }
+            if (++sb == NB) { sb = 0; phb ^= 1; }
+          }
+          if (++sa == NA) { sa = 0; pha ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
+    if (rank == 0 && elect_one()) {
+      int sa = 0, sb = 0, local = 0;
+      uint32_t pha = 0, phb = 0;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA)), b_lo0 = umma_desc_lo(smem_u32(sB));
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++local) {
+        const int as = local & 1;
+        mbar_wait(&tempty_bar[as], ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * STAGE_COLS;
+        for (int c = 0; c < chunks; ++c) {
+          mbar_wait(&a_full[sa], pha);
+          const uint32_t halo_lo = a_lo0 + sa * (HALO_SLOT >> 4);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {      // unrolled: the tap offsets are immediates
+            mbar_wait(&b_full[sb], phb);
+            tc_fence_after();
+            const uint32_t b_lo = b_lo0 + sb * (B_BYTES >> 4);
+#pragma unroll
+            for (int sub = 0; sub < MSUB; ++sub) {
+              const uint32_t a_lo = halo_lo + ((sub + tap / 3) * kHaloW + tap % 3) * 8;     // 128-byte rows = 8 x 16 B
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint32_t acc = (tap | k) != 0 ? 1u : (c != 0 ? 1u : 0u);
+                if (PAIR) umma_f16_ss_pair_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, IDESC, acc);
+                else umma_f16_ss_lo(d_tmem + sub * 128, a_lo + 2 * k, b_lo + 2 * k, IDESC, acc);
+              }
+            }
+            if (PAIR) umma_commit_pair(&b_empty[sb], 3); else umma_commit(&b_empty[sb]);
+            if (++sb == NB) { sb = 0; phb ^= 1; }
+          }
+          if (PAIR) umma_commit_pair(&a_empty[sa], 3); else umma_commit(&a_empty[sa]);
+          if (++sa == NA) { sa = 0; pha ^= 1; }
+        }
+        if (PAIR) umma_commit_pair(&tfull_bar[as], 3); else umma_commit(&tfull_bar[as]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (thread == pixel, half the columns)
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    constexpr int kChunks = BN / 2 / 32;
+    const int c_begin = half * (BN / 2);
+    int local = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++local) {
+      const int ms = tile / n_tiles_n, nt = tile - ms * n_tiles_n;
+      const int img = ms / per_img, rem = ms - img * per_img;
+      const int h0 = (rem / tiles_w) * 2 + static_cast<int>(rank), w0 = (rem % tiles_w) << 7;
+      const int as = local & 1;
+      const long grow0 = (static_cast<long>(img) * p.img_h + h0) * p.img_w + w0 + row;
+      uint4 resid[RESID ? MSUB : 1][RESID ? kChunks : 1][4];
+      if (RESID) {
+#pragma unroll
+        for (int sub = 0; sub < MSUB; ++sub)
+#pragma unroll
+          for (int ci = 0; ci < kChunks; ++ci) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (grow0 + static_cast<long>(sub) * p.img_w) * p.res_stride +
+                                                             nt * BN + c_begin + ci * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) resid[sub][ci][q] = __ldg(rp + q);
+          }
+      }
+      mbar_wait(&tfull_bar[as], (local >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int sub = 0; sub < MSUB; ++sub) {
+        const long grow = grow0 + static_cast<long>(sub) * p.img_w;
+        const uint32_t taddr = tmem_base + as * STAGE_COLS + (PAIR ? 0 : sub * 128) + lane_addr;
+#pragma unroll
+        for (int ci = 0; ci < kChunks; ++ci) {
+          const int c0 = c_begin + ci * 32;
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          epilogue_store32_pre(v, resid[RESID ? sub : 0][RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
+        }
+      }
+      tc_fence_before();
+      if (PAIR) mbar_arrive_cluster(dsmem_addr(smem_u32(&tempty_bar[as]), 0));
+      else mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, bool PAIR, bool RESID>
+static int launch_halo_r(const GemmKParams& kp, cudaStream_t stream) {
+  constexpr int msub = PAIR ? 1 : 2;
+  constexpr int halo_slot = ((msub + 2) * kHaloW * 128 + 1023) / 1024 * 1024;
+  constexpr int smem = 2 * halo_slot + (PAIR ? 7 : 5) * 128 * kBK * 2 + 1024 + 256;
+  static bool attr_done = false;  // benign race: idempotent
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel<BN, PAIR, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv3_halo<%d>): %s", BN, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const long tiles = static_cast<long>(kp.bn) * (kp.img_h / 2) * (kp.img_w / 128) * (kp.N / BN);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kPersistThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    cfg.gridDim = dim3(2 * static_cast<unsigned>(tiles < 74 ? tiles : 74));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(static_cast<unsigned>(tiles < 148 ? tiles : 148));
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3_halo_kernel<BN, PAIR, RESID>, kp);
+  if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "conv3_halo launch: %s", cudaGetErrorString(e));
+  IR_CUDA_LAUNCH_CHECK("conv3_halo launch");
+  return 0;
+}
+
+static int launch_halo(const GemmKParams& kp, bool pair, cudaStream_t stream) {
+  const bool resid = kp.residual != nullptr;
+  if (pair) return resid ? launch_halo_r<256, true, true>(kp, stream) : launch_halo_r<256, true, false>(kp, stream);
+  return resid ? launch_halo_r<128, false, true>(kp, stream) : launch_halo_r<128, false, false>(kp, stream);
 }
 
 template <int BN, int STAGES, int MSUB, bool RESID>
@@ -878,6 +1137,36 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
   kp.act = p->act;
 
   const uint64_t rs = static_cast<uint64_t>(p->a_row_stride) * 2;  // pixel stride in bytes
+
+  // Halo kernel: 3x3 stride-1 convolutions on images >= 128 pixels wide (every input pixel enters the SM once per
+  // 64-channel slice instead of once per tap). 256-wide N tiles run on the CTA pair, 128-wide ones on a single CTA.
+  if (p->halo < 0 || p->halo > 2) return set_error(IR_ERR_ARG, "ir_conv_gemm: halo=%d (0 = auto, 1 = off, 2 = force)", p->halo);
+  {
+    const bool eligible = p->ksize == 3 && p->stride == 1 && p->w_in % 128 == 0 && p->h_in % 2 == 0 && !geglu &&
+                          p->c_out % 128 == 0 && p->split_k <= 1 && p->tile_n == 0 && p->out_row_stride % 8 == 0 &&
+                          (p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0);
+    if (p->halo == 2 && !eligible)
+      return set_error(IR_ERR_SHAPE, "ir_conv_gemm: halo needs a 3x3 stride-1 conv, w %% 128 == 0, even h, c_out %% 128 == 0, no K split / tile_n");
+    if (eligible && p->halo != 1) {
+      const bool pair = p->c_out % 256 == 0 && p->cta_pair != 1;
+      const long tiles = static_cast<long>(p->batch) * (p->h_in / 2) * (p->w_in / 128) * (p->c_out / (pair ? 256 : 128));
+      if (p->halo == 2 || (p->no_persistent != 1 && tiles >= (pair ? 74 : 148))) {
+        kp.img_h = p->h_in;
+        kp.img_w = p->w_in;
+        kp.bn = p->batch;
+        uint64_t dims[4] = {static_cast<uint64_t>(p->c_in), static_cast<uint64_t>(p->w_in), static_cast<uint64_t>(p->h_in),
+                            static_cast<uint64_t>(p->batch)};
+        uint64_t str[3] = {rs, rs * p->w_in, rs * p->w_in * p->h_in};
+        uint32_t box[4] = {64, 130, pair ? 3u : 4u, 1};
+        if (int rc = make_tmap_f16(&kp.tma_a[0], p->a, 4, dims, str, box)) return rc;
+        uint64_t wdims[2] = {static_cast<uint64_t>(taps) * p->c_in, static_cast<uint64_t>(p->c_out)};
+        uint64_t wstr[1] = {static_cast<uint64_t>(taps) * p->c_in * 2};
+        uint32_t wbox[2] = {64, 128};
+        if (int rc = make_tmap_f16(&kp.tma_b, p->w, 2, wdims, wstr, wbox)) return rc;
+        return launch_halo(kp, pair, stream);
+      }
+    }
+  }
   int m_tiles;
   if (p->ksize == 1) {
     // flattened token-major GEMM: dims (c_in, M, 1, 1)

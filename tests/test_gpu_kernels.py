@@ -165,6 +165,31 @@ def test_conv3x3_cta_pair(L, B, H, Ci, Co, stride):
     assert torch.equal(out, again)
 
 
+@pytest.mark.parametrize("B,H,W,Ci,Co,use_res", [
+    (1, 128, 128, 64, 128, True), (2, 128, 128, 128, 256, True), (1, 4, 256, 64, 128, False), (3, 2, 128, 128, 256, False),
+    (1, 256, 256, 128, 128, True), (1, 6, 384, 64, 512, True), (5, 8, 128, 192, 384, True),
+])
+def test_conv3x3_halo(L, B, H, W, Ci, Co, use_res):
+    """Halo kernel (input slice staged once, nine shifted views): image borders (TMA zero fill), several 128-pixel tiles
+    per row, odd tile counts over the CTA pair, 128-wide (single CTA) and 256-wide (pair) N tiles."""
+    g = _gen(33)
+    x = torch.randn(B, Ci, H, W, device="cuda", generator=g).half()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Ci)).half()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    r = torch.randn(B * H * W, Co, device="cuda", generator=g).half() if use_res else None
+    ref = F.conv2d(x.float(), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
+    if use_res:
+        ref = ref.half().float() + r.float()
+    a = x.permute(0, 2, 3, 1).contiguous().reshape(-1, Ci)
+    wk = w.permute(0, 2, 3, 1).contiguous().reshape(Co, 9 * Ci)
+    kw = dict(batch=B, h_in=H, w_in=W, c_in=Ci, ksize=3, bias=bias, residual=r, split_k=1)
+    out = L.conv_gemm(a, wk, halo=2, **kw)
+    assert rel_l2(out, ref) <= TOL
+    assert torch.equal(out, L.conv_gemm(a, wk, halo=2, **kw))
+    if (W & (W - 1)) == 0 and (H & (H - 1)) == 0:      # the tap-by-tap kernels need power-of-two images
+        assert rel_l2(out, L.conv_gemm(a, wk, halo=1, **kw)) <= 3e-4      # same products, different fp32 summation order
+
+
 def test_conv_rejects_bad_shapes(L):
     a = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
     w = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
