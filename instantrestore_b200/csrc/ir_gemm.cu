@@ -585,11 +585,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
 // CTAs' TMA loads signal the leader's full barrier (expect_tx covers both halves).
 template <int BN, int STAGES, bool RESID>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) conv_gemm_pair_kernel(const __grid_constant__ GemmKParams p) {
-  static_assert(BN == 128 || BN == 256, "pair tile N");
+  static_assert(BN == 128 || BN == 160 || BN == 256, "pair tile N");
   constexpr int B_BYTES = (BN / 2) * kBK * 2;   // this CTA's half of the weight box
   constexpr int STAGE_BYTES = kABytes + B_BYTES;
-  constexpr uint32_t ACC_COLS = BN;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr uint32_t ACC_COLS = BN <= 128 ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
   constexpr uint32_t IDESC = umma_idesc_f16(256, BN, 0, 0);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -696,8 +696,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
     const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const int c_begin = half * (BN / 2);
-    constexpr int kChunks = BN / 2 / 32;          // 4
+    // 160-wide tiles split 96 | 64 so both halves work in 32-column chunks
+    const int c_begin = half == 0 ? 0 : (BN == 160 ? 96 : BN / 2);
+    const int c_end = half == 0 ? (BN == 160 ? 96 : BN / 2) : BN;
+    constexpr int kChunks = BN == 160 ? 3 : BN / 2 / 32;
     const bool fast = p.N % 32 == 0 && (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     int local = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++local) {
@@ -709,34 +711,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
       if (RESID && row_ok) {
 #pragma unroll
         for (int ci = 0; ci < kChunks; ++ci) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + nt * BN + c_begin + ci * 32);
+          if (c_begin + ci * 32 < c_end) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + nt * BN + c_begin + ci * 32);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) resid[ci][q] = __ldg(rp + q);
+            for (int q = 0; q < 4; ++q) resid[ci][q] = __ldg(rp + q);
+          }
         }
       }
       mbar_wait(&tfull_bar[as], (local >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * ACC_COLS + lane_addr;
       if (p.act == IR_ACT_GEGLU) {
+        if constexpr (BN % 128 == 0) {
 #pragma unroll 1
-        for (int blk = 0; blk < BN / 128; ++blk) {
-          const int wcol = nt * BN + blk * 128 + half * 32;
-          const int ocol = (nt * BN + blk * 128) / 2 + half * 32;
-          geglu_store32(taddr + blk * 128 + half * 32, p, grow, wcol, ocol, row_ok);
+          for (int blk = 0; blk < BN / 128; ++blk) {
+            const int wcol = nt * BN + blk * 128 + half * 32;
+            const int ocol = (nt * BN + blk * 128) / 2 + half * 32;
+            geglu_store32(taddr + blk * 128 + half * 32, p, grow, wcol, ocol, row_ok);
+          }
         }
       } else {
 #pragma unroll
         for (int ci = 0; ci < kChunks; ++ci) {
           const int c0 = c_begin + ci * 32;
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
-          tmem_ld_wait();
-          if (row_ok) {
-            float v[32];
+          if (c0 < c_end) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c0, r);
+            tmem_ld_wait();
+            if (row_ok) {
+              float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            if (fast) epilogue_store32_pre(v, resid[RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
-            else epilogue_store<32>(v, p, grow, nt * BN + c0);
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+              if (fast) epilogue_store32_pre(v, resid[RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
+              else epilogue_store<32>(v, p, grow, nt * BN + c0);
+            }
           }
         }
       }
@@ -770,6 +778,7 @@ static int launch_pair(const GemmKParams& kp, int bn_pair, cudaStream_t stream) 
   const bool resid = kp.residual != nullptr && kp.act != IR_ACT_GEGLU && kp.N % 32 == 0 &&
                      (kp.bias == nullptr || (reinterpret_cast<uintptr_t>(kp.bias) & 15) == 0);
   if (bn_pair == 128) return resid ? launch_pair_r<128, 8, true>(kp, stream) : launch_pair_r<128, 8, false>(kp, stream);
+  if (bn_pair == 160) return resid ? launch_pair_r<160, 7, true>(kp, stream) : launch_pair_r<160, 7, false>(kp, stream);
   return resid ? launch_pair_r<256, 6, true>(kp, stream) : launch_pair_r<256, 6, false>(kp, stream);
 }
 
@@ -1286,15 +1295,20 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
   if (p->cta_pair != 1 && split == 1 && m_tiles >= 2) {
     int cand = 0;
     if (p->c_out % 256 == 0 && (p->tile_n == 0 || p->tile_n == 256)) cand = 256;
+    else if (p->c_out % 160 == 0 && !geglu && (p->tile_n == 0 || p->tile_n == 160)) cand = 160;
     else if (p->c_out % 128 == 0 && (p->tile_n == 0 || p->tile_n == 128)) cand = 128;
     if (cand) {
       const long ptiles = static_cast<long>((m_tiles + 1) / 2) * (p->c_out / cand);
       if (p->cta_pair == 2) bn_pair = cand;
-      else if (!geglu && p->no_persistent != 1 && cand == 256 && bn_tile == 256 && ptiles >= 296 && num_k >= 16) bn_pair = cand;
+      // auto: 3x3 convolutions (K >= 1152) from 64 pair tiles, linears from 4 tiles per cluster; not the 128-wide
+      // tiles (the stacked-M single-CTA kernel and the halo kernel are ahead there)
+      else if (!geglu && p->no_persistent != 1 && cand != 128 && p->split_k == 0 &&
+               ((p->ksize == 3 && num_k >= 18 && ptiles >= 64) || (num_k >= 16 && ptiles >= 296)))
+        bn_pair = cand;
     }
   }
   if (p->cta_pair == 2 && !bn_pair)
-    return set_error(IR_ERR_SHAPE, "ir_conv_gemm: cta_pair needs c_out %% 128 == 0, no K split, >= 2 M tiles (c_out=%d split=%d m_tiles=%d)", p->c_out, split, m_tiles);
+    return set_error(IR_ERR_SHAPE, "ir_conv_gemm: cta_pair needs c_out %% 128 == 0 or %% 160 == 0, no K split, >= 2 M tiles (c_out=%d split=%d m_tiles=%d)", p->c_out, split, m_tiles);
   const bool use_pair = bn_pair != 0;
 
   {

@@ -120,7 +120,8 @@ def test_conv3x3_split_k_cluster(L, B, H, Ci, Co, stride, split):
 @pytest.mark.parametrize("M,K,N,use_res,geglu", [
     (4096, 512, 512, True, False), (640, 320, 256, True, False), (1000, 1280, 1280, False, False), (257, 64, 256, True, False),
     (20000, 640, 1024, True, False), (4096, 320, 2560, False, True), (777, 128, 512, False, True),
-    (5000, 1152, 128, True, False), (900, 64, 640, False, False),
+    (5000, 1152, 128, True, False), (900, 64, 640, False, False), (4096, 320, 320, True, False), (3000, 640, 960, True, False),
+    (130, 64, 160, False, False),
 ])
 def test_linear_cta_pair(L, M, K, N, use_res, geglu):
     """tcgen05 cta_group::2 kernel (256 x 256 tiles over two SMs): odd tile counts, ragged M, residual, GEGLU; must agree
@@ -149,7 +150,8 @@ def test_linear_cta_pair(L, M, K, N, use_res, geglu):
 
 @pytest.mark.parametrize("B,H,Ci,Co,stride", [
     (1, 64, 512, 512, 1), (2, 32, 256, 256, 1), (3, 16, 1280, 1280, 1), (5, 8, 128, 256, 1), (1, 64, 128, 256, 2),
-    (2, 128, 64, 256, 1), (2, 128, 64, 128, 1), (3, 32, 128, 128, 2),
+    (2, 128, 64, 256, 1), (2, 128, 64, 128, 1), (3, 32, 128, 128, 2), (2, 32, 320, 640, 1), (1, 64, 320, 320, 1),
+    (4, 16, 640, 1280, 2),
 ])
 def test_conv3x3_cta_pair(L, B, H, Ci, Co, stride):
     g = _gen(32)
