@@ -85,6 +85,11 @@ typedef struct {
                       bottom/right only (diffusers Downsample2D(padding=0) of the VAE encoder) */
   int cta_pair; /* A-B measurement: 0 = auto, 1 = never, 2 = always the CTA-pair (tcgen05 cta_group::2, 256 x 256
                    tiles over two SMs) kernel; needs c_out % 256 == 0, no K split, >= 2 M tiles */
+  void* gn_partial; /* optional fp32 [batch, h_out*w_out/32, gn_groups, 2]: (mean, M2) of every 32-pixel slab of the
+                       stored outputs per GroupNorm group — pass A of the NEXT GroupNorm, computed in the epilogue (or by
+                       a separate pass when the kernel chosen for the shape has no fused statistics). Needs
+                       c_out / gn_groups in {4, 8, 16} and h_out*w_out % 128 == 0. Hand it to ir_groupnorm.partial_in */
+  int gn_groups;
   int halo; /* A-B measurement: 0 = auto, 1 = never, 2 = always the halo kernel (3x3 stride 1, w_in % 128 == 0, even
                h_in, c_out % 128 == 0): each 64-channel input slice is staged once per tile as a (rows+2) x 130 pixel box
                and the nine taps read shifted views of it */
@@ -160,6 +165,7 @@ typedef struct {
   void* out;
   int out_row_stride;
   void* workspace;
+  const void* partial_in; /* optional: slab moments written by ir_conv_gemm (gn_partial) for exactly this x; pass A is skipped */
 } ir_groupnorm_params;
 size_t ir_groupnorm_workspace_bytes(int batch, int groups);
 int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream);

@@ -31,7 +31,7 @@ class ConvGemmParams(C.Structure):
         ("w", C.c_void_p), ("c_out", C.c_int), ("bias", C.c_void_p), ("residual", C.c_void_p),
         ("res_row_stride", C.c_int), ("act", C.c_int), ("out", C.c_void_p), ("out_row_stride", C.c_int),
         ("tile_n", C.c_int), ("split_k", C.c_int), ("m_sub", C.c_int), ("no_persistent", C.c_int), ("pad_hi_only", C.c_int),
-        ("cta_pair", C.c_int), ("halo", C.c_int),
+        ("cta_pair", C.c_int), ("gn_partial", C.c_void_p), ("gn_groups", C.c_int), ("halo", C.c_int),
     ]
 
 
@@ -54,7 +54,7 @@ class GroupNormParams(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("x_row_stride", C.c_int), ("batch", C.c_int), ("hw", C.c_int), ("channels", C.c_int),
         ("groups", C.c_int), ("eps", C.c_float), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("silu", C.c_int),
-        ("out", C.c_void_p), ("out_row_stride", C.c_int), ("workspace", C.c_void_p),
+        ("out", C.c_void_p), ("out_row_stride", C.c_int), ("workspace", C.c_void_p), ("partial_in", C.c_void_p),
     ]
 
 
@@ -230,9 +230,11 @@ def _scratch(device, nbytes: int) -> torch.Tensor:
 def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: int, c_in: int, ksize: int = 1,
               stride: int = 1, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
               act: int = IR_ACT_NONE, out: torch.Tensor | None = None, tile_n: int = 0, split_k: int = 0,
-              a_row_stride: int | None = None, pad_hi_only: bool = False, no_persistent: int = 0, m_sub: int = 0, cta_pair: int = 0, halo: int = 0) -> torch.Tensor:
-    """a: fp16 channel-last [batch*h_in*w_in, >=c_in]; w: fp16 [c_out, ksize*ksize*c_in]."""
-    _h(a, "a"); _h(w, "w"); _f(bias, "bias")
+              a_row_stride: int | None = None, pad_hi_only: bool = False, no_persistent: int = 0, m_sub: int = 0, cta_pair: int = 0, halo: int = 0, gn_partial: torch.Tensor | None = None,
+              gn_groups: int = 32) -> torch.Tensor:
+    """a: fp16 channel-last [batch*h_in*w_in, >=c_in]; w: fp16 [c_out, ksize*ksize*c_in].
+    gn_partial: fp32 [batch * (h_out*w_out/32) * gn_groups * 2] (gn_partial_numel) to receive pass A of the next GroupNorm."""
+    _h(a, "a"); _h(w, "w"); _f(bias, "bias"); _f(gn_partial, "gn_partial")
     c_out = w.shape[0]
     assert w.shape[1] == ksize * ksize * c_in and w.is_contiguous(), (w.shape, ksize, c_in)
     m = batch * (h_in // stride) * (w_in // stride)
@@ -245,7 +247,7 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
         ksize=ksize, stride=stride, w=ptr(w), c_out=c_out, bias=ptr(bias),
         residual=ptr(residual), res_row_stride=residual.stride(-2) if residual is not None else 0,
         act=act, out=ptr(out), out_row_stride=out.stride(-2), tile_n=tile_n, split_k=split_k,
-        pad_hi_only=int(pad_hi_only), no_persistent=int(no_persistent), m_sub=m_sub, cta_pair=cta_pair, halo=halo)
+        pad_hi_only=int(pad_hi_only), no_persistent=int(no_persistent), m_sub=m_sub, cta_pair=cta_pair, halo=halo, gn_partial=ptr(gn_partial), gn_groups=gn_groups)
     k_tot = ksize * ksize * c_in
     _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks{ksize}s{stride}", 2.0 * m * k_tot * c_out,
          2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out
@@ -296,10 +298,21 @@ def shared_attn(q: torch.Tensor, *, heads: int, scale: float, batch: int, s_q: i
     return (out, mass) if chunk_mass else out
 
 
+def gn_partial_supported(hw: int, channels: int, groups: int = 32) -> bool:
+    """Shapes for which conv_gemm can emit GroupNorm pass A of its output (whole groups per 32-column accumulator chunk,
+    whole 32-pixel slabs per image)."""
+    return channels % groups == 0 and channels // groups in (4, 8, 16) and hw % 128 == 0
+
+
+def gn_partial_numel(batch: int, hw: int, groups: int = 32) -> int:
+    return batch * (hw // 32) * groups * 2
+
+
 def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch: int, hw: int, groups: int = 32,
               eps: float = 1e-5, silu: bool = False, out: torch.Tensor | None = None,
-              workspace: torch.Tensor | None = None) -> torch.Tensor:
-    _h(x, "x"); _f(gamma, "gamma"); _f(beta, "beta")
+              workspace: torch.Tensor | None = None, partial_in: torch.Tensor | None = None) -> torch.Tensor:
+    """partial_in: the gn_partial tensor a conv_gemm call filled for exactly this x (pass A is then skipped)."""
+    _h(x, "x"); _f(gamma, "gamma"); _f(beta, "beta"); _f(partial_in, "partial_in")
     channels = x.shape[-1]
     if out is None:
         out = torch.empty((batch * hw, channels), dtype=torch.float16, device=x.device)
@@ -308,7 +321,7 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch
                                 device=x.device)
     p = GroupNormParams(x=ptr(x), x_row_stride=x.stride(-2), batch=batch, hw=hw, channels=channels, groups=groups,
                         eps=eps, gamma=ptr(gamma), beta=ptr(beta), silu=int(silu), out=ptr(out),
-                        out_row_stride=out.stride(-2), workspace=ptr(workspace))
+                        out_row_stride=out.stride(-2), workspace=ptr(workspace), partial_in=ptr(partial_in))
     _run("ir_groupnorm", f"b{batch}_hw{hw}_c{channels}", 0.0, 4.0 * batch * hw * channels, load().ir_groupnorm,
          C.byref(p), stream_ptr())
     return out

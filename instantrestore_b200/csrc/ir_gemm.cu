@@ -47,6 +47,8 @@ struct GemmKParams {
   int split, kb_per_split;
   int m_tiles;
   int img_h, img_w;     // halo kernel: output (= input) image size
+  float2* gn_partial;   // optional: per-(image, 32-row slab, group) (mean, M2) of the stored outputs (GroupNorm pass A)
+  int gn_cpg, gn_hw, gn_groups;
   const float* bias;
   const __half* residual;
   int res_stride;
@@ -313,6 +315,61 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
 }
 
 
+// GroupNorm pass A fused into the conv epilogue: (mean, M2) of one warp's 32 rows x 32 columns (= 32 / CPG whole groups)
+// of the fp16-rounded outputs. Per-lane group sums, then a reduce-scatter butterfly over the 32 lanes (each halving
+// step keeps half of the groups) — fixed summation tree, deterministic. The slab format is the one gn_merge_kernel
+// reads (rows_per_slab = 32).
+template <int CPG>
+__device__ __forceinline__ void gn_stats_chunk(const float (&v)[32], int lane, float2* __restrict__ dst) {
+  constexpr int G = 32 / CPG;
+  constexpr int LOG2G = G == 8 ? 3 : G == 4 ? 2 : 1;
+  float s[G], q[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    s[g] = 0.f;
+    q[g] = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) {
+      const float r = round_h(v[g * CPG + j]);
+      s[g] += r;
+      q[g] = fmaf(r, r, q[g]);
+    }
+  }
+  int off = 16;
+#pragma unroll
+  for (int h = G / 2; h >= 1; h >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float s_send = up ? s[i] : s[i + h], s_keep = up ? s[i + h] : s[i];
+      const float q_send = up ? q[i] : q[i + h], q_keep = up ? q[i + h] : q[i];
+      s[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+      q[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (int o = 16 >> LOG2G; o >= 1; o >>= 1) {
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], o);
+  }
+  if ((lane & ((32 >> LOG2G) - 1)) == 0) {
+    const float mean = s[0] * (1.0f / (32 * CPG));
+    dst[lane >> (5 - LOG2G)] = make_float2(mean, fmaxf(q[0] - s[0] * mean, 0.f));
+  }
+}
+
+__device__ __forceinline__ void gn_stats32(const float (&v)[32], const GemmKParams& p, long grow, int gcol) {
+  const int lane = threadIdx.x & 31;
+  const int w0 = static_cast<int>(grow) - lane;          // first row of this warp's 32-row slab (all of one image)
+  const int img = w0 / p.gn_hw;
+  const int slab = (w0 - img * p.gn_hw) >> 5;
+  float2* dst = p.gn_partial + (static_cast<size_t>(img) * (p.gn_hw >> 5) + slab) * p.gn_groups + gcol / p.gn_cpg;
+  if (p.gn_cpg == 4) gn_stats_chunk<4>(v, lane, dst);
+  else if (p.gn_cpg == 8) gn_stats_chunk<8>(v, lane, dst);
+  else gn_stats_chunk<16>(v, lane, dst);
+}
+
 // epilogue_store<32> with the residual already in registers (prefetched before the accumulator was ready)
 __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4 (&res)[4], bool has_res, const GemmKParams& p,
                                                      long grow, int gcol) {
@@ -339,6 +396,7 @@ __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = silu(round_h(v[i]));
   }
+  if (p.gn_partial) gn_stats32(v, p, grow, gcol);
   __half* op = p.out + grow * p.out_stride + gcol;
 #pragma unroll
   for (int q = 0; q < 4; ++q)
@@ -1105,7 +1163,20 @@ static int pow2_floor(int x) {
 
 }  // namespace ir
 
+static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_, bool* stats_fused);
+
 extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
+  using namespace ir;
+  bool stats_fused = false;
+  const int rc = conv_gemm_dispatch(p, stream_, &stats_fused);
+  if (rc != 0 || !p->gn_partial || stats_fused) return rc;
+  // the kernel chosen for this shape (one tile per CTA / split-K) has no fused statistics: separate pass A
+  const int hw = (p->h_in / p->stride) * (p->w_in / p->stride);
+  return launch_gn_partial(p->out, p->out_row_stride, p->batch, hw, p->c_out, p->gn_groups, 32, p->gn_partial,
+                           static_cast<cudaStream_t>(stream_));
+}
+
+static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_, bool* stats_fused) {
   using namespace ir;
   if (!p || !p->a || !p->w || !p->out) return set_error(IR_ERR_ARG, "ir_conv_gemm: NULL argument");
   if (int rc = check_arch()) return rc;
@@ -1144,6 +1215,21 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
   kp.out = static_cast<__half*>(p->out);
   kp.out_stride = p->out_row_stride;
   kp.act = p->act;
+  // GroupNorm pass A on the outputs (optional): whole groups per 32-column chunk, whole 32-row slabs per image
+  const bool fast_epilogue = p->c_out % 32 == 0 && (p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0);
+  if (p->gn_partial) {
+    const int hw_out = h_out * w_out;
+    const int cpg = p->gn_groups > 0 && p->c_out % p->gn_groups == 0 ? p->c_out / p->gn_groups : 0;
+    if (geglu || (cpg != 4 && cpg != 8 && cpg != 16) || hw_out % 128 != 0 || (reinterpret_cast<uintptr_t>(p->gn_partial) & 7))
+      return set_error(IR_ERR_SHAPE, "ir_conv_gemm: gn_partial needs c_out / gn_groups in {4, 8, 16}, h_out*w_out %% 128 == 0, no GEGLU (c_out=%d groups=%d hw=%d)",
+                       p->c_out, p->gn_groups, hw_out);
+    if (fast_epilogue) {
+      kp.gn_partial = static_cast<float2*>(p->gn_partial);
+      kp.gn_cpg = cpg;
+      kp.gn_hw = hw_out;
+      kp.gn_groups = p->gn_groups;
+    }
+  }
 
   const uint64_t rs = static_cast<uint64_t>(p->a_row_stride) * 2;  // pixel stride in bytes
 
@@ -1172,6 +1258,7 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
         uint64_t wstr[1] = {static_cast<uint64_t>(taps) * p->c_in * 2};
         uint32_t wbox[2] = {64, 128};
         if (int rc = make_tmap_f16(&kp.tma_b, p->w, 2, wdims, wstr, wbox)) return rc;
+        *stats_fused = kp.gn_partial != nullptr;
         return launch_halo(kp, pair, stream);
       }
     }
@@ -1319,7 +1406,10 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
   }
 
   kp.m_tiles = m_tiles;
-  if (use_pair) return launch_pair(kp, bn_pair, stream);
+  if (use_pair) {
+    *stats_fused = kp.gn_partial != nullptr;
+    return launch_pair(kp, bn_pair, stream);
+  }
   // Persistent kernel when the epilogue / per-CTA set-up is a visible fraction of a tile (short K, GEGLU) and the
   // tile count quantises well over 148 SMs; long-K layers keep two one-tile CTAs per SM (measured: tools/gemm_bench.py).
   bool persistent = false;
@@ -1333,6 +1423,7 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
   if (persistent) {
     // 256 x 128 CTA tiles (two stacked M tiles sharing the weight boxes) when there are plenty of M tiles
     const bool tall = bn_tile == 128 && !geglu && m_tiles >= 2 * 148 && num_k >= 16 && p->m_sub != 1;
+    *stats_fused = kp.gn_partial != nullptr;
     switch (bn_tile) {
       case 64: return launch_persistent<64, 8, 1>(kp, stream);
       case 128: return tall ? launch_persistent<128, 4, 2>(kp, stream) : launch_persistent<128, 6, 1>(kp, stream);
@@ -1341,6 +1432,7 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
       default: return set_error(IR_ERR_SHAPE, "ir_conv_gemm: tile_n=%d unsupported", bn_tile);
     }
   }
+  kp.gn_partial = nullptr;   // one tile per CTA / split-K: statistics come from the separate pass (ir_conv_gemm)
   switch (bn_tile) {
     case 64: return launch<64, 4>(kp, m_tiles, stream);
     case 128: return launch<128, 3>(kp, m_tiles, stream);

@@ -19,6 +19,11 @@ int check_arch();
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
 
+// GroupNorm pass A as a stand-alone launch (ir_norm.cu): partial[(b * slabs + slab) * groups + g] = (mean, M2) over
+// `rows_per_slab` pixels; slabs = ceil(hw / rows_per_slab).
+int launch_gn_partial(const void* x, int row_stride, int batch, int hw, int channels, int groups, int rows_per_slab,
+                      void* partial, cudaStream_t stream);
+
 // Counts kernel launches issued (or captured into a CUDA graph) through the C ABI; read by ir_launch_count().
 void count_launch();
 

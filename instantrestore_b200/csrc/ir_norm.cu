@@ -288,6 +288,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 
 constexpr int kGnMaxSlabs = 1024;
 
+int ir::launch_gn_partial(const void* x, int row_stride, int batch, int hw, int channels, int groups, int rows_per_slab,
+                          void* partial, cudaStream_t stream) {
+  const int slabs = (hw + rows_per_slab - 1) / rows_per_slab;
+  const int vpr = channels >> 3;
+  const int rgroups = vpr < 256 ? 256 / vpr : 1;
+  gn_partial_kernel<<<dim3(slabs, batch), 256, static_cast<size_t>(rgroups) * channels * 2 * sizeof(float), stream>>>(
+      static_cast<const __half*>(x), row_stride, hw, channels, groups, rows_per_slab, static_cast<float2*>(partial));
+  IR_CUDA_LAUNCH_CHECK("gn_partial launch");
+  return 0;
+}
+
 static void gn_plan(int batch, int hw, int* slabs, int* rows_per_slab) {
   // enough CTAs for ~10 MB of loads in flight (592 = 4 per SM), >= 8 rows per slab
   int want = (592 + batch - 1) / batch;
@@ -318,12 +329,18 @@ extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
   float2* partial = static_cast<float2*>(p->workspace);
   float2* stats = partial + static_cast<size_t>(p->batch) * kGnMaxSlabs * p->groups;
   int slabs, rps;
-  gn_plan(p->batch, p->hw, &slabs, &rps);
   const int vpr = p->channels >> 3;
   const int rgroups = vpr < 256 ? 256 / vpr : 1;
-  gn_partial_kernel<<<dim3(slabs, p->batch), 256, static_cast<size_t>(rgroups) * p->channels * 2 * sizeof(float), stream>>>(
-      static_cast<const __half*>(p->x), p->x_row_stride, p->hw, p->channels, p->groups, rps, partial);
-  IR_CUDA_LAUNCH_CHECK("gn_partial launch");
+  if (p->partial_in) {
+    // pass A already ran in the epilogue of the convolution that produced x: 32-pixel slabs
+    if (p->hw % 32 != 0) return set_error(IR_ERR_SHAPE, "ir_groupnorm: partial_in needs hw %% 32 == 0 (hw=%d)", p->hw);
+    slabs = p->hw / 32;
+    rps = 32;
+    partial = const_cast<float2*>(static_cast<const float2*>(p->partial_in));
+  } else {
+    gn_plan(p->batch, p->hw, &slabs, &rps);
+    if (int rc = launch_gn_partial(p->x, p->x_row_stride, p->batch, p->hw, p->channels, p->groups, rps, partial, stream)) return rc;
+  }
   gn_merge_kernel<<<dim3(p->groups, p->batch), 256, 0, stream>>>(partial, p->groups, slabs, rps, p->hw, p->channels / p->groups, p->eps, stats);
   IR_CUDA_LAUNCH_CHECK("gn_merge launch");
   // apply: ~8 CTAs per SM in total, >= 4 * rgroups rows per CTA so the unrolled loop is used

@@ -14,6 +14,7 @@ reference's baddbmm under autocast (diffusers Attention.get_attention_scores), s
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -23,6 +24,7 @@ from .weights import StateDictView, conv_weight_khwc
 
 GN_EPS = 1e-6
 GROUPS = 32
+FUSED_GN_STATS = os.environ.get("IR_FUSED_GN", "1") != "0"     # A-B measurement switch
 
 
 class _Conv:
@@ -125,27 +127,50 @@ class VaeEngine:
             ch=wq.shape[0])
 
     # ------------------------------------------------------------------------------------------ ops
-    def _conv(self, x, cv: _Conv, B, H, W, residual=None):
-        return L.conv_gemm(x, cv.w, batch=B, h_in=H, w_in=W, c_in=cv.c_in, ksize=cv.ksize, stride=cv.stride, bias=cv.b,
-                           residual=residual, pad_hi_only=cv.pad_hi_only)
+    # A producer whose output feeds a GroupNorm computes that norm's pass A (per-slab moments) in its epilogue
+    # (`stats=True` -> returns (out, partial)); the partial travels with the tensor to `_gn`. Shapes the fused
+    # statistics do not cover (tiny test geometries) return partial = None and take the three-kernel GroupNorm.
+    def _partial(self, x, B, hw_out, c_out):
+        if not FUSED_GN_STATS or not L.gn_partial_supported(hw_out, c_out, GROUPS):
+            return None
+        return torch.empty(L.gn_partial_numel(B, hw_out, GROUPS), dtype=torch.float32, device=x.device)
 
-    def _lin(self, x, lin: _Lin, residual=None):
-        return L.conv_gemm(x, lin.w, batch=1, h_in=1, w_in=x.shape[0], c_in=lin.c_in, bias=lin.b, residual=residual)
+    def _conv(self, x, cv: _Conv, B, H, W, residual=None, stats=False):
+        part = self._partial(x, B, (H // cv.stride) * (W // cv.stride), cv.c_out) if stats else None
+        out = L.conv_gemm(x, cv.w, batch=B, h_in=H, w_in=W, c_in=cv.c_in, ksize=cv.ksize, stride=cv.stride, bias=cv.b,
+                          residual=residual, pad_hi_only=cv.pad_hi_only, gn_partial=part, gn_groups=GROUPS)
+        return (out, part) if stats else out
 
-    def _gn(self, x, n: _Norm, B, HW, silu):
-        return L.groupnorm(x, n.g, n.b, batch=B, hw=HW, groups=GROUPS, eps=GN_EPS, silu=silu)
+    def _lin(self, x, lin: _Lin, residual=None, stats_bhw=None):
+        """stats_bhw = (B, hw): also emit the GroupNorm moments of the output, viewed as B images of hw pixels."""
+        part = None
+        if stats_bhw is not None:
+            part = self._partial(x, stats_bhw[0], stats_bhw[1], lin.c_out)
+        if part is None:
+            out = L.conv_gemm(x, lin.w, batch=1, h_in=1, w_in=x.shape[0], c_in=lin.c_in, bias=lin.b, residual=residual)
+        else:   # same GEMM, described as B "images" of 1 x hw tokens so the slabs are per image
+            out = L.conv_gemm(x, lin.w, batch=stats_bhw[0], h_in=1, w_in=stats_bhw[1], c_in=lin.c_in, bias=lin.b,
+                              residual=residual, gn_partial=part, gn_groups=GROUPS)
+        return (out, part) if stats_bhw is not None else out
 
-    def _resnet(self, x, p, B, H, W):
-        t = self._gn(x, p["norm1"], B, H * W, True)
-        h = self._conv(t, p["conv1"], B, H, W)
-        t = self._gn(h, p["norm2"], B, H * W, True)
+    def _gn(self, x, n: _Norm, B, HW, silu, part=None):
+        return L.groupnorm(x, n.g, n.b, batch=B, hw=HW, groups=GROUPS, eps=GN_EPS, silu=silu, partial_in=part)
+
+    def _resnet(self, x, p, B, H, W, xs=None, stats=True):
+        """xs: pass-A moments of x (or None). Returns (out, moments of out) — the next consumer is a GroupNorm everywhere
+        except in front of a down/upsampler (stats=False there)."""
+        t = self._gn(x, p["norm1"], B, H * W, True, xs)
+        h, hs = self._conv(t, p["conv1"], B, H, W, stats=True)
+        t = self._gn(h, p["norm2"], B, H * W, True, hs)
         skip = x if p["shortcut"] is None else self._lin(x, p["shortcut"])
-        return self._conv(t, p["conv2"], B, H, W, residual=skip)
+        if not stats:
+            return self._conv(t, p["conv2"], B, H, W, residual=skip), None
+        return self._conv(t, p["conv2"], B, H, W, residual=skip, stats=True)
 
-    def _mid(self, x, p, B, H, W):
+    def _mid(self, x, p, B, H, W, xs=None):
         S, C = H * W, p["ch"]
-        x = self._resnet(x, p["res0"], B, H, W)
-        t = self._gn(x, p["norm"], B, S, False)
+        x, xs = self._resnet(x, p["res0"], B, H, W, xs)
+        t = self._gn(x, p["norm"], B, S, False, xs)
         q_all, k_all = self._lin(t, p["q"]), self._lin(t, p["k"])           # [B*S, C] each
         attn = torch.empty((B * S, C), dtype=torch.float16, device=x.device)
         scale = float(C) ** -0.5
@@ -156,8 +181,8 @@ class VaeEngine:
             L.softmax_rows(scores, scale)
             v_t = L.conv_gemm(p["v_t"], tb, batch=1, h_in=1, w_in=C, c_in=C)   # [C, S] = W_v X^T
             L.conv_gemm(scores, v_t, batch=1, h_in=1, w_in=S, c_in=S, out=attn[rows])
-        x = self._lin(attn, p["out"], residual=x)
-        return self._resnet(x, p["res1"], B, H, W)
+        x, xs = self._lin(attn, p["out"], residual=x, stats_bhw=(B, S))
+        return self._resnet(x, p["res1"], B, H, W, xs)
 
     # ------------------------------------------------------------------------------------------ public
     def encode(self, images: torch.Tensor, eps: Optional[torch.Tensor]) -> torch.Tensor:
@@ -165,17 +190,17 @@ class VaeEngine:
         Returns latent_dist.sample() * scaling_factor, fp32 NCHW. Records the skip activations (model.py:19-30)."""
         B, _, H, W = images.shape
         x = L.image_in(images.contiguous())
-        x = self._conv(x, self.e_conv_in, B, H, W)
+        x, xs = self._conv(x, self.e_conv_in, B, H, W, stats=True)
         skips = []
         for res, ds in self.e_down:
             skips.append((x, H, W))
-            for r in res:
-                x = self._resnet(x, r, B, H, W)
+            for j, r in enumerate(res):
+                x, xs = self._resnet(x, r, B, H, W, xs, stats=(ds is None or j + 1 < len(res)))
             if ds is not None:
-                x = self._conv(x, ds, B, H, W)
+                x, xs = self._conv(x, ds, B, H, W, stats=True)
                 H, W = H // 2, W // 2
-        x = self._mid(x, self.e_mid, B, H, W)
-        t = self._gn(x, self.e_norm_out, B, H * W, True)
+        x, xs = self._mid(x, self.e_mid, B, H, W, xs)
+        t = self._gn(x, self.e_norm_out, B, H * W, True, xs)
         mom = self._conv(t, self.e_conv_out, B, H, W)                    # [B*hw, 2*lat] mean | logvar
         self.skip_acts = skips
         return L.vae_sample(mom, eps, self.sf, batch=B, c=self.lat, h=H, w=W)
@@ -186,20 +211,21 @@ class VaeEngine:
         B, _, H, W = latents.shape
         z = latents / self.sf + self.d_latent_shift.view(1, -1, 1, 1)
         x = L.latent_in(z.contiguous(), None, 1.0, 0.0)
-        x = self._conv(x, self.d_conv_in, B, H, W)
-        x = self._mid(x, self.d_mid, B, H, W)
+        x, xs = self._conv(x, self.d_conv_in, B, H, W, stats=True)
+        x, xs = self._mid(x, self.d_mid, B, H, W, xs)
         skips = skip_acts if skip_acts is not None else self.skip_acts
         for i, (res, us) in enumerate(self.d_up):
             if self.d_skip is not None:
                 s_act, sh, sw = skips[::-1][i]
                 assert (sh, sw) == (H, W)
-                x = self._lin(s_act, self.d_skip[i], residual=x)          # sample + skip_conv(act * gamma), gamma = 1
-            for r in res:
-                x = self._resnet(x, r, B, H, W)
+                # sample + skip_conv(act * gamma), gamma = 1
+                x, xs = self._lin(s_act, self.d_skip[i], residual=x, stats_bhw=(B, H * W))
+            for j, r in enumerate(res):
+                x, xs = self._resnet(x, r, B, H, W, xs, stats=(us is None or j + 1 < len(res)))
             if us is not None:
                 x = L.upsample_nearest2x(x, batch=B, h=H, w=W)
                 H, W = 2 * H, 2 * W
-                x = self._conv(x, us, B, H, W)
-        t = self._gn(x, self.d_norm_out, B, H * W, True)
+                x, xs = self._conv(x, us, B, H, W, stats=True)
+        t = self._gn(x, self.d_norm_out, B, H * W, True, xs)
         y = self._conv(t, self.d_conv_out, B, H, W)                      # [B*HW, 3]
         return L.image_out(y, batch=B, c=y.shape[1], h=H, w=W, dtype=dtype)

@@ -192,6 +192,47 @@ def test_conv3x3_halo(L, B, H, W, Ci, Co, use_res):
         assert rel_l2(out, L.conv_gemm(a, wk, halo=1, **kw)) <= 3e-4      # same products, different fp32 summation order
 
 
+@pytest.mark.parametrize("kind,B,H,W,Ci,Co,kw", [
+    ("conv", 2, 128, 128, 128, 128, {}),                    # halo kernel, single CTA
+    ("conv", 1, 128, 128, 256, 256, {}),                    # halo kernel, CTA pair
+    ("conv", 4, 64, 64, 512, 512, dict(halo=1)),            # CTA-pair kernel (tap by tap)
+    ("conv", 2, 64, 64, 128, 256, dict(halo=1, cta_pair=1)),  # persistent single-CTA kernel
+    ("conv", 1, 16, 8, 128, 128, {}),                       # one tile per CTA: statistics from the separate pass
+    ("conv", 2, 32, 32, 256, 512, dict(stride=2)),          # stride 2 (16 x 16 outputs)
+    ("lin", 3, 1, 1024, 512, 512, {}),                      # 1 x 1 / linear with a residual, three "images" of 1024 tokens
+])
+def test_conv_emits_groupnorm_pass_a(L, kind, B, H, W, Ci, Co, kw):
+    """ir_conv_gemm(gn_partial=...) + ir_groupnorm(partial_in=...) == the three-kernel GroupNorm of the same tensor."""
+    g = _gen(34)
+    stride = kw.pop("stride", 1)
+    ks = 3 if kind == "conv" else 1
+    a = torch.randn(B * H * W, Ci, device="cuda", generator=g).half()
+    w = (torch.randn(Co, ks * ks * Ci, device="cuda", generator=g) / math.sqrt(ks * ks * Ci)).half()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    hw = (H // stride) * (W // stride)
+    r = torch.randn(B * hw, Co, device="cuda", generator=g).half()
+    gamma, beta = torch.randn(Co, device="cuda", generator=g), torch.randn(Co, device="cuda", generator=g)
+    assert L.gn_partial_supported(hw, Co)
+    part = torch.full((L.gn_partial_numel(B, hw),), float("nan"), device="cuda")
+    args = dict(batch=B, h_in=H, w_in=W, c_in=Ci, ksize=ks, stride=stride, bias=bias, residual=r, **kw)
+    y = L.conv_gemm(a, w, gn_partial=part, **args)
+    assert torch.equal(y, L.conv_gemm(a, w, **args))              # the statistics do not disturb the outputs
+    assert torch.isfinite(part).all()                              # every (image, slab, group) slot was written
+    fused = L.groupnorm(y, gamma, beta, batch=B, hw=hw, eps=1e-6, silu=True, partial_in=part)
+    plain = L.groupnorm(y, gamma, beta, batch=B, hw=hw, eps=1e-6, silu=True)
+    assert rel_l2(fused, plain) <= 2e-4
+    x = y.float().view(B, hw, Co).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(x, 32, gamma, beta, eps=1e-6)).permute(0, 2, 1).reshape(-1, Co)
+    assert rel_l2(fused, ref) <= TOL
+    # slab moments against fp32 math on the stored outputs
+    pm = part.view(B, hw // 32, 32, 2)
+    yv = y.float().view(B, hw // 32, 32, 32, Co // 32)               # [image, slab, pixel, group, channel in group]
+    mean = yv.mean(dim=(2, 4))
+    m2 = ((yv - mean[:, :, None, :, None]) ** 2).sum(dim=(2, 4))
+    assert float((pm[..., 0] - mean).abs().max()) <= 1e-4
+    assert rel_l2(pm[..., 1], m2) <= 1e-3
+
+
 def test_conv_rejects_bad_shapes(L):
     a = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
     w = torch.zeros(64, 60, device="cuda", dtype=torch.float16)

@@ -105,6 +105,49 @@ def test_vae_engine_vs_reference_golden(case, golden):
     assert ey <= 4e-3 and ey <= 1.5 * ey_ac + 3e-4
 
 
+def test_full_geometry_vae_with_fused_groupnorm_statistics(monkeypatch):
+    """sd-vae-ft-mse widths (128/256/512/512, skip convolutions, LoRA) on 128 x 128 images: the shapes where the conv
+    epilogues emit GroupNorm pass A (halo, CTA-pair, persistent and one-tile kernels all occur). Checked against the
+    oracle VAE under the reference's precision contract on the same GPU, and against the same engine with the fused
+    statistics switched off."""
+    from instantrestore_b200 import _lib as L
+    from instantrestore_b200.vae_engine import VaeEngine
+    from oracle import synth
+    from oracle.vae import VaeConfig
+    vcfg = VaeConfig(use_shortcuts=True)
+    vae = synth.make_vae(vcfg, seed=100, lora_rank=4)
+    eng = VaeEngine(vae.state_dict(), "cuda:0", block_out_channels=vcfg.block_out_channels, use_shortcuts=True)
+    c_t, _, eps_main, _, _, _ = synth.images(2, 1, 128, 16)
+    c_t, eps_main = c_t.cuda(), eps_main.cuda()
+    n0 = L.launch_count()
+    z = eng.encode(c_t, eps_main)
+    y = eng.decode(z)
+    torch.cuda.synchronize()
+    launches_fused = L.launch_count() - n0
+    monkeypatch.setattr(L, "gn_partial_supported", lambda *a, **k: False)
+    n0 = L.launch_count()
+    z_plain = eng.encode(c_t, eps_main)
+    y_plain = eng.decode(z_plain)
+    torch.cuda.synchronize()
+    launches_plain = L.launch_count() - n0
+    assert launches_fused < launches_plain, (launches_fused, launches_plain)    # GroupNorm pass-A launches gone
+    assert rel_l2(z, z_plain) <= 1e-3 and rel_l2(y.float(), y_plain.float()) <= 2e-3
+    vae_c = vae.cuda()
+    with torch.no_grad():
+        z_gold = vae_c.encode_sample(c_t, eps_main) * vcfg.scaling_factor
+        vae_c.decoder.incoming_skip_acts = vae_c.encoder.current_down_blocks
+        y_gold = vae_c.decode(z_gold / vcfg.scaling_factor).clamp(-1, 1)
+        with torch.autocast("cuda", dtype=torch.float16):
+            z_ac = vae_c.encode_sample(c_t, eps_main) * vcfg.scaling_factor
+            vae_c.decoder.incoming_skip_acts = vae_c.encoder.current_down_blocks
+            y_ac = vae_c.decode(z_ac.float() / vcfg.scaling_factor).clamp(-1, 1)
+    ez, ez_ac = rel_l2(z, z_gold), rel_l2(z_ac.float(), z_gold)
+    ey, ey_ac = rel_l2(y.float(), y_gold), rel_l2(y_ac.float(), y_gold)
+    print(f"full-geometry VAE: latent ours {ez:.3e} autocast {ez_ac:.3e} | image ours {ey:.3e} autocast {ey_ac:.3e}")
+    assert ez <= 2e-3 and ez <= 1.5 * ez_ac + 2e-4
+    assert ey <= 4e-3 and ey <= 1.5 * ey_ac + 3e-4
+
+
 def _image_cases():
     from oracle.make_golden import IMAGE_CASES
     return IMAGE_CASES
