@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, smoke, bench, ncu launch list (+ optional full capture). Logs -> gpurun_out/.
-# usage: tools/gpu_round.sh <tag> [tests|bench|ncu|full ...]   (default: tests bench ncu)
+# usage: tools/gpu_round.sh <tag> [tests|bench|ncu|caps|full ...]   (default: tests bench ncu)
 set -u
 TAG=${1:-r01}; shift || true
 WHAT=${*:-tests bench ncu}
@@ -24,6 +24,20 @@ ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_launches.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
   wc -l $OUT/${TAG}_launches.csv ;;
+caps)
+  # ncu --set full of the dominant kernels on micro-drivers; summarised on the box (reports are ~10 MB each and
+  # gpurun_out is capped at 64 MiB), only the text summaries and ncu_traffic.json travel back
+  cap() { n=$1; k=$2; key=$3; shift 3
+    timeout 150 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o /tmp/${TAG}_$n python "$@" > $OUT/${TAG}_cap_$n.log 2>&1
+    echo "cap $n rc=$?"
+    ncu -i /tmp/${TAG}_$n.ncu-rep --page raw --csv > $OUT/${TAG}_raw_$n.csv 2>/dev/null
+    python tools/ncu_summary.py /tmp/${TAG}_$n.ncu-rep profiles/${TAG}_ncu_full_$n.txt "$key" > /dev/null && cp profiles/${TAG}_ncu_full_$n.txt profiles/ncu_traffic.json $OUT/
+    rm -f /tmp/${TAG}_$n.ncu-rep; }
+  cap conv_halo_pair_512 conv "ir_conv_gemm:m65536_k4608_n512_ks3s1" tools/gemm_one.py conv3 4 128 512 512
+  cap conv_halo_128 conv "ir_conv_gemm:m1048576_k1152_n128_ks3s1" tools/gemm_one.py conv3 4 512 128 128
+  cap conv_pair160_320 conv "ir_conv_gemm:m131072_k2880_n320_ks3s1" tools/gemm_one.py conv3 32 64 320 320
+  cap attn_b32 shared_attn "ir_shared_attn_fwd:b32_h5_sq4096_skv4096" tools/attn_one.py 32 5 4096 1 0 0
+  cap attn_b4 shared_attn "ir_shared_attn_fwd:b4_h5_sq4096_skv4096" tools/attn_one.py 4 5 4096 1 0 0 ;;
 full)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-shared_attn} -s ${NCU_SKIP:-20} -c ${NCU_COUNT:-3} \
      -f -o $OUT/${TAG}_prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
