@@ -33,6 +33,10 @@ UNET_CASES = [  # name, batch, n_ref, use_adain, train_input, lora_rank, valid
     ("unet_tiny_base", 1, 2, False, True, 0, None),
     ("unet_tiny_final", 2, 2, True, False, 4, None),
     ("unet_tiny_padded", 2, 3, True, False, 4, [3, 1]),
+    # reference-count sweep of BASELINE configs[4] (N_ref in {1, 2, 4, 8}); N = 2, 3 above, N = 4 at full width
+    ("unet_tiny_n1", 2, 1, True, False, 4, None),
+    ("unet_tiny_n8", 1, 8, True, False, 0, None),
+    ("unet_tiny_n8_ragged_own", 2, 8, True, True, 4, [8, 5]),
 ]
 
 
