@@ -162,3 +162,16 @@ def test_image_transform_matches_reference_transform():
     x = torch.rand(3, 8, 8) * 2.4 - 1.2
     ref = ((x * 0.5 + 0.5).clamp(0, 1) * 255).permute(1, 2, 0).numpy().astype("uint8")     # vis_utils.py:14-23
     assert np.array_equal(np.asarray(tensor2im(x, unnorm=True)), ref)
+
+
+def test_fused_groupnorm_statistics_shape_rules():
+    """Which conv outputs can carry GroupNorm pass A out of the epilogue (ir_conv_gemm.gn_partial): whole groups per
+    32-column accumulator chunk (4, 8 or 16 channels per group) and whole 32-pixel slabs per image (hw % 128 == 0)."""
+    from instantrestore_b200 import _lib as L
+    for hw, c, ok in [(512 * 512, 128, True), (256 * 256, 256, True), (64 * 64, 512, True), (64 * 64, 320, False),
+                      (32 * 32, 640, False), (8 * 8, 512, False), (16 * 8, 128, True), (4096, 64, False), (4096, 1024, False)]:
+        assert L.gn_partial_supported(hw, c) is ok, (hw, c)
+    assert L.gn_partial_numel(3, 4096) == 3 * 128 * 32 * 2
+    # the VAE of the step: every GroupNorm input at 512x512 images qualifies
+    for hw, c in [(512 * 512, 128), (256 * 256, 128), (256 * 256, 256), (128 * 128, 256), (128 * 128, 512), (64 * 64, 512)]:
+        assert L.gn_partial_supported(hw, c)
