@@ -93,6 +93,8 @@ typedef struct {
   int halo; /* A-B measurement: 0 = auto, 1 = never, 2 = always the halo kernel (3x3 stride 1, w_in % 128 == 0, even
                h_in, c_out % 128 == 0): each 64-channel input slice is staged once per tile as a (rows+2) x 130 pixel box
                and the nine taps read shifted views of it */
+  int wide_io; /* A-B measurement: 0 = auto (256-bit residual loads / output stores in the epilogue whenever out and
+                  residual rows are 32-byte aligned; results are bit-identical), 1 = always 128-bit */
 } ir_conv_gemm_params;
 int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
 

@@ -49,6 +49,7 @@ struct GemmKParams {
   int img_h, img_w;     // halo kernel: output (= input) image size
   float2* gn_partial;   // optional: per-(image, 32-row slab, group) (mean, M2) of the stored outputs (GroupNorm pass A)
   int gn_cpg, gn_hw, gn_groups;
+  int wide_io;          // 256-bit epilogue loads / stores (rows are 32-byte aligned)
   const float* bias;
   const __half* residual;
   int res_stride;
@@ -370,6 +371,37 @@ __device__ __forceinline__ void gn_stats32(const float (&v)[32], const GemmKPara
   else gn_stats_chunk<16>(v, lane, dst);
 }
 
+// 64 bytes of one output row (32 fp16 columns) per thread: four 16-byte accesses, or two 32-byte ones (sm_100
+// LDG/STG.256) — the thread-per-row epilogue touches one sector per thread per access, so halving the number of
+// accesses halves the L1TEX LSU wavefronts (the busiest unit of the short-K 128-channel layers).
+__device__ __forceinline__ void load_row64(const __half* ptr, uint4 (&r)[4], int wide) {
+  if (wide) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0].x), "=r"(r[0].y), "=r"(r[0].z), "=r"(r[0].w), "=r"(r[1].x), "=r"(r[1].y), "=r"(r[1].z), "=r"(r[1].w)
+                 : "l"(ptr));
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[2].x), "=r"(r[2].y), "=r"(r[2].z), "=r"(r[2].w), "=r"(r[3].x), "=r"(r[3].y), "=r"(r[3].z), "=r"(r[3].w)
+                 : "l"(ptr + 16));
+  } else {
+    const uint4* rp = reinterpret_cast<const uint4*>(ptr);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = __ldg(rp + q);
+  }
+}
+__device__ __forceinline__ void store_row64(__half* ptr, const uint4 (&r)[4], int wide) {
+  if (wide) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r[0].x), "r"(r[0].y), "r"(r[0].z),
+                 "r"(r[0].w), "r"(r[1].x), "r"(r[1].y), "r"(r[1].z), "r"(r[1].w)
+                 : "memory");
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr + 16), "r"(r[2].x), "r"(r[2].y), "r"(r[2].z),
+                 "r"(r[2].w), "r"(r[3].x), "r"(r[3].y), "r"(r[3].z), "r"(r[3].w)
+                 : "memory");
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(ptr)[q] = r[q];
+  }
+}
+
 // epilogue_store<32> with the residual already in registers (prefetched before the accumulator was ready)
 __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4 (&res)[4], bool has_res, const GemmKParams& p,
                                                      long grow, int gcol) {
@@ -398,10 +430,12 @@ __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4
   }
   if (p.gn_partial) gn_stats32(v, p, grow, gcol);
   __half* op = p.out + grow * p.out_stride + gcol;
+  uint4 packed[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
-    reinterpret_cast<uint4*>(op)[q] = make_uint4(pack_half2(v[q * 8], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
-                                                 pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+    packed[q] = make_uint4(pack_half2(v[q * 8], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
+                           pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+  store_row64(op, packed, p.wide_io);
 }
 
 // ------------------------------------------------------------------------------------------------ persistent kernel
@@ -572,9 +606,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
           for (int ci = 0; ci < kMaxChunks; ++ci) {
             const int gcol = nt * BN + cb + ci * 32;
             if (gr < p.M && cb + ci * 32 < ce && gcol < p.N) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + gr * p.res_stride + gcol);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) resid[sub][ci][q] = __ldg(rp + q);
+              load_row64(p.residual + gr * p.res_stride + gcol, resid[sub][ci], p.wide_io);
             }
           }
         }
@@ -770,9 +802,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
 #pragma unroll
         for (int ci = 0; ci < kChunks; ++ci) {
           if (c_begin + ci * 32 < c_end) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + nt * BN + c_begin + ci * 32);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) resid[ci][q] = __ldg(rp + q);
+            load_row64(p.residual + grow * p.res_stride + nt * BN + c_begin + ci * 32, resid[ci], p.wide_io);
           }
         }
       }
@@ -1020,10 +1050,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
         for (int sub = 0; sub < MSUB; ++sub)
 #pragma unroll
           for (int ci = 0; ci < kChunks; ++ci) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (grow0 + static_cast<long>(sub) * p.img_w) * p.res_stride +
-                                                             nt * BN + c_begin + ci * 32);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) resid[sub][ci][q] = __ldg(rp + q);
+            load_row64(p.residual + (grow0 + static_cast<long>(sub) * p.img_w) * p.res_stride + nt * BN + c_begin + ci * 32,
+                       resid[sub][ci], p.wide_io);
           }
       }
       mbar_wait(&tfull_bar[as], (local >> 1) & 1);
@@ -1215,6 +1243,11 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   kp.out = static_cast<__half*>(p->out);
   kp.out_stride = p->out_row_stride;
   kp.act = p->act;
+  // 256-bit epilogue accesses whenever every row the epilogue touches starts on a 32-byte boundary (bit-identical
+  // results; +14 % on the 128-channel VAE layers, tools/wide_bench.py)
+  if (p->wide_io != 1 && (reinterpret_cast<uintptr_t>(p->out) & 31) == 0 && p->out_row_stride % 16 == 0 &&
+      (!p->residual || ((reinterpret_cast<uintptr_t>(p->residual) & 31) == 0 && p->res_row_stride % 16 == 0)))
+    kp.wide_io = 1;
   // GroupNorm pass A on the outputs (optional): whole groups per 32-column chunk, whole 32-row slabs per image
   const bool fast_epilogue = p->c_out % 32 == 0 && (p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0);
   if (p->gn_partial) {

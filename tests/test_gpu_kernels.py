@@ -233,6 +233,28 @@ def test_conv_emits_groupnorm_pass_a(L, kind, B, H, W, Ci, Co, kw):
     assert rel_l2(pm[..., 1], m2) <= 1e-3
 
 
+@pytest.mark.parametrize("kind,B,H,Ci,Co", [("conv", 2, 128, 128, 128), ("conv", 1, 128, 256, 256), ("conv", 4, 64, 320, 320),
+                                           ("conv", 2, 32, 640, 640), ("lin", 1, 4096, 320, 320), ("lin", 1, 1000, 512, 512)])
+def test_epilogue_256bit_io_is_bit_identical(L, kind, B, H, Ci, Co):
+    """256-bit residual loads / output stores (auto when rows are 32-byte aligned) against the 128-bit path, and a
+    misaligned output view (column offset of 8 channels) that has to fall back."""
+    g = _gen(35)
+    ks = 3 if kind == "conv" else 1
+    M = B * H * H if kind == "conv" else H
+    a = torch.randn(M, Ci, device="cuda", generator=g).half()
+    w = (torch.randn(Co, ks * ks * Ci, device="cuda", generator=g) / math.sqrt(ks * ks * Ci)).half()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    r = torch.randn(M, Co, device="cuda", generator=g).half()
+    args = dict(batch=B, h_in=H, w_in=H, c_in=Ci, ksize=3, bias=bias, residual=r) if kind == "conv" else \
+        dict(batch=1, h_in=1, w_in=M, c_in=Ci, bias=bias, residual=r)
+    wide, narrow = L.conv_gemm(a, w, wide_io=0, **args), L.conv_gemm(a, w, wide_io=1, **args)
+    assert torch.equal(wide, narrow)
+    buf = torch.zeros(M, Co + 16, device="cuda", dtype=torch.float16)
+    view = buf[:, 8:8 + Co]                                # rows start 16 bytes off a 32-byte boundary
+    L.conv_gemm(a, w, out=view, **args)
+    assert torch.equal(view, narrow) and float(buf[:, :8].abs().max()) == 0 and float(buf[:, 8 + Co:].abs().max()) == 0
+
+
 def test_conv_rejects_bad_shapes(L):
     a = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
     w = torch.zeros(64, 60, device="cuda", dtype=torch.float16)
