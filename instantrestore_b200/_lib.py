@@ -173,8 +173,29 @@ def _run(op: str, tag: str, flops: float, nbytes: float, fn, *args) -> None:
     tr.records.append((op, tag, flops, nbytes, e0, e1))
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    """Raw handle of torch's current stream on `device` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """Makes the device of tensor `t` current for the duration of a C-ABI call: the library launches on the current
+    device (tensor maps, function attributes and the architecture check are per device), so a pipeline built with
+    device='cuda:1' must not launch against device 0's context."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, t: torch.Tensor):
+        self.idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
 
 
 def ptr(t: torch.Tensor | None) -> int | None:
@@ -253,10 +274,11 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
         act=act, out=ptr(out), out_row_stride=out.stride(-2), tile_n=tile_n, split_k=split_k,
         pad_hi_only=int(pad_hi_only), no_persistent=int(no_persistent), m_sub=m_sub, cta_pair=cta_pair, halo=halo, gn_partial=ptr(gn_partial), gn_groups=gn_groups, wide_io=wide_io or _NARROW_IO)
     k_tot = ksize * ksize * c_in
-    _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks{ksize}s{stride}", 2.0 * m * k_tot * c_out,
-         2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out
-                + (m * n_out if residual is not None else 0)),
-         load().ir_conv_gemm, C.byref(p), stream_ptr())
+    with on_device(a):
+        _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks{ksize}s{stride}", 2.0 * m * k_tot * c_out,
+             2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out
+                    + (m * n_out if residual is not None else 0)),
+             load().ir_conv_gemm, C.byref(p), stream_ptr(a.device))
     return out
 
 
@@ -297,8 +319,9 @@ def shared_attn(q: torch.Tensor, *, heads: int, scale: float, batch: int, s_q: i
         _h(k_ref, "k_ref"); _h(v_ref, "v_ref")
         assert k_ref.stride(-2) == v_ref.stride(-2)
     s_kv = (s_own if k_own is not None else 0) + n_ref * s_ref
-    _run("ir_shared_attn_fwd", f"b{batch}_h{heads}_sq{s_q}_skv{s_kv}", 4.0 * batch * heads * s_q * s_kv * 64,
-         2.0 * batch * heads * 64 * (2 * s_q + 2 * s_kv), load().ir_shared_attn_fwd, C.byref(p), stream_ptr())
+    with on_device(q):
+        _run("ir_shared_attn_fwd", f"b{batch}_h{heads}_sq{s_q}_skv{s_kv}", 4.0 * batch * heads * s_q * s_kv * 64,
+             2.0 * batch * heads * 64 * (2 * s_q + 2 * s_kv), load().ir_shared_attn_fwd, C.byref(p), stream_ptr(q.device))
     return (out, mass) if chunk_mass else out
 
 
@@ -326,8 +349,9 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch
     p = GroupNormParams(x=ptr(x), x_row_stride=x.stride(-2), batch=batch, hw=hw, channels=channels, groups=groups,
                         eps=eps, gamma=ptr(gamma), beta=ptr(beta), silu=int(silu), out=ptr(out),
                         out_row_stride=out.stride(-2), workspace=ptr(workspace), partial_in=ptr(partial_in))
-    _run("ir_groupnorm", f"b{batch}_hw{hw}_c{channels}", 0.0, 4.0 * batch * hw * channels, load().ir_groupnorm,
-         C.byref(p), stream_ptr())
+    with on_device(x):
+        _run("ir_groupnorm", f"b{batch}_hw{hw}_c{channels}", 0.0, 4.0 * batch * hw * channels, load().ir_groupnorm,
+             C.byref(p), stream_ptr(x.device))
     return out
 
 
@@ -339,8 +363,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
         out = torch.empty((rows, channels), dtype=torch.float16, device=x.device)
     p = LayerNormParams(x=ptr(x), x_row_stride=x.stride(-2), rows=rows, channels=channels, eps=eps, gamma=ptr(gamma),
                         beta=ptr(beta), out=ptr(out), out_row_stride=out.stride(-2))
-    _run("ir_layernorm", f"r{rows}_c{channels}", 0.0, 4.0 * rows * channels, load().ir_layernorm, C.byref(p),
-         stream_ptr())
+    with on_device(x):
+        _run("ir_layernorm", f"r{rows}_c{channels}", 0.0, 4.0 * rows * channels, load().ir_layernorm, C.byref(p),
+             stream_ptr(x.device))
     return out
 
 
@@ -361,8 +386,9 @@ def adain_coeffs(v_own: torch.Tensor, v_ref: torch.Tensor, *, batch: int, s_own:
                           v_ref=ptr(v_ref), ref_row_stride=v_ref.stride(-2), ref_col_off=ref_col_off, n_ref=n_ref,
                           s_ref=s_ref, batch=batch, channels=channels, eps=eps, scale=ptr(scale), shift=ptr(shift),
                           workspace=ptr(workspace))
-    _run("ir_adain_coeffs", f"b{batch}_n{n_ref}_s{s_ref}_c{channels}", 0.0,
-         2.0 * batch * channels * (s_own + n_ref * s_ref), load().ir_adain_coeffs, C.byref(p), stream_ptr())
+    with on_device(v_own):
+        _run("ir_adain_coeffs", f"b{batch}_n{n_ref}_s{s_ref}_c{channels}", 0.0,
+             2.0 * batch * channels * (s_own + n_ref * s_ref), load().ir_adain_coeffs, C.byref(p), stream_ptr(v_own.device))
     return scale, shift
 
 
@@ -375,8 +401,9 @@ def concat_freeu(hidden: torch.Tensor, skip: torch.Tensor, *, batch: int, h: int
         out = torch.empty((batch * h * w, ch + cs), dtype=torch.float16, device=hidden.device)
     p = ConcatFreeuParams(hidden=ptr(hidden), skip=ptr(skip), batch=batch, h=h, w=w, c_hidden=ch, c_skip=cs,
                           backbone_scale=backbone_scale, skip_scale=skip_scale, out=ptr(out))
-    _run("ir_concat_freeu", f"b{batch}_hw{h * w}_c{ch}+{cs}", 0.0, 4.0 * batch * h * w * (ch + cs),
-         load().ir_concat_freeu, C.byref(p), stream_ptr())
+    with on_device(hidden):
+        _run("ir_concat_freeu", f"b{batch}_hw{h * w}_c{ch}+{cs}", 0.0, 4.0 * batch * h * w * (ch + cs),
+             load().ir_concat_freeu, C.byref(p), stream_ptr(hidden.device))
     return out
 
 
@@ -386,8 +413,9 @@ def upsample_nearest2x(x: torch.Tensor, *, batch: int, h: int, w: int, out: torc
     c = x.shape[-1]
     if out is None:
         out = torch.empty((batch * 4 * h * w, c), dtype=torch.float16, device=x.device)
-    _run("ir_upsample_nearest2x", f"b{batch}_hw{h * w}_c{c}", 0.0, 10.0 * batch * h * w * c,
-         load().ir_upsample_nearest2x, ptr(x), ptr(out), batch, h, w, c, stream_ptr())
+    with on_device(x):
+        _run("ir_upsample_nearest2x", f"b{batch}_hw{h * w}_c{c}", 0.0, 10.0 * batch * h * w * c,
+             load().ir_upsample_nearest2x, ptr(x), ptr(out), batch, h, w, c, stream_ptr(x.device))
     return out
 
 
@@ -398,7 +426,8 @@ def latent_in(x: torch.Tensor, noise: torch.Tensor | None, a: float, s: float, *
     b, c, hh, ww = x.shape
     if out is None:
         out = torch.empty((b * hh * ww, c_pad), dtype=torch.float16, device=x.device)
-    check(load().ir_latent_in(ptr(x), ptr(noise), a, s, ptr(out), b, c, hh * ww, c_pad, stream_ptr()), "ir_latent_in")
+    with on_device(x):
+        check(load().ir_latent_in(ptr(x), ptr(noise), a, s, ptr(out), b, c, hh * ww, c_pad, stream_ptr(x.device)), "ir_latent_in")
     return out
 
 
@@ -409,8 +438,9 @@ def latent_out(eps: torch.Tensor, x: torch.Tensor, noise: torch.Tensor | None, a
     b, c, hh, ww = x.shape
     if out is None:
         out = torch.empty_like(x)
-    check(load().ir_latent_out(ptr(eps), eps.stride(-2), ptr(x), ptr(noise), a, s, ptr(out), b, c, hh * ww,
-                               stream_ptr()), "ir_latent_out")
+    with on_device(eps):
+        check(load().ir_latent_out(ptr(eps), eps.stride(-2), ptr(x), ptr(noise), a, s, ptr(out), b, c, hh * ww,
+                                   stream_ptr(eps.device)), "ir_latent_out")
     return out
 
 
@@ -418,8 +448,9 @@ def softmax_rows(x: torch.Tensor, scale: float) -> torch.Tensor:
     """In-place softmax(x * scale) over the last dim of an fp16 [rows, cols] matrix (fp32 math)."""
     _h(x, "x")
     rows, cols = x.shape
-    _run("ir_softmax_rows", f"r{rows}_c{cols}", 0.0, 4.0 * rows * cols, load().ir_softmax_rows, ptr(x), rows, cols,
-         x.stride(0), scale, stream_ptr())
+    with on_device(x):
+        _run("ir_softmax_rows", f"r{rows}_c{cols}", 0.0, 4.0 * rows * cols, load().ir_softmax_rows, ptr(x), rows, cols,
+             x.stride(0), scale, stream_ptr(x.device))
     return x
 
 
@@ -430,8 +461,9 @@ def image_in(x: torch.Tensor, *, c_pad: int = 64, out: torch.Tensor | None = Non
     b, c, hh, ww = x.shape
     if out is None:
         out = torch.empty((b * hh * ww, c_pad), dtype=torch.float16, device=x.device)
-    _run("ir_image_in", f"b{b}_hw{hh * ww}", 0.0, b * hh * ww * (c * x.element_size() + 2.0 * c_pad), load().ir_image_in,
-         ptr(x), int(x.dtype == torch.float32), ptr(out), b, c, hh * ww, c_pad, stream_ptr())
+    with on_device(x):
+        _run("ir_image_in", f"b{b}_hw{hh * ww}", 0.0, b * hh * ww * (c * x.element_size() + 2.0 * c_pad), load().ir_image_in,
+             ptr(x), int(x.dtype == torch.float32), ptr(out), b, c, hh * ww, c_pad, stream_ptr(x.device))
     return out
 
 
@@ -441,8 +473,9 @@ def image_out(y: torch.Tensor, *, batch: int, c: int, h: int, w: int, lo: float 
     _h(y, "y")
     if out is None:
         out = torch.empty((batch, c, h, w), dtype=dtype, device=y.device)
-    _run("ir_image_out", f"b{batch}_hw{h * w}", 0.0, batch * h * w * c * (2.0 + out.element_size()), load().ir_image_out,
-         ptr(y), y.stride(-2), lo, hi, ptr(out), int(out.dtype == torch.float32), batch, c, h * w, stream_ptr())
+    with on_device(y):
+        _run("ir_image_out", f"b{batch}_hw{h * w}", 0.0, batch * h * w * c * (2.0 + out.element_size()), load().ir_image_out,
+             ptr(y), y.stride(-2), lo, hi, ptr(out), int(out.dtype == torch.float32), batch, c, h * w, stream_ptr(y.device))
     return out
 
 
@@ -452,6 +485,7 @@ def vae_sample(moments: torch.Tensor, eps: torch.Tensor | None, scale: float, *,
     _h(moments, "moments"); _f(eps, "eps")
     if out is None:
         out = torch.empty((batch, c, h, w), dtype=torch.float32, device=moments.device)
-    check(load().ir_vae_sample(ptr(moments), moments.stride(-2), ptr(eps), scale, ptr(out), batch, c, h * w, stream_ptr()),
-          "ir_vae_sample")
+    with on_device(moments):
+        check(load().ir_vae_sample(ptr(moments), moments.stride(-2), ptr(eps), scale, ptr(out), batch, c, h * w, stream_ptr(moments.device)),
+              "ir_vae_sample")
     return out

@@ -49,27 +49,84 @@ def adain(content_features: torch.Tensor, style_mean: torch.Tensor, style_std: t
     return (content_features.float() * scale + (style_mean.float() - c_mean * scale)).to(content_features.dtype)
 
 
+def _effective_weight(mod):
+    """Weight a projection module actually applies, fp32, plus the parameters it was built from.
+
+    In the reference's main UNet every to_q/to_k/to_v/to_out.0 is a peft LoRA layer (pix2pix_turbo.py:171-179) whose
+    `.weight` property returns only `base_layer.weight`; the module computes base(x) + scaling * B(A(x)), so the weight
+    to run is W + sum_adapters scaling * B @ A (adapters already merged into the base, or disabled, contribute nothing)."""
+    base = getattr(mod, "base_layer", None)
+    if base is None:
+        return mod.weight.detach().float(), [mod.weight]
+    params = [base.weight]
+    w = base.weight.detach().float()
+    lora_a, lora_b = getattr(mod, "lora_A", None), getattr(mod, "lora_B", None)
+    if lora_a is None or lora_b is None:
+        raise NotImplementedError(f"{type(mod).__name__}: adapter wrapper without lora_A / lora_B is not supported")
+    if getattr(mod, "merged", False) or getattr(mod, "disable_adapters", False):
+        return w, params
+    names = getattr(mod, "active_adapters", None)
+    if callable(names):
+        names = names()
+    if not names:
+        one = getattr(mod, "adapter", None)
+        names = [one] if one is not None else list(lora_a.keys())
+    if isinstance(names, str):
+        names = [names]
+    for name in names:
+        if name not in lora_a:
+            continue
+        a, b = lora_a[name].weight, lora_b[name].weight
+        scaling = mod.scaling[name] if isinstance(mod.scaling, dict) else mod.scaling
+        w = w + float(scaling) * (b.detach().float().flatten(1) @ a.detach().float().flatten(1))
+        params += [a, b]
+    return w, params
+
+
+def _module_bias(mod):
+    b = getattr(getattr(mod, "base_layer", mod), "bias", None)
+    return b
+
+
 class _ProjCache:
     """fp16 copies of an Attention module's projection weights (the reference keeps fp32 parameters and lets
-    autocast cast them on every call, test.py:82-83); rebuilt when a parameter is replaced or modified in place."""
+    autocast cast them on every call, test.py:82-83), LoRA deltas merged; rebuilt when any parameter they were built
+    from (base weight, LoRA A / B, bias) is replaced or modified in place."""
 
     def __init__(self):
         self.key = None
         self.w = {}
 
+    @staticmethod
+    def _sources(attn):
+        mods = {"q": attn.to_q, "k": attn.to_k, "v": attn.to_v, "o": attn.to_out[0]}
+        params = []
+        for m in mods.values():
+            base = getattr(m, "base_layer", m)
+            params.append(base.weight)
+            if getattr(base, "bias", None) is not None:
+                params.append(base.bias)
+            for d in (getattr(m, "lora_A", None), getattr(m, "lora_B", None)):
+                if d is not None:
+                    params += [l.weight for l in d.values()]
+            params.append(bool(getattr(m, "merged", False)))
+        return mods, params
+
     def get(self, attn, self_attention: bool):
-        params = [attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_out[0].weight]
-        key = tuple((p.data_ptr(), p._version) for p in params) + (self_attention,)
+        mods, params = self._sources(attn)
+        key = tuple((p.data_ptr(), p._version) if isinstance(p, torch.Tensor) else p for p in params) + (self_attention,)
         if key != self.key:
-            h = lambda t: t.detach().to(torch.float16).contiguous()
-            w = {"q": h(attn.to_q.weight), "k": h(attn.to_k.weight), "v": h(attn.to_v.weight), "o": h(attn.to_out[0].weight)}
+            h = lambda t: t.to(torch.float16).contiguous()
+            w = {name: h(_effective_weight(m)[0]) for name, m in mods.items()}
+            for name in ("q", "k", "v", "o"):
+                b = _module_bias(mods[name])
+                w[name + "b"] = None if b is None else b.detach().float().contiguous()
             if self_attention:
                 w["qkv"] = torch.cat([w["q"], w["k"], w["v"]], 0).contiguous()
-            ob = attn.to_out[0].bias
-            w["ob"] = None if ob is None else ob.detach().float().contiguous()
-            for name in ("q", "k", "v"):
-                b = getattr(attn, f"to_{name}").bias
-                w[name + "b"] = None if b is None else b.detach().float().contiguous()
+                w["qkvb"] = None
+                if any(w[n + "b"] is not None for n in ("q", "k", "v")):      # a bias on any of the three projections
+                    zeros = lambda n: torch.zeros(w[n].shape[0], dtype=torch.float32, device=w[n].device)
+                    w["qkvb"] = torch.cat([w[n + "b"] if w[n + "b"] is not None else zeros(n) for n in ("q", "k", "v")]).contiguous()
             self.w, self.key = w, key
         return self.w
 
@@ -81,7 +138,7 @@ def _check(attn, hidden_states, attention_mask):
         raise NotImplementedError("attention masks are never passed on the reference hot path")
     if getattr(attn, "spatial_norm", None) is not None or getattr(attn, "group_norm", None) is not None or getattr(attn, "norm_cross", None):
         raise NotImplementedError("spatial_norm / group_norm / norm_cross are None for the SD-Turbo UNet")
-    if attn.to_q.weight.shape[0] != attn.heads * 64:
+    if getattr(attn.to_q, "base_layer", attn.to_q).weight.shape[0] != attn.heads * 64:
         raise NotImplementedError("the B200 attention kernel is specialised for head_dim 64")
 
 
@@ -126,7 +183,7 @@ class AttnProcessor(nn.Module):
         self.is_self_attn = encoder_hidden_states is None
         w = self._cache.get(attn, self.is_self_attn)
         if self.is_self_attn:
-            qkv = _project(x, w["qkv"], None)
+            qkv = _project(x, w["qkv"], w["qkvb"])
             inner = w["q"].shape[0]
             q, k, v, s_kv = qkv, qkv[:, inner:2 * inner], qkv[:, 2 * inner:], s
         else:
@@ -164,9 +221,12 @@ class FaceIDAttnProcessor(nn.Module):
         x, b, s, c, shape4 = _as_tokens(hidden_states)
         self.is_self_attn = encoder_hidden_states is None
         w = self._cache.get(attn, False)
-        ctx = (hidden_states if self.is_self_attn else encoder_hidden_states).to(torch.float16)
-        s_kv = ctx.shape[1]
-        ctx = ctx.reshape(-1, ctx.shape[-1]).contiguous()
+        if self.is_self_attn:        # reference :150-151: the (tokenised) hidden states are their own context
+            ctx, s_kv = x, s
+        else:
+            ctx = encoder_hidden_states.to(torch.float16)
+            s_kv = ctx.shape[1]
+            ctx = ctx.reshape(-1, ctx.shape[-1]).contiguous()
         h = lambda t: t.detach().to(torch.float16).contiguous()
         f = lambda t: None if t is None else t.detach().float().contiguous()
         q = _project(x, w["q"], w["qb"])
@@ -199,7 +259,7 @@ class SharedAttnProcessor(nn.Module):
         w = self._cache.get(attn, is_self)
         inner = w["q"].shape[0]
         if is_self:
-            qkv = _project(x, w["qkv"], None)
+            qkv = _project(x, w["qkv"], w["qkvb"])
             q, k, v, s_kv = qkv, qkv[:, inner:2 * inner], qkv[:, 2 * inner:], s
         else:
             ctx = encoder_hidden_states.to(torch.float16)

@@ -645,7 +645,8 @@ extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t st
     kp.part_ml = reinterpret_cast<float2*>(kp.part_o + units * 128 * kD);
   }
 
-  static bool attr_done = false;
+  static PerDeviceOnce attr_once;   // function attributes are per device
+  bool& attr_done = attr_once.slot();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(shared_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(shared_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);

@@ -849,7 +849,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
 template <int BN, int STAGES, bool RESID>
 static int launch_pair_r(const GemmKParams& kp, cudaStream_t stream) {
   constexpr int smem = STAGES * (kABytes + (BN / 2) * kBK * 2) + 1024 + 256;
-  static bool attr_done = false;  // benign race: idempotent
+  static PerDeviceOnce attr_once;   // function attributes are per device
+  bool& attr_done = attr_once.slot();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<BN, STAGES, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm_pair): %s", cudaGetErrorString(e));
@@ -1091,7 +1092,8 @@ static int launch_halo_r(const GemmKParams& kp, cudaStream_t stream) {
   constexpr int msub = PAIR ? 1 : 2;
   constexpr int halo_slot = ((msub + 2) * kHaloW * 128 + 1023) / 1024 * 1024;
   constexpr int smem = 2 * halo_slot + (PAIR ? 7 : 5) * 128 * kBK * 2 + 1024 + 256;
-  static bool attr_done = false;  // benign race: idempotent
+  static PerDeviceOnce attr_once;   // function attributes are per device
+  bool& attr_done = attr_once.slot();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel<BN, PAIR, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv3_halo<%d>): %s", BN, cudaGetErrorString(e));
@@ -1130,7 +1132,8 @@ static int launch_halo(const GemmKParams& kp, bool pair, cudaStream_t stream) {
 template <int BN, int STAGES, int MSUB, bool RESID>
 static int launch_persistent_r(const GemmKParams& kp, cudaStream_t stream) {
   constexpr int smem = STAGES * (MSUB * kABytes + BN * kBK * 2) + 1024 + 256;
-  static bool attr_done = false;  // benign race: idempotent
+  static PerDeviceOnce attr_once;   // function attributes are per device
+  bool& attr_done = attr_once.slot();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, STAGES, MSUB, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm_persistent<%d,%d>): %s", BN, MSUB, cudaGetErrorString(e));
@@ -1153,7 +1156,8 @@ static int launch_persistent(const GemmKParams& kp, cudaStream_t stream) {
 template <int BN, int STAGES>
 static int launch(const GemmKParams& kp, int m_tiles, cudaStream_t stream) {
   constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 1024 + 256;
-  static bool attr_done = false;  // benign race: idempotent
+  static PerDeviceOnce attr_once;   // function attributes are per device
+  bool& attr_done = attr_once.slot();
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm<%d>): %s", BN, cudaGetErrorString(e));

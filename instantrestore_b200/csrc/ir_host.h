@@ -27,6 +27,16 @@ int launch_gn_partial(const void* x, int row_stride, int batch, int hw, int chan
 // Counts kernel launches issued (or captured into a CUDA graph) through the C ABI; read by ir_launch_count().
 void count_launch();
 
+// cudaFuncSetAttribute state is per device: one flag per device ordinal (benign race: setting it twice is idempotent).
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool& slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return done[d & 63];
+  }
+};
+
 #define IR_CUDA_LAUNCH_CHECK(what)                                                      \
   do {                                                                                  \
     ir::count_launch();                                                                 \

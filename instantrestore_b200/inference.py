@@ -29,17 +29,12 @@ PROMPT = "A high-quality photo of a person; professional, 8k"       # pix2pix_tu
 MODEL_NAME = "stabilityai/sd-turbo"                                    # pix2pix_turbo.py:17
 
 
-def decode_cfg(cfg: Any) -> SimpleNamespace:
-    """Minimal stand-in for pyrallis.decode(TrainConfig, ckpt['cfg']) (test.py:43): nested dict -> attribute access,
-    with the ModelConfig / DataConfig defaults the inference path reads (configs/train_config.py:111,118-147)."""
-    cfg = dict(cfg or {})
-    model = dict(net_type="pix2pix_turbo", lora_rank_unet=16, lora_rank_vae=16, condition_on_face_embeds=False,
-                 use_shared_attention=True, noise_timestep=249, use_shortcuts=False, train_reference_networks=False,
-                 use_adain=False, train_input=True)
-    model.update(cfg.get("model", {}) or {})
-    data = dict(max_conditioning_images=4)
-    data.update({k: v for k, v in (cfg.get("data", {}) or {}).items() if k in data})
-    return SimpleNamespace(model=SimpleNamespace(**model), data=SimpleNamespace(**data), raw=cfg)
+def decode_cfg(cfg: Any):
+    """`pyrallis.decode(TrainConfig, ckpt['cfg'])` of the reference (test.py:43) without pyrallis: nested mapping ->
+    face_replace.configs.train_config.TrainConfig (typed `model` / `data` sections with the reference defaults,
+    configs/train_config.py:94-147; training-only sections kept loosely)."""
+    from face_replace.configs.train_config import TrainConfig, decode
+    return decode(TrainConfig, cfg)
 
 
 def split_state_dict(sd: dict) -> dict:
@@ -97,6 +92,58 @@ def _caption_from_text_encoder(text_encoder_sd: dict, device) -> Optional[torch.
         return None
 
 
+class FaceReplaceModel:
+    """`face_replace.models.face_replace_model.FaceReplaceModel` of the reference (:8-45) for inference: holds the
+    configuration and, once `load_state_dict` has seen the checkpoint, `.net` — the B200 RestorePipeline standing in
+    for `Pix2Pix_Turbo` (same forward signature, `noise_timesteps`, `unet.attn_processors`). Geometry (UNet / VAE
+    widths) is read from the checkpoint, so the released SD-Turbo checkpoints and reduced test models load alike."""
+
+    def __init__(self, cfg, full_cfg=None, evaluating: bool = False, device="cuda:0", use_cuda_graph: bool = True,
+                 caption_enc: Optional[torch.Tensor] = None):
+        self.cfg, self.full_cfg = cfg, full_cfg
+        if cfg.net_type != "pix2pix_turbo":
+            raise ValueError(f"Invalid encoder type: {cfg.net_type}")
+        self.device = torch.device(device)
+        self.use_cuda_graph = use_cuda_graph
+        self.caption_enc = caption_enc
+        self.net: Optional[RestorePipeline] = None
+
+    def load_state_dict(self, state_dict: dict, strict: bool = True, caption_enc: Optional[torch.Tensor] = None):
+        from .unet_engine import UNetSpec
+        from .weights import infer_unet_geometry, infer_vae_channels
+        parts = split_state_dict(state_dict)
+        need = ("unet", "original_unet", "vae", "original_vae") if self.cfg.use_shared_attention else ("unet", "vae")
+        missing = [f"net.{n}.*" for n in need if n not in parts]
+        if missing and strict:
+            raise KeyError(f"checkpoint has no {', '.join(missing)} weights")
+        cap = caption_enc if caption_enc is not None else self.caption_enc
+        if cap is None and "text_encoder" in parts:
+            cap = _caption_from_text_encoder(parts["text_encoder"], self.device)
+        if cap is None:
+            raise RuntimeError("caption_enc is not in the checkpoint and the sd-turbo tokenizer/text-encoder config are "
+                               "not available locally: pass caption_enc=<(1,77,1024) tensor>")
+        m = self.cfg
+        flags = ModelFlags(use_shared_attention=m.use_shared_attention, use_adain=m.use_adain, train_input=m.train_input,
+                           condition_on_face_embeds=m.condition_on_face_embeds, lora_rank_unet=m.lora_rank_unet)
+        spec = UNetSpec(**infer_unet_geometry(parts["unet"]))
+        self.net = RestorePipeline(parts["unet"], parts.get("original_unet"), parts["vae"], parts.get("original_vae"), cap,
+                                   flags, spec=spec, vae_block_out_channels=infer_vae_channels(parts["vae"]),
+                                   use_shortcuts=m.use_shortcuts, device=self.device, noise_timestep=m.noise_timestep,
+                                   use_cuda_graph=self.use_cuda_graph)
+        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+    def eval(self):
+        return self
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def forward(self, *args, **kwargs):
+        return self.net.forward(*args, **kwargs)
+
+    __call__ = forward
+
+
 class Predictor:
     logging.basicConfig(level=logging.INFO)
 
@@ -104,30 +151,21 @@ class Predictor:
                  use_cuda_graph: bool = True):
         ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
         self.cfg = decode_cfg(ckpt.get("cfg"))
-        m = self.cfg.model
-        if m.net_type != "pix2pix_turbo":
-            raise ValueError(f"Invalid encoder type: {m.net_type}")
-        parts = split_state_dict(ckpt["state_dict"])
-        for need in ("unet", "original_unet", "vae", "original_vae"):
-            if need not in parts:
-                raise KeyError(f"checkpoint has no net.{need}.* weights")
         if caption_enc is None:
             caption_enc = ckpt.get("caption_enc")
-        if caption_enc is None and "text_encoder" in parts:
-            caption_enc = _caption_from_text_encoder(parts["text_encoder"], device)
-        if caption_enc is None:
-            raise RuntimeError("caption_enc is not in the checkpoint and the sd-turbo tokenizer/text-encoder config are "
-                               "not available locally: pass Predictor(..., caption_enc=<(1,77,1024) tensor>)")
-        flags = ModelFlags(use_shared_attention=m.use_shared_attention, use_adain=m.use_adain, train_input=m.train_input,
-                           condition_on_face_embeds=m.condition_on_face_embeds, lora_rank_unet=m.lora_rank_unet)
-        self.max_conditioning_images = self.cfg.data.max_conditioning_images
-        self.dtype = torch.float16
         self.device = torch.device(device)
+        self.face_replace_model = FaceReplaceModel(cfg=self.cfg.model, full_cfg=self.cfg, device=device,
+                                                   use_cuda_graph=use_cuda_graph, caption_enc=caption_enc)
         logging.info("Moving model to GPU")
-        self.net = RestorePipeline(parts["unet"], parts["original_unet"], parts["vae"], parts["original_vae"], caption_enc,
-                                   flags, use_shortcuts=m.use_shortcuts, device=device, noise_timestep=249,
-                                   use_cuda_graph=use_cuda_graph)
-        self.net.noise_timesteps = [249]                                # test.py:62
+        self.face_replace_model.load_state_dict(ckpt["state_dict"], strict=True)   # '.module.' stripped like test.py:49
+        self.face_replace_model.eval()
+        self.max_conditioning_images = self.cfg.data.max_conditioning_images
+        self.face_replace_model.net.noise_timesteps = [249]             # test.py:62
+        self.dtype = torch.float16
+
+    @property
+    def net(self) -> RestorePipeline:
+        return self.face_replace_model.net
 
     def _apply_transforms_on_image_list(self, images: List[Image.Image]) -> List[torch.Tensor]:
         return [image_to_tensor(im) for im in images]

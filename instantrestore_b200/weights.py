@@ -87,3 +87,51 @@ def geglu_interleave_index(n_total: int) -> torch.Tensor:
     for blk in range(half // 64):
         idx += list(range(blk * 64, blk * 64 + 64)) + list(range(half + blk * 64, half + blk * 64 + 64))
     return torch.tensor(idx, dtype=torch.long)
+
+
+def _leaf_shape(sd: Dict[str, torch.Tensor], mod: str):
+    t = sd.get(f"{mod}.weight")
+    if t is None:
+        t = sd.get(f"{mod}.base_layer.weight")
+    return None if t is None else tuple(t.shape)
+
+
+def infer_unet_geometry(sd: Dict[str, torch.Tensor]) -> dict:
+    """block_out_channels / head counts / cross_attention_dim of a UNet state_dict in the reference layout (the
+    released checkpoints are SD-Turbo: 320/640/1280/1280, head_dim 64, 1024-wide captions). head_dim is 64 in every
+    supported model, so heads = channels // 64."""
+    boc = []
+    i = 0
+    while True:
+        s = _leaf_shape(sd, f"down_blocks.{i}.resnets.0.conv1")
+        if s is None:
+            break
+        boc.append(int(s[0]))
+        i += 1
+    if not boc:
+        raise KeyError("not a UNet state_dict: down_blocks.0.resnets.0.conv1 is missing")
+    cross = None
+    for i in range(len(boc)):
+        s = _leaf_shape(sd, f"down_blocks.{i}.attentions.0.transformer_blocks.0.attn2.to_k")
+        if s is not None:
+            cross = int(s[1])
+            break
+    down_attn = tuple(_leaf_shape(sd, f"down_blocks.{i}.attentions.0.proj_in") is not None for i in range(len(boc)))
+    up_attn = tuple(_leaf_shape(sd, f"up_blocks.{i}.attentions.0.proj_in") is not None for i in range(len(boc)))
+    return dict(block_out_channels=tuple(boc), attention_head_dim=tuple(max(1, c // 64) for c in boc),
+                cross_attention_dim=cross if cross is not None else 1024, down_has_attn=down_attn, up_has_attn=up_attn)
+
+
+def infer_vae_channels(sd: Dict[str, torch.Tensor]):
+    """encoder block_out_channels of an AutoencoderKL state_dict (sd-vae-ft-mse: 128/256/512/512)."""
+    out = []
+    i = 0
+    while True:
+        s = _leaf_shape(sd, f"encoder.down_blocks.{i}.resnets.0.conv1")
+        if s is None:
+            break
+        out.append(int(s[0]))
+        i += 1
+    if not out:
+        raise KeyError("not a VAE state_dict: encoder.down_blocks.0.resnets.0.conv1 is missing")
+    return tuple(out)

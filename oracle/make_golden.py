@@ -40,30 +40,79 @@ UNET_CASES = [  # name, batch, n_ref, use_adain, train_input, lora_rank, valid
 ]
 
 
+# Full-width cases of the BENCHMARKED configurations (BASELINE.json configs[1..4]); generated with --full-only / default.
+# The shared-attention layer at SD-Turbo widths: (heads, S) = (20, 256), (10, 1024), (5, 4096), N_ref in {1, 2, 8}
+# (N_ref = 4 is inside the full pipeline cases). Output rows are subsampled (every `row_step`-th token) to keep the
+# fixtures small; inputs are rebuilt from the seed.
+ATTN_FULL_CASES = [  # name, heads, S, n_ref, use_adain, train_input, zeroed_slots, row_step
+    (f"attn_full_s{s}_n{n}", h, s, n, True, False, (2 if n == 8 else 0), max(1, s // 64))
+    for (h, s) in [(20, 256), (10, 1024), (5, 4096)] for n in (1, 2, 8)
+] + [("attn_full_s4096_n4_own", 5, 4096, 4, True, True, 0, 64)]
+FULL_LATENT_CASES = [  # name, batch, n_ref, use_adain, train_input, lora_rank, valid
+    ("unet_full_final_n1", 1, 1, True, False, 4, None),
+    ("unet_full_final_n2", 1, 2, True, False, 4, None),
+    ("unet_full_final_n8", 1, 8, True, False, 4, None),
+    ("unet_full_final_b8_n4", 8, 4, True, False, 4, [4, 4, 3, 4, 1, 4, 4, 2]),
+]
+# whole image pipeline at the benchmarked geometry: 512 x 512 images, SD-Turbo + sd-vae-ft-mse widths
+IMAGE_FULL_CASES = [  # name, batch, n_ref, use_adain, train_input, lora_rank_unet, lora_rank_vae, use_shortcuts
+    ("image_full_final_n4", 1, 4, True, False, 4, 4, False),
+]
+
+
+def full_image_models(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, reference_forwards, RefUNet=None, ref_ap=None):
+    """Full-geometry models (SD-Turbo UNet widths, sd-vae-ft-mse VAE widths) for the 512 x 512 image cases."""
+    from oracle import synth
+    from oracle.pipeline import ImageRestorePipeline, LatentRestorePipeline
+    from oracle.unet import UNetConfig
+    from oracle.vae import VaeConfig
+    ucfg = UNetConfig()
+    vcfg = VaeConfig(use_shortcuts=use_shortcuts)
+    flags = synth.ModelFlags(use_adain=use_adain, train_input=train_input)
+    if RefUNet is not None:
+        latent = build_pipeline(RefUNet, ref_ap, ucfg, flags, lora_unet)
+    else:
+        latent = LatentRestorePipeline(synth.make_unet(ucfg, seed=0, lora_rank=lora_unet), synth.make_unet(ucfg, seed=0),
+                                       synth.caption_embedding(ucfg.cross_attention_dim), flags)
+    vae = synth.make_vae(vcfg, seed=100, lora_rank=lora_vae)
+    ovae = synth.make_vae(VaeConfig(), seed=100)
+    if reference_forwards:
+        bind_reference_vae_forwards(vae)
+        bind_reference_vae_forwards(ovae)
+        ovae.decoder.ignore_skip = True
+    return ImageRestorePipeline(latent, vae, ovae)
+
+
 def import_reference():
     if not REFERENCE.exists():
         raise RuntimeError("/root/reference is not mounted: golden vectors can only be regenerated in the build container")
+    # this repo ships a `face_replace` package of its own (the drop-in import paths): make sure the REFERENCE's is the one
+    # imported here — its directory goes first on sys.path and any already-imported copy is dropped
+    for mod in [m for m in sys.modules if m == "face_replace" or m.startswith("face_replace.")]:
+        del sys.modules[mod]
     sys.path.insert(0, str(ROOT / "oracle" / "shim"))
     sys.path.insert(0, str(REFERENCE))
     from face_replace.models import attn_processors as ref_ap
+    if not str(Path(ref_ap.__file__).resolve()).startswith(str(REFERENCE)):
+        raise RuntimeError(f"expected the reference's attn_processors, imported {ref_ap.__file__}")
     from face_replace.models.unet_2d_condition import block as ref_block
     from face_replace.models.unet_2d_condition.unet import UNet2DConditionModel as RefUNet
     return ref_ap, ref_block, RefUNet
 
 
-def attn_inputs(heads, s, n_ref, zeroed, seed=7):
+def attn_inputs(heads, s, n_ref, zeroed, seed=7, batch=2):
     """Inputs of one processor call: hidden states, an Attention module, reference keys/values (B, N, S, C)."""
     from oracle.diffusers024 import Attention
     from oracle.synth import seeded_init_
     g = torch.Generator().manual_seed(seed)
     c = heads * 64
     attn = seeded_init_(Attention(query_dim=c, heads=heads, dim_head=64), seed).eval().requires_grad_(False)
-    hidden = torch.randn(2, s, c, generator=g)
-    rk = torch.randn(2, max(n_ref, 1), s, c, generator=g)
-    rv = torch.randn(2, max(n_ref, 1), s, c, generator=g) * 1.5 + 0.25
+    hidden = torch.randn(batch, s, c, generator=g)
+    rk = torch.randn(batch, max(n_ref, 1), s, c, generator=g)
+    rv = torch.randn(batch, max(n_ref, 1), s, c, generator=g) * 1.5 + 0.25
     if zeroed:
-        rk[1, -zeroed:] = 0
-        rv[1, -zeroed:] = 0
+        rk[-1, -zeroed:] = 0
+        rv[-1, -zeroed:] = 0
     return attn, hidden, rk, rv
 
 
@@ -152,76 +201,81 @@ def tiny_image_models(use_adain, train_input, lora_unet, lora_vae, use_shortcuts
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-full", action="store_true")
+    ap.add_argument("--full-only", action="store_true", help="only the full-width cases (sections 4-7)")
+    ap.add_argument("--only", default="", help="comma-separated case names (full-width sections only)")
     args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    want = lambda name: not only or name in only
     ref_ap, ref_block, RefUNet = import_reference()
     from oracle import synth
     from oracle.unet import UNetConfig
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.manual_seed(0)
 
-    # 1) the operator: SharedAttnProcessor.forward / AttnProcessor.forward of the reference
-    for name, heads, s, n_ref, use_adain, train_input, zeroed in ATTN_CASES:
-        attn, hidden, rk, rv = attn_inputs(heads, s, n_ref, zeroed)
-        proc = ref_ap.SharedAttnProcessor(self_attn_idx=0 if n_ref else None, save_self_attentions=True,
-                                          use_adain=use_adain, train_input=train_input)
+    if not (args.full_only or only):
+        # 1) the operator: SharedAttnProcessor.forward / AttnProcessor.forward of the reference
+        for name, heads, s, n_ref, use_adain, train_input, zeroed in ATTN_CASES:
+            attn, hidden, rk, rv = attn_inputs(heads, s, n_ref, zeroed)
+            proc = ref_ap.SharedAttnProcessor(self_attn_idx=0 if n_ref else None, save_self_attentions=True,
+                                              use_adain=use_adain, train_input=train_input)
+            with torch.no_grad():
+                out = proc(attn, hidden, ref_keys=[rk] if n_ref else None, ref_values=[rv] if n_ref else None)
+            mass = proc.attention_probs.sum(dim=2)  # (B, H, S_k): column mass, used for the per-chunk read-out
+            np.savez_compressed(GOLDEN / f"{name}.npz", out=out.numpy(), probs_colsum=mass.numpy(),
+                                meta=np.array([heads, s, n_ref, int(use_adain), int(train_input), zeroed]))
+            print(name, tuple(out.shape), float(out.abs().max()))
+        # the KV-capturing processor of the reference-image UNet
+        attn, hidden, _, _ = attn_inputs(2, 64, 0, 0)
+        cap_proc = ref_ap.AttnProcessor()
         with torch.no_grad():
-            out = proc(attn, hidden, ref_keys=[rk] if n_ref else None, ref_values=[rv] if n_ref else None)
-        mass = proc.attention_probs.sum(dim=2)  # (B, H, S_k): column mass, used for the per-chunk read-out
-        np.savez_compressed(GOLDEN / f"{name}.npz", out=out.numpy(), probs_colsum=mass.numpy(),
-                            meta=np.array([heads, s, n_ref, int(use_adain), int(train_input), zeroed]))
-        print(name, tuple(out.shape), float(out.abs().max()))
-    # the KV-capturing processor of the reference-image UNet
-    attn, hidden, _, _ = attn_inputs(2, 64, 0, 0)
-    cap_proc = ref_ap.AttnProcessor()
-    with torch.no_grad():
-        out = cap_proc(attn, hidden)
-    np.savez_compressed(GOLDEN / "attn_kv_capture.npz", out=out.numpy(), keys=cap_proc.keys.numpy(), values=cap_proc.values.numpy())
+            out = cap_proc(attn, hidden)
+        np.savez_compressed(GOLDEN / "attn_kv_capture.npz", out=out.numpy(), keys=cap_proc.keys.numpy(), values=cap_proc.values.numpy())
 
-    # the face-embedding cross-attention processor (reference attn_processors.py:100-180)
-    out, _ = faceid_case(ref_ap.FaceIDAttnProcessor)
-    np.savez_compressed(GOLDEN / "attn_faceid.npz", out=out.numpy())
+        # the face-embedding cross-attention processor (reference attn_processors.py:100-180)
+        out, _ = faceid_case(ref_ap.FaceIDAttnProcessor)
+        np.savez_compressed(GOLDEN / "attn_faceid.npz", out=out.numpy())
 
-    # 2) FreeU (reference block.py:3495-3520 on top of the restated fourier_filter)
-    g = torch.Generator().manual_seed(11)
-    for idx, (h, c) in enumerate([(8, 64), (16, 32)]):
-        hs = torch.randn(2, c, h, h, generator=g)
-        res = torch.randn(2, c, h, h, generator=g)
-        hs2, res2 = ref_block.apply_freeu(idx, hs.clone(), res.clone(), s1=0.9, s2=0.2, b1=1.4, b2=1.6)
-        np.savez_compressed(GOLDEN / f"freeu_stage{idx}.npz", hidden=hs2.numpy(), skip=res2.numpy())
+        # 2) FreeU (reference block.py:3495-3520 on top of the restated fourier_filter)
+        g = torch.Generator().manual_seed(11)
+        for idx, (h, c) in enumerate([(8, 64), (16, 32)]):
+            hs = torch.randn(2, c, h, h, generator=g)
+            res = torch.randn(2, c, h, h, generator=g)
+            hs2, res2 = ref_block.apply_freeu(idx, hs.clone(), res.clone(), s1=0.9, s2=0.2, b1=1.4, b2=1.6)
+            np.savez_compressed(GOLDEN / f"freeu_stage{idx}.npz", hidden=hs2.numpy(), skip=res2.numpy())
 
-    # 3) whole pipeline at the latent boundary on the reduced-width UNet
-    tiny = UNetConfig.tiny()
-    for name, batch, n_ref, use_adain, train_input, lora_rank, valid in UNET_CASES:
-        flags = synth.ModelFlags(use_adain=use_adain, train_input=train_input)
-        pipe = build_pipeline(RefUNet, ref_ap, tiny, flags, lora_rank)
-        enc, refs, nm, nr = synth.latents(batch, n_ref, tiny.sample_size)
-        out = pipe.forward_latents(enc, refs, nm, nr, valid_indices=valid)
-        np.savez_compressed(GOLDEN / f"{name}.npz", x0=out.numpy(),
-                            meta=np.array([batch, n_ref, int(use_adain), int(train_input), lora_rank]),
-                            valid=np.array(valid if valid is not None else [n_ref] * batch))
-        print(name, tuple(out.shape), float(out.std()))
+        # 3) whole pipeline at the latent boundary on the reduced-width UNet
+        tiny = UNetConfig.tiny()
+        for name, batch, n_ref, use_adain, train_input, lora_rank, valid in UNET_CASES:
+            flags = synth.ModelFlags(use_adain=use_adain, train_input=train_input)
+            pipe = build_pipeline(RefUNet, ref_ap, tiny, flags, lora_rank)
+            enc, refs, nm, nr = synth.latents(batch, n_ref, tiny.sample_size)
+            out = pipe.forward_latents(enc, refs, nm, nr, valid_indices=valid)
+            np.savez_compressed(GOLDEN / f"{name}.npz", x0=out.numpy(),
+                                meta=np.array([batch, n_ref, int(use_adain), int(train_input), lora_rank]),
+                                valid=np.array(valid if valid is not None else [n_ref] * batch))
+            print(name, tuple(out.shape), float(out.std()))
 
-    # 3b) VAE alone through the reference's own patched forwards (models/model.py:15-63), and the whole image pipeline
-    from oracle.vae import VaeConfig
-    for name, use_shortcuts, lora_rank in VAE_CASES:
-        vcfg = VaeConfig.tiny()
-        vcfg.use_shortcuts = use_shortcuts
-        vae = bind_reference_vae_forwards(synth.make_vae(vcfg, seed=100, lora_rank=lora_rank))
-        c_t, _, eps_main, _, _, _ = synth.images(2, 1, IMAGE_SIZE, IMAGE_LATENT)
-        with torch.no_grad():
-            z = vae.encode_sample(c_t, eps_main) * vcfg.scaling_factor
-            vae.decoder.incoming_skip_acts = vae.encoder.current_down_blocks
-            y = vae.decode(z / vcfg.scaling_factor).clamp(-1, 1)
-        np.savez_compressed(GOLDEN / f"{name}.npz", latent=z.numpy(), image=y.numpy().astype(np.float16))
-        print(name, tuple(z.shape), float(z.std()), tuple(y.shape), float(y.std()))
-    for name, batch, n_ref, use_adain, train_input, lora_unet, lora_vae, use_shortcuts in IMAGE_CASES:
-        pipe = tiny_image_models(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, True, RefUNet, ref_ap)
-        out = pipe.forward(*synth.images(batch, n_ref, IMAGE_SIZE, IMAGE_LATENT))
-        np.savez_compressed(GOLDEN / f"{name}.npz", image=out.numpy().astype(np.float16))
-        print(name, tuple(out.shape), float(out.std()))
+        # 3b) VAE alone through the reference's own patched forwards (models/model.py:15-63), and the whole image pipeline
+        from oracle.vae import VaeConfig
+        for name, use_shortcuts, lora_rank in VAE_CASES:
+            vcfg = VaeConfig.tiny()
+            vcfg.use_shortcuts = use_shortcuts
+            vae = bind_reference_vae_forwards(synth.make_vae(vcfg, seed=100, lora_rank=lora_rank))
+            c_t, _, eps_main, _, _, _ = synth.images(2, 1, IMAGE_SIZE, IMAGE_LATENT)
+            with torch.no_grad():
+                z = vae.encode_sample(c_t, eps_main) * vcfg.scaling_factor
+                vae.decoder.incoming_skip_acts = vae.encoder.current_down_blocks
+                y = vae.decode(z / vcfg.scaling_factor).clamp(-1, 1)
+            np.savez_compressed(GOLDEN / f"{name}.npz", latent=z.numpy(), image=y.numpy().astype(np.float16))
+            print(name, tuple(z.shape), float(z.std()), tuple(y.shape), float(y.std()))
+        for name, batch, n_ref, use_adain, train_input, lora_unet, lora_vae, use_shortcuts in IMAGE_CASES:
+            pipe = tiny_image_models(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, True, RefUNet, ref_ap)
+            out = pipe.forward(*synth.images(batch, n_ref, IMAGE_SIZE, IMAGE_LATENT))
+            np.savez_compressed(GOLDEN / f"{name}.npz", image=out.numpy().astype(np.float16))
+            print(name, tuple(out.shape), float(out.std()))
 
     # 4) full-width SD-Turbo geometry, released "final model" flags (AdaIN on, refs-only KV), B=1, N=4
-    if not args.no_full:
+    if not args.no_full and want("unet_full_final_n4"):
         full = UNetConfig()
         flags = synth.ModelFlags(use_adain=True, train_input=False)
         pipe = build_pipeline(RefUNet, ref_ap, full, flags, lora_rank=0)
@@ -229,6 +283,45 @@ def main():
         out = pipe.forward_latents(enc, refs, nm, nr)
         np.savez_compressed(GOLDEN / "unet_full_final_n4.npz", x0=out.numpy(), meta=np.array([1, 4, 1, 0, 0]))
         print("unet_full_final_n4", tuple(out.shape), float(out.std()))
+    if args.no_full:
+        return
+
+    # 5) the shared-attention operator at SD-Turbo widths, reference-count sweep (BASELINE configs[4])
+    for name, heads, s, n_ref, use_adain, train_input, zeroed, row_step in ATTN_FULL_CASES:
+        if not want(name):
+            continue
+        attn, hidden, rk, rv = attn_inputs(heads, s, n_ref, zeroed, batch=1)
+        proc = ref_ap.SharedAttnProcessor(self_attn_idx=0, save_self_attentions=False, use_adain=use_adain, train_input=train_input)
+        with torch.no_grad():
+            out = proc(attn, hidden, ref_keys=[rk], ref_values=[rv])
+        np.savez_compressed(GOLDEN / f"{name}.npz", out_rows=out[:, ::row_step].numpy(),
+                            meta=np.array([heads, s, n_ref, int(use_adain), int(train_input), zeroed, row_step]))
+        print(name, tuple(out.shape), float(out.abs().max()), flush=True)
+
+    # 6) latent pipeline at full width: N_ref sweep and the B = 8 batch of BASELINE configs[2] (ragged valid counts)
+    full = UNetConfig()
+    for name, batch, n_ref, use_adain, train_input, lora_rank, valid in FULL_LATENT_CASES:
+        if not want(name):
+            continue
+        flags = synth.ModelFlags(use_adain=use_adain, train_input=train_input)
+        pipe = build_pipeline(RefUNet, ref_ap, full, flags, lora_rank)
+        enc, refs, nm, nr = synth.latents(batch, n_ref, full.sample_size)
+        out = pipe.forward_latents(enc, refs, nm, nr, valid_indices=valid)
+        np.savez_compressed(GOLDEN / f"{name}.npz", x0=out.numpy(),
+                            meta=np.array([batch, n_ref, int(use_adain), int(train_input), lora_rank]),
+                            valid=np.array(valid if valid is not None else [n_ref] * batch))
+        print(name, tuple(out.shape), float(out.std()), flush=True)
+        del pipe
+
+    # 7) the BENCHMARKED workload: 512 x 512 images, full UNet + VAE widths, B = 1, N_ref = 4, AdaIN, refs-only KV
+    for name, batch, n_ref, use_adain, train_input, lora_unet, lora_vae, use_shortcuts in IMAGE_FULL_CASES:
+        if not want(name):
+            continue
+        pipe = full_image_models(use_adain, train_input, lora_unet, lora_vae, use_shortcuts, True, RefUNet, ref_ap)
+        ins = synth.images(batch, n_ref, 512, 64)
+        out = pipe.forward(*ins)
+        np.savez_compressed(GOLDEN / f"{name}.npz", image=out.numpy().astype(np.float16))
+        print(name, tuple(out.shape), float(out.std()), flush=True)
 
 
 if __name__ == "__main__":

@@ -37,3 +37,10 @@ def golden():
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def max_rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    """Element-wise figure next to rel_l2: max |a - b| / max |b| (the largest single-element deviation in units of the
+    reference's dynamic range)."""
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

@@ -7,7 +7,7 @@ import torch
 
 from oracle import attn_processors as oap
 from oracle import synth
-from oracle.make_golden import ATTN_CASES, UNET_CASES, attn_inputs
+from oracle.make_golden import ATTN_CASES, ATTN_FULL_CASES, UNET_CASES, attn_inputs
 from oracle.pipeline import LatentRestorePipeline
 from oracle.unet import UNetConfig, apply_freeu
 
@@ -30,6 +30,19 @@ def test_shared_attn_processor_matches_reference(case, golden):
     g = golden(name)
     _close(out, g["out"])
     _close(proc.attention_probs.sum(dim=2), g["probs_colsum"])
+
+
+@pytest.mark.parametrize("case", ATTN_FULL_CASES, ids=[c[0] for c in ATTN_FULL_CASES])
+def test_shared_attn_processor_full_width_matches_reference(case, golden):
+    """SD-Turbo widths, reference counts 1 / 2 / 8 (zero-filled padded slots at N = 8) and the 1+4 own-chunk case."""
+    name, heads, s, n_ref, use_adain, train_input, zeroed, row_step = case
+    attn, hidden, rk, rv = attn_inputs(heads, s, n_ref, zeroed, batch=1)
+    proc = oap.SharedAttnProcessor(self_attn_idx=0, use_adain=use_adain, train_input=train_input)
+    with torch.no_grad():
+        out = proc(attn, hidden, ref_keys=[rk], ref_values=[rv])
+    g = golden(name)
+    assert list(g["meta"]) == [heads, s, n_ref, int(use_adain), int(train_input), zeroed, row_step]
+    _close(out[:, ::row_step], g["out_rows"])
 
 
 def test_kv_capture_processor_matches_reference(golden):
