@@ -19,7 +19,7 @@ IR_ACT_NONE, IR_ACT_GEGLU, IR_ACT_SILU = 0, 1, 2
 EXPORTED_SYMBOLS = [
     "ir_last_error_string", "ir_version", "ir_check_device", "ir_launch_count", "ir_conv_gemm", "ir_shared_attn_fwd",
     "ir_shared_attn_workspace_bytes",
-    "ir_groupnorm", "ir_groupnorm_workspace_bytes", "ir_layernorm", "ir_adain_coeffs", "ir_adain_workspace_bytes",
+    "ir_groupnorm", "ir_groupnorm_workspace_bytes", "ir_groupnorm_fused_supported", "ir_layernorm", "ir_adain_coeffs", "ir_adain_workspace_bytes",
     "ir_concat_freeu", "ir_upsample_nearest2x", "ir_latent_in", "ir_latent_out",
     "ir_softmax_rows", "ir_image_in", "ir_image_out", "ir_vae_sample",
 ]
@@ -56,6 +56,7 @@ class GroupNormParams(C.Structure):
         ("x", C.c_void_p), ("x_row_stride", C.c_int), ("batch", C.c_int), ("hw", C.c_int), ("channels", C.c_int),
         ("groups", C.c_int), ("eps", C.c_float), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("silu", C.c_int),
         ("out", C.c_void_p), ("out_row_stride", C.c_int), ("workspace", C.c_void_p), ("partial_in", C.c_void_p),
+        ("fused", C.c_int),
     ]
 
 
@@ -100,6 +101,7 @@ def load() -> C.CDLL:
     lib.ir_last_error_string.restype = C.c_char_p
     lib.ir_launch_count.restype = C.c_ulonglong
     lib.ir_groupnorm_workspace_bytes.restype = C.c_size_t
+    lib.ir_groupnorm_fused_supported.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     lib.ir_adain_workspace_bytes.restype = C.c_size_t
     lib.ir_shared_attn_workspace_bytes.restype = C.c_size_t
     lib.ir_conv_gemm.argtypes = [C.POINTER(ConvGemmParams), C.c_void_p]
@@ -136,11 +138,16 @@ def launch_count() -> int:
 class Trace:
     """Per-call device timing for the roofline report: while active, every C-ABI call is bracketed by CUDA events
     recorded on the launching stream, together with its algorithmic work (flops, bytes). Not usable under graph
-    capture; bench.py runs one eager instrumented step with it."""
+    capture; bench.py runs one eager instrumented step with it.
+
+    The eager event pairs include launch gaps, so the numbers bench.py reports come from `replay_table`: every distinct
+    (op, shape) of the step is re-issued `reps` times back to back inside a small CUDA graph (same arguments, same
+    buffers, which the trace keeps alive) and timed by replaying that graph — per-launch device time as the kernel
+    runs inside the step's own graph, without host launch latency."""
     active: "Trace | None" = None
 
     def __init__(self):
-        self.records = []   # (op, tag, flops, bytes, start_event, end_event)
+        self.records = []   # (op, tag, flops, bytes, start_event, end_event, fn, args_without_stream, keep, device)
 
     def __enter__(self):
         Trace.active = self
@@ -152,7 +159,7 @@ class Trace:
     def summary(self):
         torch.cuda.synchronize()
         rows = {}
-        for op, tag, flops, nbytes, e0, e1 in self.records:
+        for op, tag, flops, nbytes, e0, e1, *_ in self.records:
             r = rows.setdefault((op, tag), dict(op=op, shape=tag, calls=0, ms=0.0, flops=0.0, bytes=0.0))
             r["calls"] += 1
             r["ms"] += e0.elapsed_time(e1)
@@ -160,8 +167,46 @@ class Trace:
             r["bytes"] += nbytes
         return sorted(rows.values(), key=lambda r: -r["ms"])
 
+    def replay_table(self, reps: int = 8, iters: int = 3):
+        """Rows like summary(), with `us` = device time per launch from CUDA-graph replays of `reps` back-to-back
+        launches (best of `iters`), `ms` = us * calls."""
+        torch.cuda.synchronize()
+        rows, first = {}, {}
+        for rec in self.records:
+            op, tag, flops, nbytes = rec[:4]
+            r = rows.setdefault((op, tag), dict(op=op, shape=tag, calls=0, flops=0.0, bytes=0.0, ms_eager=0.0))
+            r["calls"] += 1
+            r["flops"] += flops
+            r["bytes"] += nbytes
+            r["ms_eager"] += rec[4].elapsed_time(rec[5])
+            first.setdefault((op, tag), rec)
+        for key, rec in first.items():
+            fn, args, _keep, dev = rec[6:10]
+            with on_device(torch.empty(0, device=dev)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    sp = torch.cuda.current_stream(dev).cuda_stream
+                    for _ in range(reps):
+                        check(fn(*args, sp), key[0])
+                g.replay()
+                torch.cuda.synchronize(dev)
+                best = float("inf")
+                for _ in range(iters):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    g.replay()
+                    e1.record()
+                    e1.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                del g
+            rows[key]["us"] = best * 1e3 / reps
+            rows[key]["ms"] = rows[key]["us"] * rows[key]["calls"] * 1e-3
+        return sorted(rows.values(), key=lambda r: -r["ms"])
 
-def _run(op: str, tag: str, flops: float, nbytes: float, fn, *args) -> None:
+
+def _run(op: str, tag: str, flops: float, nbytes: float, fn, *args, keep=()) -> None:
+    """args[-1] is the stream handle. `keep`: the tensors behind the raw pointers in `args` (kept alive by an active
+    Trace so the call can be re-issued by replay_table)."""
     tr = Trace.active
     if tr is None:
         check(fn(*args), op)
@@ -170,7 +215,8 @@ def _run(op: str, tag: str, flops: float, nbytes: float, fn, *args) -> None:
     e0.record()
     check(fn(*args), op)
     e1.record()
-    tr.records.append((op, tag, flops, nbytes, e0, e1))
+    dev = next((t.device for t in keep if isinstance(t, torch.Tensor)), torch.device("cuda", torch.cuda.current_device()))
+    tr.records.append((op, tag, flops, nbytes, e0, e1, fn, args[:-1], keep, dev))
 
 
 def stream_ptr(device=None) -> int:
@@ -278,7 +324,7 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
         _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks{ksize}s{stride}", 2.0 * m * k_tot * c_out,
              2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out
                     + (m * n_out if residual is not None else 0)),
-             load().ir_conv_gemm, C.byref(p), stream_ptr(a.device))
+             load().ir_conv_gemm, C.byref(p), stream_ptr(a.device), keep=(a, w, bias, residual, out, gn_partial))
     return out
 
 
@@ -320,8 +366,8 @@ def shared_attn(q: torch.Tensor, *, heads: int, scale: float, batch: int, s_q: i
         assert k_ref.stride(-2) == v_ref.stride(-2)
     s_kv = (s_own if k_own is not None else 0) + n_ref * s_ref
     with on_device(q):
-        _run("ir_shared_attn_fwd", f"b{batch}_h{heads}_sq{s_q}_skv{s_kv}", 4.0 * batch * heads * s_q * s_kv * 64,
-             2.0 * batch * heads * 64 * (2 * s_q + 2 * s_kv), load().ir_shared_attn_fwd, C.byref(p), stream_ptr(q.device))
+        _run("ir_shared_attn_fwd", f"b{batch}_h{heads}_sq{s_q}_skv{s_kv}" + ("_adain" if adain_scale is not None else ""), 4.0 * batch * heads * s_q * s_kv * 64,
+             2.0 * batch * heads * 64 * (2 * s_q + 2 * s_kv), load().ir_shared_attn_fwd, C.byref(p), stream_ptr(q.device), keep=(q, k_own, v_own, k_ref, v_ref, adain_scale, adain_shift, out, mass, p.workspace and ws))
     return (out, mass) if chunk_mass else out
 
 
@@ -335,23 +381,35 @@ def gn_partial_numel(batch: int, hw: int, groups: int = 32) -> int:
     return batch * (hw // 32) * groups * 2
 
 
+_GN_FUSED_MODE = {"0": 1, "2": 2}.get(os.environ.get("IR_GN_SINGLE_LAUNCH", "1"), 0)   # A-B switch: 0 -> three-kernel path
+
+
+def gn_fused_supported(batch: int, hw: int, channels: int, groups: int = 32) -> bool:
+    """True when ir_groupnorm runs as ONE launch with ONE read of x (cluster kernel); conv_gemm's gn_partial is then not
+    needed for this tensor."""
+    return _GN_FUSED_MODE != 1 and bool(load().ir_groupnorm_fused_supported(batch, hw, channels, groups))
+
+
 def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, batch: int, hw: int, groups: int = 32,
               eps: float = 1e-5, silu: bool = False, out: torch.Tensor | None = None,
-              workspace: torch.Tensor | None = None, partial_in: torch.Tensor | None = None) -> torch.Tensor:
-    """partial_in: the gn_partial tensor a conv_gemm call filled for exactly this x (pass A is then skipped)."""
+              workspace: torch.Tensor | None = None, partial_in: torch.Tensor | None = None, fused: int | None = None) -> torch.Tensor:
+    """partial_in: the gn_partial tensor a conv_gemm call filled for exactly this x (pass A is then skipped).
+    fused: None = library default (single-launch cluster kernel when supported), 1 = three-kernel path, 2 = require it."""
     _h(x, "x"); _f(gamma, "gamma"); _f(beta, "beta"); _f(partial_in, "partial_in")
     channels = x.shape[-1]
+    fused = _GN_FUSED_MODE if fused is None else fused
     if out is None:
         out = torch.empty((batch * hw, channels), dtype=torch.float16, device=x.device)
-    if workspace is None:
+    single = fused != 1 and bool(load().ir_groupnorm_fused_supported(batch, hw, channels, groups))
+    if workspace is None and not single:
         workspace = torch.empty(load().ir_groupnorm_workspace_bytes(batch, groups) // 4, dtype=torch.float32,
                                 device=x.device)
     p = GroupNormParams(x=ptr(x), x_row_stride=x.stride(-2), batch=batch, hw=hw, channels=channels, groups=groups,
                         eps=eps, gamma=ptr(gamma), beta=ptr(beta), silu=int(silu), out=ptr(out),
-                        out_row_stride=out.stride(-2), workspace=ptr(workspace), partial_in=ptr(partial_in))
+                        out_row_stride=out.stride(-2), workspace=ptr(workspace), partial_in=ptr(partial_in), fused=fused)
     with on_device(x):
-        _run("ir_groupnorm", f"b{batch}_hw{hw}_c{channels}", 0.0, 4.0 * batch * hw * channels, load().ir_groupnorm,
-             C.byref(p), stream_ptr(x.device))
+        _run("ir_groupnorm", f"b{batch}_hw{hw}_c{channels}" + ("_1launch" if single else ""), 0.0, 4.0 * batch * hw * channels, load().ir_groupnorm,
+             C.byref(p), stream_ptr(x.device), keep=(x, gamma, beta, out, workspace, partial_in))
     return out
 
 
@@ -365,7 +423,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
                         beta=ptr(beta), out=ptr(out), out_row_stride=out.stride(-2))
     with on_device(x):
         _run("ir_layernorm", f"r{rows}_c{channels}", 0.0, 4.0 * rows * channels, load().ir_layernorm, C.byref(p),
-             stream_ptr(x.device))
+             stream_ptr(x.device), keep=(x, gamma, beta, out))
     return out
 
 
@@ -388,7 +446,7 @@ def adain_coeffs(v_own: torch.Tensor, v_ref: torch.Tensor, *, batch: int, s_own:
                           workspace=ptr(workspace))
     with on_device(v_own):
         _run("ir_adain_coeffs", f"b{batch}_n{n_ref}_s{s_ref}_c{channels}", 0.0,
-             2.0 * batch * channels * (s_own + n_ref * s_ref), load().ir_adain_coeffs, C.byref(p), stream_ptr(v_own.device))
+             2.0 * batch * channels * (s_own + n_ref * s_ref), load().ir_adain_coeffs, C.byref(p), stream_ptr(v_own.device), keep=(v_own, v_ref, scale, shift, workspace))
     return scale, shift
 
 
@@ -403,7 +461,7 @@ def concat_freeu(hidden: torch.Tensor, skip: torch.Tensor, *, batch: int, h: int
                           backbone_scale=backbone_scale, skip_scale=skip_scale, out=ptr(out))
     with on_device(hidden):
         _run("ir_concat_freeu", f"b{batch}_hw{h * w}_c{ch}+{cs}", 0.0, 4.0 * batch * h * w * (ch + cs),
-             load().ir_concat_freeu, C.byref(p), stream_ptr(hidden.device))
+             load().ir_concat_freeu, C.byref(p), stream_ptr(hidden.device), keep=(hidden, skip, out))
     return out
 
 
@@ -415,7 +473,7 @@ def upsample_nearest2x(x: torch.Tensor, *, batch: int, h: int, w: int, out: torc
         out = torch.empty((batch * 4 * h * w, c), dtype=torch.float16, device=x.device)
     with on_device(x):
         _run("ir_upsample_nearest2x", f"b{batch}_hw{h * w}_c{c}", 0.0, 10.0 * batch * h * w * c,
-             load().ir_upsample_nearest2x, ptr(x), ptr(out), batch, h, w, c, stream_ptr(x.device))
+             load().ir_upsample_nearest2x, ptr(x), ptr(out), batch, h, w, c, stream_ptr(x.device), keep=(x, out))
     return out
 
 
@@ -450,7 +508,7 @@ def softmax_rows(x: torch.Tensor, scale: float) -> torch.Tensor:
     rows, cols = x.shape
     with on_device(x):
         _run("ir_softmax_rows", f"r{rows}_c{cols}", 0.0, 4.0 * rows * cols, load().ir_softmax_rows, ptr(x), rows, cols,
-             x.stride(0), scale, stream_ptr(x.device))
+             x.stride(0), scale, stream_ptr(x.device), keep=(x,))
     return x
 
 
@@ -463,7 +521,7 @@ def image_in(x: torch.Tensor, *, c_pad: int = 64, out: torch.Tensor | None = Non
         out = torch.empty((b * hh * ww, c_pad), dtype=torch.float16, device=x.device)
     with on_device(x):
         _run("ir_image_in", f"b{b}_hw{hh * ww}", 0.0, b * hh * ww * (c * x.element_size() + 2.0 * c_pad), load().ir_image_in,
-             ptr(x), int(x.dtype == torch.float32), ptr(out), b, c, hh * ww, c_pad, stream_ptr(x.device))
+             ptr(x), int(x.dtype == torch.float32), ptr(out), b, c, hh * ww, c_pad, stream_ptr(x.device), keep=(x, out))
     return out
 
 
@@ -475,7 +533,7 @@ def image_out(y: torch.Tensor, *, batch: int, c: int, h: int, w: int, lo: float 
         out = torch.empty((batch, c, h, w), dtype=dtype, device=y.device)
     with on_device(y):
         _run("ir_image_out", f"b{batch}_hw{h * w}", 0.0, batch * h * w * c * (2.0 + out.element_size()), load().ir_image_out,
-             ptr(y), y.stride(-2), lo, hi, ptr(out), int(out.dtype == torch.float32), batch, c, h * w, stream_ptr(y.device))
+             ptr(y), y.stride(-2), lo, hi, ptr(out), int(out.dtype == torch.float32), batch, c, h * w, stream_ptr(y.device), keep=(y, out))
     return out
 
 

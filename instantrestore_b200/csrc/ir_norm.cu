@@ -217,6 +217,147 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
   }
 }
 
+// ---- GroupNorm(+SiLU) in ONE launch with ONE read of the activation (every UNet norm and the VAE norms up to 128 x 128).
+// grid = (CL, slices, batch), thread-block cluster (CL, 1, 1). A CTA owns `rows` pixels x `slice_ch` channels of one
+// image (slice_ch = a multiple of lcm(8, channels per group): whole groups AND whole 16-byte vectors); its tile lives in
+// registers (<= KMAX 16-byte vectors per thread, every thread keeps one fixed channel vector so its per-channel sums and
+// later its 16 affine coefficients stay in registers). Per-CTA (mean, M2) of each group of the slice are exchanged
+// through distributed shared memory: after one cluster barrier every CTA merges the CL partials in rank order (Chan;
+// deterministic and identical in every CTA), applies a*x+b (+SiLU) to its registers and stores. The second cluster
+// barrier (no CTA may exit while a peer still reads its shared memory) is split: arrive right after the remote reads,
+// wait after the stores.
+__device__ __forceinline__ float2 dsmem_ld_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <int KMAX>
+__global__ void __launch_bounds__(256) gn_fused_kernel(const __half* __restrict__ x, int x_stride, int hw, int channels,
+                                                       int groups, int slice_ch, int rows, int cl, float eps,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int silu, __half* __restrict__ out, int out_stride) {
+  __shared__ float2 s_acc[256 * 8];      // [row group][slice channel] (sum, sumsq) of the thread-level partials
+  __shared__ float2 s_ch[256];           // stage A: [T][slice channel], T * slice_ch <= 256
+  __shared__ float2 s_part[64];          // this CTA's (mean, M2) per group of the slice (read by the cluster)
+  __shared__ float2 s_stat[64];          // merged (mean, rstd) per group of the slice
+  const int tid = threadIdx.x;
+  const int V = slice_ch >> 3;                    // 16-byte vectors per row of the slice
+  const int rgroups = 256 / V;                    // rows in flight per sweep
+  const int v = tid % V, rg = tid / V;
+  const bool active = rg < rgroups;
+  const int b = blockIdx.z, c_base = blockIdx.y * slice_ch;
+  const int r0 = blockIdx.x * rows;               // cluster rank == blockIdx.x (cluster spans the x dimension)
+  const int cpg = channels / groups;
+  const int gs = slice_ch / cpg;                  // groups in this slice
+  const __half* xb = x + (static_cast<size_t>(b) * hw + r0) * x_stride + c_base + (v << 3);
+
+  uint4 u[KMAX];
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int r = rg + k * rgroups;
+      if (r < rows) u[k] = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r) * x_stride);
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int r = rg + k * rgroups;
+      if (r < rows) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          s[2 * j] += f.x; q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+          s[2 * j + 1] += f.y; q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+        }
+      }
+    }
+    float2* dst = s_acc + rg * slice_ch + (v << 3);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_float2(s[j], q[j]);
+  }
+  __syncthreads();
+  // stage A: T threads per channel, each sums a strided subset of the row groups (fixed order)
+  const int T = 256 / slice_ch > 0 ? 256 / slice_ch : 1;
+  for (int i = tid; i < T * slice_ch; i += 256) {
+    const int ch = i % slice_ch, t = i / slice_ch;
+    float a = 0.f, c = 0.f;
+    for (int k = t; k < rgroups; k += T) {
+      const float2 e = s_acc[k * slice_ch + ch];
+      a += e.x; c += e.y;
+    }
+    s_ch[t * slice_ch + ch] = make_float2(a, c);
+  }
+  __syncthreads();
+  // stage B: one thread per group of the slice
+  const float n_cta = static_cast<float>(rows) * cpg;
+  if (tid < gs) {
+    float a = 0.f, c = 0.f;
+    for (int t = 0; t < T; ++t)
+      for (int ch = tid * cpg; ch < (tid + 1) * cpg; ++ch) {
+        const float2 e = s_ch[t * slice_ch + ch];
+        a += e.x; c += e.y;
+      }
+    const float mean = a / n_cta;
+    s_part[tid] = make_float2(mean, fmaxf(c - a * mean, 0.f));
+  }
+  if (cl > 1) {
+    cluster_arrive();
+    cluster_wait();
+  } else {
+    __syncthreads();
+  }
+  if (tid < gs) {
+    float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
+    const uint32_t local = smem_u32(&s_part[tid]);
+    for (int r = 0; r < cl; ++r) {
+      const float2 pm = cl > 1 ? dsmem_ld_f2(dsmem_addr(local, static_cast<uint32_t>(r))) : s_part[tid];
+      if (r == 0) { n_a = n_cta; mean_a = pm.x; m2_a = pm.y; }
+      else merge_moments(n_a, mean_a, m2_a, n_cta, pm.x, pm.y);
+    }
+    s_stat[tid] = make_float2(mean_a, rsqrtf(m2_a / n_a + eps));
+  }
+  if (cl > 1) cluster_arrive();      // my remote reads are done
+  __syncthreads();
+  if (active) {
+    const int c0 = c_base + (v << 3);
+    float ca[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 st = s_stat[((v << 3) + j) / cpg];
+      ca[j] = st.y * __ldg(gamma + c0 + j);
+      cb[j] = fmaf(-st.x, ca[j], __ldg(beta + c0 + j));
+    }
+    __half* ob = out + (static_cast<size_t>(b) * hw + r0) * out_stride + c0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int r = rg + k * rgroups;
+      if (r < rows) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(h2[j]);
+          f[2 * j] = fmaf(t.x, ca[2 * j], cb[2 * j]);
+          f[2 * j + 1] = fmaf(t.y, ca[2 * j + 1], cb[2 * j + 1]);
+        }
+        if (silu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + fast_exp2(-1.4426950408889634f * f[j]));
+        }
+        *reinterpret_cast<uint4*>(ob + static_cast<size_t>(r) * out_stride) =
+            make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
+      }
+    }
+  }
+  if (cl > 1) cluster_wait();
+}
+
 // ---- LayerNorm: one warp per row; the row (<= 2560 channels = 10 sixteen-byte vectors per lane) is read from
 // global memory once and stays in registers for the mean, the centred variance and the affine.
 template <int kMaxVec>
@@ -311,6 +452,61 @@ static void gn_plan(int batch, int hw, int* slabs, int* rows_per_slab) {
   *slabs = (hw + rps - 1) / rps;
 }
 
+// ---- plan of the single-launch GroupNorm: slice width, cluster size, rows per CTA, register tile depth
+struct GnFusedPlan { int slice_ch, cl, rows, kmax; };
+
+static int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+static bool gn_fused_plan(int batch, int hw, int channels, int groups, GnFusedPlan* pl) {
+  if (groups <= 0 || channels % groups || channels % 8) return false;
+  const int cpg = channels / groups;
+  const int wmin = cpg / gcd_i(cpg, 8) * 8;               // lcm(8, channels per group)
+  if (wmin > 256 || channels % wmin) return false;
+  int w = wmin;
+  while (w < 32 && channels % (2 * w) == 0) w *= 2;        // >= 64-byte row segments where the width allows
+  if (w / cpg > 64) return false;
+  const int rgroups = 256 / (w / 8);
+  // smallest power-of-two cluster (<= 8: portable) whose per-CTA tile fits 32 vectors per thread
+  auto depth = [&](int c) { return (hw / c + rgroups - 1) / rgroups; };
+  int cl = 1;
+  while (cl <= 8 && (hw % cl != 0 || depth(cl) > 32)) cl *= 2;
+  if (cl > 8) return false;
+  // prefer <= 16 vectors per thread; then more CTAs while the grid is small (latency-bound tensors) and every thread
+  // keeps >= 2 vectors
+  const long slices = channels / w;
+  while (cl < 8 && hw % (2 * cl) == 0 && depth(cl) > 16) cl *= 2;
+  while (cl < 8 && hw % (2 * cl) == 0 && slices * cl * batch < 296 && hw / (2 * cl) >= 2 * rgroups) cl *= 2;
+  const int rows = hw / cl;
+  const int k = (rows + rgroups - 1) / rgroups;
+  pl->slice_ch = w; pl->cl = cl; pl->rows = rows;
+  pl->kmax = k <= 4 ? 4 : k <= 8 ? 8 : k <= 16 ? 16 : 32;
+  return true;
+}
+
+extern "C" int ir_groupnorm_fused_supported(int batch, int hw, int channels, int groups) {
+  GnFusedPlan pl;
+  return batch > 0 && hw > 0 && gn_fused_plan(batch, hw, channels, groups, &pl) ? 1 : 0;
+}
+
+template <int KMAX>
+static cudaError_t launch_gn_fused(const ir_groupnorm_params* p, const GnFusedPlan& pl, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl.cl, p->channels / pl.slice_ch, p->batch);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pl.cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pl.cl > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, ir::gn_fused_kernel<KMAX>, static_cast<const __half*>(p->x), p->x_row_stride, p->hw,
+                            p->channels, p->groups, pl.slice_ch, pl.rows, pl.cl, p->eps, p->gamma, p->beta, p->silu,
+                            static_cast<__half*>(p->out), p->out_row_stride);
+}
+
 extern "C" size_t ir_groupnorm_workspace_bytes(int batch, int groups) {
   // per-(batch, slab, group) partial moments + per-(batch, group) mean / rstd
   return static_cast<size_t>(batch) * (kGnMaxSlabs + 1) * groups * sizeof(float2);
@@ -318,7 +514,7 @@ extern "C" size_t ir_groupnorm_workspace_bytes(int batch, int groups) {
 
 extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
   using namespace ir;
-  if (!p || !p->x || !p->out || !p->gamma || !p->beta || !p->workspace) return set_error(IR_ERR_ARG, "ir_groupnorm: NULL argument");
+  if (!p || !p->x || !p->out || !p->gamma || !p->beta) return set_error(IR_ERR_ARG, "ir_groupnorm: NULL argument");
   if (int rc = check_arch()) return rc;
   if (p->groups <= 0 || p->channels % p->groups != 0 || p->channels % 8 != 0 || p->channels > 4096)
     return set_error(IR_ERR_SHAPE, "ir_groupnorm: channels=%d groups=%d (need channels %% 8 == 0, channels %% groups == 0, channels <= 4096)", p->channels, p->groups);
@@ -326,6 +522,18 @@ extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
     return set_error(IR_ERR_ALIGN, "ir_groupnorm: pointers/strides must be 16-byte aligned");
   if (p->batch <= 0 || p->hw <= 0) return set_error(IR_ERR_SHAPE, "ir_groupnorm: non-positive dims");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GnFusedPlan pl;
+  const bool fused_ok = p->fused != 1 && gn_fused_plan(p->batch, p->hw, p->channels, p->groups, &pl);
+  if (p->fused == 2 && !fused_ok)
+    return set_error(IR_ERR_SHAPE, "ir_groupnorm: fused=2 but batch=%d hw=%d channels=%d groups=%d has no single-launch plan", p->batch, p->hw, p->channels, p->groups);
+  if (fused_ok) {
+    cudaError_t e = pl.kmax == 4 ? launch_gn_fused<4>(p, pl, stream) : pl.kmax == 8 ? launch_gn_fused<8>(p, pl, stream)
+                  : pl.kmax == 16 ? launch_gn_fused<16>(p, pl, stream) : launch_gn_fused<32>(p, pl, stream);
+    count_launch();
+    if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "gn_fused launch: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  if (!p->workspace) return set_error(IR_ERR_ARG, "ir_groupnorm: workspace is NULL (required when the single-launch path does not apply)");
   float2* partial = static_cast<float2*>(p->workspace);
   float2* stats = partial + static_cast<size_t>(p->batch) * kGnMaxSlabs * p->groups;
   int slabs, rps;

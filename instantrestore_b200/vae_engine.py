@@ -8,8 +8,9 @@ quant_conv (1x1) into encoder.conv_out; post_quant_conv (1x1) into decoder.conv_
 shift of the latent (W_pq^-1 b_pq) so the zero padding of conv_in stays exact; the value-projection bias of the
 mid-block attention moves behind the softmax (rows sum to 1) into the output projection's bias.
 
-Mid-block attention (head_dim 512): scores = Q K^T are materialised in fp16 by ir_conv_gemm exactly like the
-reference's baddbmm under autocast (diffusers Attention.get_attention_scores), softmax-ed in place in fp32
+Mid-block attention (head_dim 512): scores = (Q C^-1/2) K^T (the scale is folded into the Q projection at load, so
+the fp16 scores have the magnitude of the reference's baddbmm(alpha=scale) output under autocast, diffusers
+Attention.get_attention_scores) are materialised in fp16 by ir_conv_gemm, softmax-ed in place in fp32
 (ir_softmax_rows), and P V runs as a GEMM against V^T, which a GEMM with swapped operands produces directly.
 """
 from __future__ import annotations
@@ -121,7 +122,7 @@ class VaeEngine:
         return dict(
             res0=self._load_resnet(v.sub("resnets.0")), res1=self._load_resnet(v.sub("resnets.1")),
             norm=_Norm(a, "group_norm", dev),
-            q=_Lin(wq, bq, dev), k=_Lin(wk, bk, dev),
+            q=_Lin(wq * float(wq.shape[0]) ** -0.5, bq * float(wq.shape[0]) ** -0.5, dev), k=_Lin(wk, bk, dev),   # scale folded into Q
             v_t=wv.to(torch.float16).contiguous().to(dev),           # used as the A operand: V^T = W_v X^T
             out=_Lin(wo, bo + wo @ bv, dev),                            # value bias moved behind the softmax
             ch=wq.shape[0])
@@ -132,6 +133,8 @@ class VaeEngine:
     # statistics do not cover (tiny test geometries) return partial = None and take the three-kernel GroupNorm.
     def _partial(self, x, B, hw_out, c_out):
         if not FUSED_GN_STATS or not L.gn_partial_supported(hw_out, c_out, GROUPS):
+            return None
+        if L.gn_fused_supported(B, hw_out, c_out, GROUPS):    # the norm is ONE launch with one read: no pass A to move
             return None
         return torch.empty(L.gn_partial_numel(B, hw_out, GROUPS), dtype=torch.float32, device=x.device)
 
@@ -173,12 +176,11 @@ class VaeEngine:
         t = self._gn(x, p["norm"], B, S, False, xs)
         q_all, k_all = self._lin(t, p["q"]), self._lin(t, p["k"])           # [B*S, C] each
         attn = torch.empty((B * S, C), dtype=torch.float16, device=x.device)
-        scale = float(C) ** -0.5
         for b in range(B):
             rows = slice(b * S, (b + 1) * S)
             q, k, tb = q_all[rows], k_all[rows], t[rows]
-            scores = L.conv_gemm(q, k, batch=1, h_in=1, w_in=S, c_in=C)     # [S, S] = Q K^T (fp16, like baddbmm)
-            L.softmax_rows(scores, scale)
+            scores = L.conv_gemm(q, k, batch=1, h_in=1, w_in=S, c_in=C)     # [S, S] = (Q / sqrt(C)) K^T, fp16 like baddbmm(alpha)
+            L.softmax_rows(scores, 1.0)
             v_t = L.conv_gemm(p["v_t"], tb, batch=1, h_in=1, w_in=C, c_in=C)   # [C, S] = W_v X^T
             L.conv_gemm(scores, v_t, batch=1, h_in=1, w_in=S, c_in=S, out=attn[rows])
         x, xs = self._lin(attn, p["out"], residual=x, stats_bhw=(B, S))

@@ -16,6 +16,15 @@ import torch
 from torch import nn
 
 ADAIN_EPS = 1e-5
+# bench.py's `gpu_eager_baseline` only: the same processors with torch's fused scaled_dot_product_attention instead of
+# the reference's baddbmm + softmax + bmm (the reference never does this; it is the stronger eager-GPU bar of SURVEY 2b)
+USE_SDPA = False
+
+
+def _attend(attn, q, k, v):
+    if USE_SDPA:
+        return torch.nn.functional.scaled_dot_product_attention(q[None], k[None], v[None], scale=attn.scale)[0]
+    return torch.bmm(attn.get_attention_scores(q, k, None), v)
 
 
 def token_stats(x):
@@ -68,8 +77,7 @@ class AttnProcessor(nn.Module):
         k, v = attn.to_k(context), attn.to_v(context)
         self.keys, self.values = k, v
         q, k, v = (attn.head_to_batch_dim(t) for t in (q, k, v))
-        probs = attn.get_attention_scores(q, k, None)
-        return _epilogue(attn, torch.bmm(probs, v), residual, shape4)
+        return _epilogue(attn, _attend(attn, q, k, v), residual, shape4)
 
 
 class FaceIDAttnProcessor(nn.Module):
@@ -123,9 +131,10 @@ class SharedAttnProcessor(nn.Module):
                 rvs = [adain(x, style_mean, style_std) for x in rvs]
             own_k, own_v = ([k], [v]) if self.train_input else ([], [])
             k, v = torch.cat(own_k + rks, dim=1), torch.cat(own_v + rvs, dim=1)
+        if not self.save_self_attentions:
+            return _epilogue(attn, _attend(attn, q, k, v), residual, shape4)
         probs = attn.get_attention_scores(q, k, None)
-        if self.save_self_attentions:
-            self.attention_probs = probs.reshape(batch, attn.heads, q.shape[1], k.shape[1])
+        self.attention_probs = probs.reshape(batch, attn.heads, q.shape[1], k.shape[1])
         return _epilogue(attn, torch.bmm(probs, v), residual, shape4)
 
 

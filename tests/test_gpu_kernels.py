@@ -218,8 +218,8 @@ def test_conv_emits_groupnorm_pass_a(L, kind, B, H, W, Ci, Co, kw):
     y = L.conv_gemm(a, w, gn_partial=part, **args)
     assert torch.equal(y, L.conv_gemm(a, w, **args))              # the statistics do not disturb the outputs
     assert torch.isfinite(part).all()                              # every (image, slab, group) slot was written
-    fused = L.groupnorm(y, gamma, beta, batch=B, hw=hw, eps=1e-6, silu=True, partial_in=part)
-    plain = L.groupnorm(y, gamma, beta, batch=B, hw=hw, eps=1e-6, silu=True)
+    fused = L.groupnorm(y, gamma, beta, batch=B, hw=hw, eps=1e-6, silu=True, partial_in=part, fused=1)   # fused=1: three-kernel path
+    plain = L.groupnorm(y, gamma, beta, batch=B, hw=hw, eps=1e-6, silu=True, fused=1)
     assert rel_l2(fused, plain) <= 2e-4
     x = y.float().view(B, hw, Co).permute(0, 2, 1)
     ref = F.silu(F.group_norm(x, 32, gamma, beta, eps=1e-6)).permute(0, 2, 1).reshape(-1, Co)
@@ -371,6 +371,46 @@ def test_groupnorm(L, B, HW, C, silu):
         ref = F.silu(ref)
     out = L.groupnorm(x.reshape(-1, C), gm, bt, batch=B, hw=HW, silu=silu)
     assert rel_l2(out.reshape(B, HW, C), ref) <= TOL
+
+
+# every GroupNorm shape of the step that has a single-launch plan: UNet (B = 1 main pass, B = 4 reference pass; concat
+# widths 960 / 1920 / 2560 of the up blocks) and the VAE up to 128 x 128 (512 / 256 channels), plus odd sizes
+@pytest.mark.parametrize("B,HW,C,silu", [
+    (1, 4096, 320, True), (4, 4096, 320, True), (1, 4096, 640, True), (1, 4096, 960, True), (2, 1024, 640, False),
+    (1, 1024, 1280, True), (1, 1024, 1920, True), (4, 256, 1280, True), (1, 256, 2560, True), (1, 64, 1280, True),
+    (1, 64, 2560, True), (5, 4096, 512, True), (1, 16384, 512, True), (2, 16384, 256, True), (33, 4096, 320, True),
+    (3, 256, 64, False), (2, 48, 320, True), (1, 16, 128, True)])
+def test_groupnorm_single_launch(L, B, HW, C, silu):
+    """gn_fused_kernel (cluster + DSMEM merge, tile in registers) vs fp32 torch AND vs the three-kernel path; strided
+    input / output views; deterministic."""
+    assert L.gn_fused_supported(B, HW, C)
+    g = _gen(81)
+    xs = (torch.randn(B * HW, C + 64, device="cuda", generator=g) * 2 + 0.5).half()
+    x = xs[:, 32:32 + C]                                           # row stride C + 64, 64-byte column offset
+    gm, bt = torch.randn(C, device="cuda", generator=g), torch.randn(C, device="cuda", generator=g)
+    ref = F.group_norm(x.float().view(B, HW, C).transpose(1, 2), 32, gm, bt, 1e-5).transpose(1, 2)
+    if silu:
+        ref = F.silu(ref)
+    outs = torch.full((B * HW, C + 8), float("nan"), device="cuda", dtype=torch.float16)
+    out = L.groupnorm(x, gm, bt, batch=B, hw=HW, silu=silu, fused=2, out=outs[:, :C])
+    assert torch.isfinite(out).all()
+    assert rel_l2(out.reshape(B, HW, C), ref) <= TOL
+    three = L.groupnorm(x, gm, bt, batch=B, hw=HW, silu=silu, fused=1)
+    assert rel_l2(out, three) <= 3e-4                              # same math, different summation trees
+    again = L.groupnorm(x, gm, bt, batch=B, hw=HW, silu=silu, fused=2)
+    assert torch.equal(again, out.contiguous())
+    # in place (out aliases x) is allowed: every thread holds its tile in registers before it stores
+    xc = x.contiguous()
+    inplace = L.groupnorm(xc, gm, bt, batch=B, hw=HW, silu=silu, fused=2, out=xc)
+    assert torch.equal(inplace, out.contiguous())
+
+
+def test_groupnorm_large_tensors_keep_the_three_kernel_path(L):
+    assert not L.gn_fused_supported(1, 512 * 512, 128)
+    assert not L.gn_fused_supported(4, 256 * 256, 256)
+    with pytest.raises(RuntimeError):
+        x = torch.zeros(256 * 256, 256, device="cuda", dtype=torch.float16)
+        L.groupnorm(x, torch.ones(256, device="cuda"), torch.zeros(256, device="cuda"), batch=1, hw=256 * 256, fused=2)
 
 
 @pytest.mark.parametrize("R,C", [(4096, 320), (77, 1280), (1000, 64), (1, 640)])

@@ -15,11 +15,18 @@ tests)
 bench)
   nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > $OUT/${TAG}_clocks.csv 2>/dev/null &
   SMI=$!
-  timeout 1200 python bench.py --steps 20 --warmup 3 --trace-out $OUT/${TAG}_kernels.json > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
+  timeout 1200 python bench.py --steps 20 --warmup 5 --trace-out $OUT/${TAG}_kernels.json > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
   kill $SMI 2>/dev/null
-  cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
-  timeout 600 python bench.py --steps 10 --warmup 3 --batch 8 --no-cpu-baseline --trace-out $OUT/${TAG}_kernels_b8.json > $OUT/${TAG}_bench_b8.json 2> $OUT/${TAG}_bench_b8.err; echo "bench b8 rc=$?"
-  cat $OUT/${TAG}_bench_b8.json; tail -3 $OUT/${TAG}_bench_b8.err ;;
+  head -c 3000 $OUT/${TAG}_bench.json; echo; tail -3 $OUT/${TAG}_bench.err ;;
+bench8)
+  timeout 600 python bench.py --steps 10 --warmup 3 --batch 8 --no-cpu-baseline --no-extras --trace-out $OUT/${TAG}_kernels_b8.json > $OUT/${TAG}_bench_b8.json 2> $OUT/${TAG}_bench_b8.err; echo "bench b8 rc=$?"
+  head -c 1500 $OUT/${TAG}_bench_b8.json; echo; tail -3 $OUT/${TAG}_bench_b8.err ;;
+ab)
+  # same-box A/B of an environment switch: AB_ENV="IR_GN_SINGLE_LAUNCH=0" tools/gpu_round.sh <tag> ab
+  for B in 1 8; do for arm in "" "${AB_ENV:-IR_GN_SINGLE_LAUNCH=0}"; do
+    env $arm timeout 600 python bench.py --steps 20 --warmup 3 --batch $B --no-cpu-baseline --no-extras --no-trace > $OUT/${TAG}_ab_b${B}_${arm:-default}.json 2>> $OUT/${TAG}_ab.err
+    python -c "import json,sys; d=json.load(open('$OUT/${TAG}_ab_b${B}_${arm:-default}.json')); print('AB B=$B', '${arm:-default}', round(d['value'],2), 'images/s', round(d['ms_per_step'],3), 'ms', d['gpu_launches_per_step'], 'launches', d['clocks'])"
+  done; done ;;
 ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_launches.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
