@@ -170,8 +170,8 @@ typedef struct {
   const void* partial_in; /* optional: slab moments written by ir_conv_gemm (gn_partial) for exactly this x; pass A is skipped */
   int fused; /* 0 = auto: ONE launch with ONE read of x (thread-block cluster per (image, channel slice), tile in
                 registers, per-CTA moments merged through distributed shared memory) whenever
-                ir_groupnorm_fused_supported() — every UNet norm and the VAE norms up to 128 x 128 pixels; partial_in and
-                workspace are then unused. 1 = never (three-kernel path), 2 = require it (A-B measurement, tests) */
+                ir_groupnorm_fused_supported() — tensors up to 12 MB whose rows split into whole groups x whole 16-byte
+                vectors (the UNet norms of a single-identity step); partial_in and workspace are then unused. 1 = never (three-kernel path), 2 = require it (A-B measurement, tests) */
 } ir_groupnorm_params;
 size_t ir_groupnorm_workspace_bytes(int batch, int groups);
 int ir_groupnorm_fused_supported(int batch, int hw, int channels, int groups); /* 1 / 0 */

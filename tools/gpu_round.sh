@@ -27,6 +27,11 @@ ab)
     env $arm timeout 600 python bench.py --steps 20 --warmup 3 --batch $B --no-cpu-baseline --no-extras --no-trace > $OUT/${TAG}_ab_b${B}_${arm:-default}.json 2>> $OUT/${TAG}_ab.err
     python -c "import json,sys; d=json.load(open('$OUT/${TAG}_ab_b${B}_${arm:-default}.json')); print('AB B=$B', '${arm:-default}', round(d['value'],2), 'images/s', round(d['ms_per_step'],3), 'ms', d['gpu_launches_per_step'], 'launches', d['clocks'])"
   done; done ;;
+streams)
+  for S in 2 3 4 5 6; do
+    timeout 300 python bench.py --steps 30 --warmup 3 --streams $S --no-cpu-baseline --no-extras --no-trace > $OUT/${TAG}_streams_$S.json 2>> $OUT/${TAG}_streams.err
+    python -c "import json; d=json.load(open('$OUT/${TAG}_streams_$S.json')); print('STREAMS $S', round(d['value'],2), 'images/s e2e', round(d['e2e']['value'],2), d['clocks'])"
+  done ;;
 ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_launches.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"

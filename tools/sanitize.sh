@@ -1,0 +1,21 @@
+#!/bin/bash
+# compute-sanitizer over the kernel-level parity tests: memcheck on every kernel family at small
+# shapes, racecheck (shared-memory hazards) and synccheck on the kernels that synchronise through shared memory /
+# clusters without the async proxy (norms, AdaIN statistics, concat, layout kernels). Summaries -> gpurun_out/<tag>_san_*.txt
+# usage: tools/sanitize.sh <tag>
+TAG=${1:-r02}; OUT=gpurun_out; mkdir -p $OUT
+SAN=/usr/local/cuda/bin/compute-sanitizer
+SMALL='groupnorm or layernorm or adain or concat or upsample or latent_in or softmax'
+run() {  # name tool timeout pytest-args...
+  n=$1; tool=$2; to=$3; shift 3
+  timeout $to $SAN --tool $tool --print-limit 20 --error-exitcode 99 python -m pytest "$@" -q -x -m gpu -p no:cacheprovider > $OUT/${TAG}_san_$n.log 2>&1
+  rc=$?
+  { echo "# compute-sanitizer --tool $tool python -m pytest $* -m gpu"; echo "exit code: $rc (99 = sanitizer errors, 124 = timeout)";
+    grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|Invalid|hazard|error" $OUT/${TAG}_san_$n.log | sort | uniq -c | sort -rn | head -15; } > $OUT/${TAG}_san_$n.txt
+  cat $OUT/${TAG}_san_$n.txt
+}
+run norms_memcheck memcheck 900 tests/test_gpu_kernels.py -k "$SMALL"
+run norms_racecheck racecheck 900 tests/test_gpu_kernels.py -k "$SMALL"
+run norms_synccheck synccheck 900 tests/test_gpu_kernels.py -k "groupnorm_single_launch"
+run gemm_memcheck memcheck 1200 tests/test_gpu_kernels.py -k "test_linear or test_geglu or test_conv3x3 or pass_a"
+run attn_memcheck memcheck 900 tests/test_gpu_kernels.py -k "shared_attention and not large"
