@@ -95,6 +95,12 @@ typedef struct {
                and the nine taps read shifted views of it */
   int wide_io; /* A-B measurement: 0 = auto (256-bit residual loads / output stores in the epilogue whenever out and
                   residual rows are 32-byte aligned; results are bit-identical), 1 = always 128-bit */
+  void* col_partial; /* optional fp32 [M / 32, c_out - col_begin, 2]: per (32-row slab, output column >= col_begin) the (mean, M2)
+                        of the stored fp16 outputs, written by the GEMM epilogue (AdaIN statistics of the V third of a fused
+                        QKV projection: reference attn_processors.py:7-10, 244-245 `x.mean / x.std over tokens`). Needs a plain
+                        epilogue (no residual / activation), M % 128 == 0, c_out % 32 == 0, col_begin % 32 == 0. Hand it to
+                        ir_adain_coeffs.own_partial / ref_partial */
+  int col_begin;
 } ir_conv_gemm_params;
 int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
 
@@ -199,6 +205,8 @@ int ir_layernorm(const ir_layernorm_params* p, ir_stream_t stream);
  * v_own: fp16 [batch, s_own, *] columns v_col_off .. +channels; v_ref: fp16 [batch, n_ref, s_ref, *].
  * scale/shift: fp32 [batch, n_ref, channels].
  * workspace: ir_adain_workspace_bytes(batch, n_ref, channels) bytes (per-slab partial moments), caller-owned.
+ * With own_partial / ref_partial the mean / var reduction has already happened in the epilogue of the GEMM that produced V
+ * (north_star: "AdaIN mean/var ... fused into the preceding conv epilogue"); what is left is one merge launch.
  */
 typedef struct {
   const void* v_own;
@@ -210,6 +218,10 @@ typedef struct {
   float* scale;
   float* shift;
   void* workspace;
+  const void* own_partial; /* optional, both or neither: (mean, M2) per (32-token slab, channel) of the own V [batch, s_own/32, channels] */
+  const void* ref_partial; /* and of the reference V [batch, n_ref, s_ref/32, channels], as written by ir_conv_gemm.col_partial in the
+                              epilogues of the QKV projections (padded reference slots: zero-filled like their V). Then v_own /
+                              v_ref / workspace are not read and the statistics pass over V does not run. */
 } ir_adain_coeffs_params;
 size_t ir_adain_workspace_bytes(int batch, int n_ref, int channels);
 int ir_adain_coeffs(const ir_adain_coeffs_params* p, ir_stream_t stream);

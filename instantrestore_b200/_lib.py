@@ -33,6 +33,7 @@ class ConvGemmParams(C.Structure):
         ("res_row_stride", C.c_int), ("act", C.c_int), ("out", C.c_void_p), ("out_row_stride", C.c_int),
         ("tile_n", C.c_int), ("split_k", C.c_int), ("m_sub", C.c_int), ("no_persistent", C.c_int), ("pad_hi_only", C.c_int),
         ("cta_pair", C.c_int), ("gn_partial", C.c_void_p), ("gn_groups", C.c_int), ("halo", C.c_int), ("wide_io", C.c_int),
+        ("col_partial", C.c_void_p), ("col_begin", C.c_int),
     ]
 
 
@@ -73,6 +74,7 @@ class AdainCoeffsParams(C.Structure):
         ("v_ref", C.c_void_p), ("ref_row_stride", C.c_int), ("ref_col_off", C.c_int), ("n_ref", C.c_int),
         ("s_ref", C.c_int), ("batch", C.c_int), ("channels", C.c_int), ("eps", C.c_float),
         ("scale", C.c_void_p), ("shift", C.c_void_p), ("workspace", C.c_void_p),
+        ("own_partial", C.c_void_p), ("ref_partial", C.c_void_p),
     ]
 
 
@@ -302,10 +304,11 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
               stride: int = 1, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
               act: int = IR_ACT_NONE, out: torch.Tensor | None = None, tile_n: int = 0, split_k: int = 0,
               a_row_stride: int | None = None, pad_hi_only: bool = False, no_persistent: int = 0, m_sub: int = 0, cta_pair: int = 0, halo: int = 0, gn_partial: torch.Tensor | None = None,
-              gn_groups: int = 32, wide_io: int = 0) -> torch.Tensor:
+              gn_groups: int = 32, wide_io: int = 0, col_partial: torch.Tensor | None = None, col_begin: int = 0) -> torch.Tensor:
     """a: fp16 channel-last [batch*h_in*w_in, >=c_in]; w: fp16 [c_out, ksize*ksize*c_in].
-    gn_partial: fp32 [batch * (h_out*w_out/32) * gn_groups * 2] (gn_partial_numel) to receive pass A of the next GroupNorm."""
-    _h(a, "a"); _h(w, "w"); _f(bias, "bias"); _f(gn_partial, "gn_partial")
+    gn_partial: fp32 [batch * (h_out*w_out/32) * gn_groups * 2] (gn_partial_numel) to receive pass A of the next GroupNorm.
+    col_partial: fp32 [M/32, c_out - col_begin, 2] to receive per-(32-row slab, column) (mean, M2) of the outputs (AdaIN)."""
+    _h(a, "a"); _h(w, "w"); _f(bias, "bias"); _f(gn_partial, "gn_partial"); _f(col_partial, "col_partial")
     c_out = w.shape[0]
     assert w.shape[1] == ksize * ksize * c_in and w.is_contiguous(), (w.shape, ksize, c_in)
     m = batch * (h_in // stride) * (w_in // stride)
@@ -318,13 +321,14 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
         ksize=ksize, stride=stride, w=ptr(w), c_out=c_out, bias=ptr(bias),
         residual=ptr(residual), res_row_stride=residual.stride(-2) if residual is not None else 0,
         act=act, out=ptr(out), out_row_stride=out.stride(-2), tile_n=tile_n, split_k=split_k,
-        pad_hi_only=int(pad_hi_only), no_persistent=int(no_persistent), m_sub=m_sub, cta_pair=cta_pair, halo=halo, gn_partial=ptr(gn_partial), gn_groups=gn_groups, wide_io=wide_io or _NARROW_IO)
+        pad_hi_only=int(pad_hi_only), no_persistent=int(no_persistent), m_sub=m_sub, cta_pair=cta_pair, halo=halo, gn_partial=ptr(gn_partial), gn_groups=gn_groups, wide_io=wide_io or _NARROW_IO,
+        col_partial=ptr(col_partial), col_begin=col_begin)
     k_tot = ksize * ksize * c_in
     with on_device(a):
         _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks{ksize}s{stride}", 2.0 * m * k_tot * c_out,
              2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out
                     + (m * n_out if residual is not None else 0)),
-             load().ir_conv_gemm, C.byref(p), stream_ptr(a.device), keep=(a, w, bias, residual, out, gn_partial))
+             load().ir_conv_gemm, C.byref(p), stream_ptr(a.device), keep=(a, w, bias, residual, out, gn_partial, col_partial))
     return out
 
 
@@ -427,10 +431,33 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
     return out
 
 
-def adain_coeffs(v_own: torch.Tensor, v_ref: torch.Tensor, *, batch: int, s_own: int, n_ref: int, s_ref: int,
+def col_partial_supported(m: int, c_out: int, col_begin: int) -> bool:
+    """Shapes for which conv_gemm can emit the per-slab column moments of its outputs (AdaIN statistics)."""
+    return m % 128 == 0 and c_out % 32 == 0 and col_begin % 32 == 0
+
+
+def adain_coeffs(v_own: torch.Tensor | None, v_ref: torch.Tensor | None, *, batch: int, s_own: int, n_ref: int, s_ref: int,
                  channels: int, v_col_off: int = 0, ref_col_off: int = 0, eps: float = 1e-5,
                  scale: torch.Tensor | None = None, shift: torch.Tensor | None = None,
-                 workspace: torch.Tensor | None = None):
+                 workspace: torch.Tensor | None = None, own_partial: torch.Tensor | None = None,
+                 ref_partial: torch.Tensor | None = None):
+    """own_partial / ref_partial: the col_partial tensors the QKV GEMMs filled for the own / reference V ([batch*s/32, C, 2]
+    and [batch*n_ref*s/32, C, 2]); v_own / v_ref are then not read (may be None)."""
+    if own_partial is not None:
+        _f(own_partial, "own_partial"); _f(ref_partial, "ref_partial")
+        dev = own_partial.device
+        if scale is None:
+            scale = torch.empty((batch, n_ref, channels), dtype=torch.float32, device=dev)
+        if shift is None:
+            shift = torch.empty((batch, n_ref, channels), dtype=torch.float32, device=dev)
+        p = AdainCoeffsParams(v_own=None, own_row_stride=0, v_col_off=0, s_own=s_own, v_ref=None, ref_row_stride=0, ref_col_off=0,
+                              n_ref=n_ref, s_ref=s_ref, batch=batch, channels=channels, eps=eps, scale=ptr(scale), shift=ptr(shift),
+                              workspace=None, own_partial=ptr(own_partial), ref_partial=ptr(ref_partial))
+        with on_device(own_partial):
+            _run("ir_adain_coeffs", f"b{batch}_n{n_ref}_s{s_ref}_c{channels}_partials", 0.0,
+                 8.0 * batch * channels * (s_own + n_ref * s_ref) / 32, load().ir_adain_coeffs, C.byref(p), stream_ptr(dev),
+                 keep=(own_partial, ref_partial, scale, shift))
+        return scale, shift
     _h(v_own, "v_own"); _h(v_ref, "v_ref")
     dev = v_own.device
     if scale is None:

@@ -49,6 +49,8 @@ struct GemmKParams {
   int img_h, img_w;     // halo kernel: output (= input) image size
   float2* gn_partial;   // optional: per-(image, 32-row slab, group) (mean, M2) of the stored outputs (GroupNorm pass A)
   int gn_cpg, gn_hw, gn_groups;
+  float2* col_partial;  // optional: per-(32-row slab, column >= col_begin) (mean, M2) of the stored outputs (AdaIN statistics)
+  int col_begin;
   int wide_io;          // 256-bit epilogue loads / stores (rows are 32-byte aligned)
   const float* bias;
   const __half* residual;
@@ -121,6 +123,68 @@ __device__ __forceinline__ void epilogue_store(float (&v)[NC], const GemmKParams
   } else {
     for (int i = 0; i < NC; ++i)
       if (gcol + i < p.N) op[i] = __float2half_rn(v[i]);
+  }
+}
+
+// AdaIN statistics fused into the GEMM epilogue (the V third of a fused QKV projection): per-column (mean, M2) over
+// the warp's 32 rows (= 32 consecutive tokens of one image) of the fp16-rounded outputs. A reduce-scatter butterfly over
+// the 32 lanes (16 + 8 + 4 + 2 + 1 exchanges per quantity, fixed tree: deterministic) leaves column `lane` of the chunk
+// in lane `lane`:  col_partial[(row / 32) * (N - col_begin) + (col - col_begin)] = (mean, M2).
+__device__ __forceinline__ float col_reduce_scatter32(float (&t)[32], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? t[i] : t[i + h], keep = up ? t[i + h] : t[i];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+  return t[0];
+}
+__device__ __forceinline__ void col_stats32(const float (&v)[32], const GemmKParams& p, long grow, int gcol) {
+  const int lane = threadIdx.x & 31;
+  float t[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) t[i] = round_h(v[i]);
+  const float s = col_reduce_scatter32(t, lane);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { const float r = round_h(v[i]); t[i] = r * r; }
+  const float q = col_reduce_scatter32(t, lane);
+  const float mean = s * (1.0f / 32.0f);
+  p.col_partial[((grow - lane) >> 5) * (p.N - p.col_begin) + (gcol - p.col_begin) + lane] = make_float2(mean, fmaxf(q - s * mean, 0.f));
+}
+// the same for 8 consecutive columns (split-K epilogue): 4 + 2 + 1 exchanges scatter the columns over lane bits 4..2,
+// two more butterfly steps finish the sum over the remaining 4 lanes
+__device__ __forceinline__ void col_stats8(const float (&v)[8], const GemmKParams& p, long grow, int gcol) {
+  const int lane = threadIdx.x & 31;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = round_h(v[i]); q[i] = s[i] * s[i]; }
+  int off = 16;
+#pragma unroll
+  for (int h = 4; h >= 1; h >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float s_send = up ? s[i] : s[i + h], s_keep = up ? s[i + h] : s[i];
+      const float q_send = up ? q[i] : q[i + h], q_keep = up ? q[i + h] : q[i];
+      s[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+      q[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (int o = 2; o >= 1; o >>= 1) {
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], o);
+  }
+  if ((lane & 3) == 0) {
+    const float mean = s[0] * (1.0f / 32.0f);
+    p.col_partial[((grow - lane) >> 5) * (p.N - p.col_begin) + (gcol - p.col_begin) + (lane >> 2)] =
+        make_float2(mean, fmaxf(q[0] - s[0] * mean, 0.f));
   }
 }
 
@@ -292,7 +356,9 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
           v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
           v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
         }
-        epilogue_store<8>(v, p, grow, nt * BN + static_cast<int>(my_rank) * W + c8);
+        const int gcol = nt * BN + static_cast<int>(my_rank) * W + c8;
+        epilogue_store<8>(v, p, grow, gcol);          // leaves the stored (bias added, fp16-rounded) values in v
+        if (p.col_partial && gcol >= p.col_begin) col_stats8(v, p, grow, gcol);   // M % 128 == 0: row_ok is uniform
       }
     }
   } else {
@@ -305,7 +371,8 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_store<32>(v, p, grow, nt * BN + c0);
+        epilogue_store<32>(v, p, grow, nt * BN + c0);  // leaves the stored (bias added, fp16-rounded) values in v
+        if (p.col_partial && nt * BN + c0 >= p.col_begin && nt * BN + c0 < p.N) col_stats32(v, p, grow, nt * BN + c0);
       }
     }
   }
@@ -403,6 +470,7 @@ __device__ __forceinline__ void store_row64(__half* ptr, const uint4 (&r)[4], in
 }
 
 // epilogue_store<32> with the residual already in registers (prefetched before the accumulator was ready)
+template <bool COLS = false>
 __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4 (&res)[4], bool has_res, const GemmKParams& p,
                                                      long grow, int gcol) {
   if (p.bias) {
@@ -429,6 +497,7 @@ __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4
     for (int i = 0; i < 32; ++i) v[i] = silu(round_h(v[i]));
   }
   if (p.gn_partial) gn_stats32(v, p, grow, gcol);
+  if (COLS && p.col_partial && gcol >= p.col_begin) col_stats32(v, p, grow, gcol);   // only instantiated without a residual
   __half* op = p.out + grow * p.out_stride + gcol;
   uint4 packed[4];
 #pragma unroll
@@ -648,7 +717,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                if (fast && nt * BN + c0 < p.N) epilogue_store32_pre(v, resid[RESID ? sub : 0][RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
+                if (fast && nt * BN + c0 < p.N) epilogue_store32_pre<!RESID>(v, resid[RESID ? sub : 0][RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
                 else epilogue_store<32>(v, p, grow, nt * BN + c0);
               }
             }
@@ -830,7 +899,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-              if (fast) epilogue_store32_pre(v, resid[RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
+              if (fast) epilogue_store32_pre<!RESID>(v, resid[RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
               else epilogue_store<32>(v, p, grow, nt * BN + c0);
             }
           }
@@ -1266,6 +1335,17 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
       kp.gn_hw = hw_out;
       kp.gn_groups = p->gn_groups;
     }
+  }
+
+  // AdaIN column statistics of the outputs (optional): plain GEMM epilogue only, whole 32-row slabs, 32-column chunks
+  if (p->col_partial) {
+    if (geglu || p->residual || p->act != IR_ACT_NONE || kp.M % 128 != 0 || p->c_out % 32 != 0 || p->col_begin < 0 ||
+        p->col_begin % 32 != 0 || p->col_begin >= p->c_out || (reinterpret_cast<uintptr_t>(p->col_partial) & 7) ||
+        (p->bias && (reinterpret_cast<uintptr_t>(p->bias) & 15)))
+      return set_error(IR_ERR_SHAPE, "ir_conv_gemm: col_partial needs no residual / activation, M %% 128 == 0, c_out %% 32 == 0, col_begin %% 32 == 0 (M=%d c_out=%d col_begin=%d)",
+                       kp.M, p->c_out, p->col_begin);
+    kp.col_partial = static_cast<float2*>(p->col_partial);
+    kp.col_begin = p->col_begin;
   }
 
   const uint64_t rs = static_cast<uint64_t>(p->a_row_stride) * 2;  // pixel stride in bytes

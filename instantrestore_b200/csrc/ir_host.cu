@@ -94,6 +94,6 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 }  // namespace ir
 
 extern "C" const char* ir_last_error_string(void) { return ir::g_err; }
-extern "C" int ir_version(void) { return 103; }  // 103: ir_groupnorm_params += fused, ir_groupnorm_fused_supported; 102: ir_conv_gemm_params += cta_pair, gn_partial, gn_groups, halo; ir_groupnorm_params += partial_in
+extern "C" int ir_version(void) { return 104; }  // 104: ir_conv_gemm_params += col_partial, col_begin; ir_adain_coeffs_params += own_partial, ref_partial; 103: ir_groupnorm_params += fused, ir_groupnorm_fused_supported; 102: ir_conv_gemm_params += cta_pair, gn_partial, gn_groups, halo; ir_groupnorm_params += partial_in
 extern "C" unsigned long long ir_launch_count(void) { return ir::g_launches.load(std::memory_order_relaxed); }
 extern "C" int ir_check_device(void) { return ir::check_arch(); }

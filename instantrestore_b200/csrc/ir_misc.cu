@@ -118,6 +118,44 @@ __global__ void adain_finalize_kernel(const float2* __restrict__ ws, int n_ref, 
   shift[i] = style_mean - cm * a;
 }
 
+// AdaIN affine from the 32-row slab moments the QKV GEMM epilogues wrote (ir_conv_gemm.col_partial): no pass over V.
+// grid = (channels / 32, batch), block = (32 channels, 1 + n_ref chunks): thread (c, k) merges the slabs of chunk k
+// (k = 0: the image's own V = the style; k >= 1: reference k - 1 = the content) for its channel in slab order (Chan, equal
+// counts), the style statistics go through shared memory, threads k >= 1 write scale / shift.
+//   own_partial [batch, s_own / 32, channels], ref_partial [batch, n_ref, s_ref / 32, channels]  (mean, M2)
+__global__ void adain_from_partials_kernel(const float2* __restrict__ own_partial, const float2* __restrict__ ref_partial,
+                                           int n_ref, int channels, int s_own, int s_ref, float eps,
+                                           float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ float2 style[32];
+  const int c = blockIdx.x * 32 + threadIdx.x, k = threadIdx.y, b = blockIdx.y;
+  const int rows = k == 0 ? s_own : s_ref;
+  const int slabs = rows >> 5;
+  const float2* src = (k == 0 ? own_partial + static_cast<size_t>(b) * slabs * channels
+                              : ref_partial + (static_cast<size_t>(b) * n_ref + (k - 1)) * slabs * channels) + c;
+  float n_a = 32.f, mean_a = 0.f, m2_a = 0.f;
+  {
+    const float2 pm = __ldg(src);
+    mean_a = pm.x; m2_a = pm.y;
+  }
+  for (int sl = 1; sl < slabs; ++sl) {
+    const float2 pm = __ldg(src + static_cast<size_t>(sl) * channels);
+    const float n = n_a + 32.f, d = pm.x - mean_a, f = 32.f / n;
+    mean_a = fmaf(d, f, mean_a);
+    m2_a = m2_a + pm.y + d * d * n_a * f;
+    n_a = n;
+  }
+  const float sd = rows > 1 ? sqrtf(m2_a / (rows - 1)) : 0.f;      // unbiased, like torch.std
+  if (k == 0) style[threadIdx.x] = make_float2(mean_a, sd);
+  __syncthreads();
+  if (k > 0) {
+    const float2 st = style[threadIdx.x];
+    const float a = (st.y + eps) / (sd + eps);
+    const size_t i = (static_cast<size_t>(b) * n_ref + (k - 1)) * channels + c;
+    scale[i] = a;
+    shift[i] = st.x - mean_a * a;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ concat / FreeU
 // out[:, :, 0:c_hidden] = hidden * (c < c_hidden/2 ? bscale : 1);  out[:, :, c_hidden:] = skip  (when copy_skip)
 __global__ void __launch_bounds__(256) concat_kernel(const __half* __restrict__ hidden, const __half* __restrict__ skip,
@@ -471,10 +509,26 @@ extern "C" size_t ir_adain_workspace_bytes(int batch, int n_ref, int channels) {
 
 extern "C" int ir_adain_coeffs(const ir_adain_coeffs_params* p, ir_stream_t stream_) {
   using namespace ir;
-  if (!p || !p->v_own || !p->v_ref || !p->scale || !p->shift || !p->workspace) return set_error(IR_ERR_ARG, "ir_adain_coeffs: NULL argument");
+  if (!p || !p->scale || !p->shift) return set_error(IR_ERR_ARG, "ir_adain_coeffs: NULL argument");
+  if ((p->own_partial == nullptr) != (p->ref_partial == nullptr))
+    return set_error(IR_ERR_ARG, "ir_adain_coeffs: own_partial and ref_partial must both be set or both NULL");
+  const bool from_partials = p->own_partial != nullptr;
+  if (!from_partials && (!p->v_own || !p->v_ref || !p->workspace)) return set_error(IR_ERR_ARG, "ir_adain_coeffs: NULL argument");
   if (int rc = check_arch()) return rc;
   if (p->channels % 64 != 0 || p->n_ref <= 0 || p->batch <= 0 || p->s_own <= 0 || p->s_ref <= 0)
     return set_error(IR_ERR_SHAPE, "ir_adain_coeffs: channels=%d n_ref=%d", p->channels, p->n_ref);
+  if (from_partials) {
+    // statistics already reduced to 32-row slabs by the GEMM epilogues that produced V: one small merge kernel
+    if (p->s_own % 32 != 0 || p->s_ref % 32 != 0 || p->n_ref > 31)
+      return set_error(IR_ERR_SHAPE, "ir_adain_coeffs: slab moments need s_own %% 32 == 0, s_ref %% 32 == 0, n_ref <= 31 (s_own=%d s_ref=%d n_ref=%d)", p->s_own, p->s_ref, p->n_ref);
+    if ((reinterpret_cast<uintptr_t>(p->own_partial) | reinterpret_cast<uintptr_t>(p->ref_partial)) & 7)
+      return set_error(IR_ERR_ALIGN, "ir_adain_coeffs: partial pointers must be 8-byte aligned");
+    adain_from_partials_kernel<<<dim3(p->channels / 32, p->batch), dim3(32, 1 + p->n_ref), 0, static_cast<cudaStream_t>(stream_)>>>(
+        static_cast<const float2*>(p->own_partial), static_cast<const float2*>(p->ref_partial), p->n_ref, p->channels, p->s_own, p->s_ref,
+        p->eps, p->scale, p->shift);
+    IR_CUDA_LAUNCH_CHECK("adain_from_partials launch");
+    return 0;
+  }
   if ((p->own_row_stride | p->ref_row_stride | p->v_col_off | p->ref_col_off) & 7)
     return set_error(IR_ERR_ALIGN, "ir_adain_coeffs: strides/offsets must be multiples of 8 elements");
   if ((reinterpret_cast<uintptr_t>(p->v_own) | reinterpret_cast<uintptr_t>(p->v_ref)) & 15)

@@ -41,6 +41,20 @@ class RefCache:
     n_ref: int
 
 
+def _as_ref_kv(cap: RefKV, B: int, N: int, valid) -> RefKV:
+    """A captured reference-UNet projection as the (B, N, S, C) K/V of the shared layer, padded slots zero-filled in place
+    (K, V and the slab moments of V) exactly as pix2pix_turbo.py:269-273 zeroes keys / values."""
+    if valid is not None:
+        rows = cap.buf.view(B, N, cap.s_ref, -1)
+        stats = None if cap.v_partial is None else cap.v_partial.view(B, N, -1)
+        for b, nv in enumerate(valid):
+            if nv < N:
+                rows[b, nv:, :, cap.k_off:].zero_()     # K and V columns of the padded slots
+                if stats is not None:
+                    stats[b, nv:].zero_()
+    return RefKV(buf=cap.buf, k_off=cap.k_off, v_off=cap.v_off, n_ref=N, s_ref=cap.s_ref, v_partial=cap.v_partial)
+
+
 def ddpm_coeffs(t: int, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012):
     """sqrt(alpha_bar_t), sqrt(1 - alpha_bar_t) of the sd-turbo scaled-linear schedule (reference models/model.py:4-12)."""
     betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
@@ -64,7 +78,8 @@ class RestoreEngine:
         self.main = UNetEngine(StateDictView(unet_sd), self.spec, noise_timestep, caption_enc, self.dev,
                                use_adain=flags.use_adain, train_input=flags.train_input,
                                consume_refs=flags.use_shared_attention)
-        self.ref = (UNetEngine(StateDictView(original_unet_sd), self.spec, ref_timestep, caption_enc, self.dev, capture_kv=True)
+        self.ref = (UNetEngine(StateDictView(original_unet_sd), self.spec, ref_timestep, caption_enc, self.dev, capture_kv=True,
+                               emit_v_stats=flags.use_adain)
                     if flags.use_shared_attention else None)
         self.a_main, self.s_main = ddpm_coeffs(noise_timestep)
         self.a_ref, self.s_ref = ddpm_coeffs(ref_timestep)
@@ -90,12 +105,7 @@ class RestoreEngine:
             self.ref.forward(rin, B * N, H, W)
             ref_kv = []
             for cap in self.ref.captured:
-                if valid is not None:
-                    rows = cap.buf.view(B, N, cap.s_ref, -1)
-                    for b, nv in enumerate(valid):
-                        if nv < N:
-                            rows[b, nv:, :, cap.k_off:].zero_()     # K and V columns of the padded slots
-                ref_kv.append(RefKV(buf=cap.buf, k_off=cap.k_off, v_off=cap.v_off, n_ref=N, s_ref=cap.s_ref))
+                ref_kv.append(_as_ref_kv(cap, B, N, valid))
         cur.wait_stream(side)                                       # join: the up blocks need both paths
         for t in (x, state[0], *[sk[0] for sk in state[1]]):
             t.record_stream(cur)
@@ -217,12 +227,7 @@ class RestorePipeline:
         eng.ref.forward(rin, B * N, lat.shape[2], lat.shape[3])
         ref_kv = []
         for cap in eng.ref.captured:
-            if valid is not None:
-                rows = cap.buf.view(B, N, cap.s_ref, -1)
-                for b, nv in enumerate(valid):
-                    if nv < N:
-                        rows[b, nv:, :, cap.k_off:].zero_()
-            ref_kv.append(RefKV(buf=cap.buf, k_off=cap.k_off, v_off=cap.v_off, n_ref=N, s_ref=cap.s_ref))
+            ref_kv.append(_as_ref_kv(cap, B, N, valid))
         return ref_kv
 
     @torch.no_grad()
@@ -251,7 +256,8 @@ class RestorePipeline:
         for r in kv:
             c = r.v_off - r.k_off
             buf = r.buf[:, r.k_off:r.k_off + 2 * c].contiguous()
-            kept.append(RefKV(buf=buf, k_off=0, v_off=c, n_ref=r.n_ref, s_ref=r.s_ref))
+            kept.append(RefKV(buf=buf, k_off=0, v_off=c, n_ref=r.n_ref, s_ref=r.s_ref,
+                              v_partial=None if r.v_partial is None else r.v_partial.clone()))
         return RefCache(kv=kept, batch=B, n_ref=N)
 
     def _step_cached(self, c_t, eps_main, noise_main, cache: RefCache):

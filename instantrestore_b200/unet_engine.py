@@ -12,6 +12,7 @@ No CPU fallback: everything here calls instantrestore_b200._lib, which raises if
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -19,6 +20,9 @@ import torch
 
 from . import _lib as L
 from .weights import StateDictView, conv_weight_khwc, geglu_interleave_index
+
+
+FUSED_ADAIN_STATS = os.environ.get("IR_FUSED_ADAIN", "1") != "0"     # A-B measurement switch
 
 
 @dataclass
@@ -46,6 +50,7 @@ class RefKV:
     v_off: int
     n_ref: int
     s_ref: int
+    v_partial: Optional[torch.Tensor] = None    # [B*N*S/32, C, 2] slab moments of V from the projection's epilogue (AdaIN)
 
 
 class _Lin:
@@ -82,11 +87,15 @@ def timestep_embedding(t: int, dim: int) -> torch.Tensor:
 class UNetEngine:
     def __init__(self, sd: StateDictView, spec: UNetSpec, timestep: int, caption_enc: torch.Tensor, device,
                  *, use_adain: bool = False, train_input: bool = True, consume_refs: bool = False,
-                 capture_kv: bool = False, freeu: Optional[Tuple[float, float, float, float]] = (0.9, 0.2, 1.4, 1.6)):
+                 capture_kv: bool = False, freeu: Optional[Tuple[float, float, float, float]] = (0.9, 0.2, 1.4, 1.6),
+                 emit_v_stats: bool = False):
         L.load()
         self.spec, self.dev = spec, torch.device(device)
         self.use_adain, self.train_input = use_adain, train_input
         self.consume_refs, self.capture_kv = consume_refs, capture_kv
+        # reference UNet of an AdaIN model: the captured QKV projections also emit the per-slab moments of V in their
+        # epilogues (the statistics belong to K/V extraction time and travel with the K/V, RefCache included)
+        self.emit_v_stats = emit_v_stats
         self.freeu = freeu
         self.captured: List[RefKV] = []
         # The reference UNet is only run for its 9 captured K/V projections (reference pix2pix_turbo.py:255-266; the
@@ -182,8 +191,8 @@ class UNetEngine:
         )
 
     # ------------------------------------------------------------------------------------------ ops
-    def _lin(self, x, lin: _Lin, residual=None, act=L.IR_ACT_NONE):
-        return L.conv_gemm(x, lin.w, batch=1, h_in=1, w_in=x.shape[0], c_in=lin.c_in, bias=lin.b, residual=residual, act=act)
+    def _lin(self, x, lin: _Lin, residual=None, act=L.IR_ACT_NONE, **kw):
+        return L.conv_gemm(x, lin.w, batch=1, h_in=1, w_in=x.shape[0], c_in=lin.c_in, bias=lin.b, residual=residual, act=act, **kw)
 
     def _conv(self, x, cv: _Conv, B, H, W, residual=None):
         return L.conv_gemm(x, cv.w, batch=B, h_in=H, w_in=W, c_in=cv.c_in, ksize=cv.ksize, stride=cv.stride, bias=cv.b,
@@ -206,19 +215,28 @@ class UNetEngine:
         h = self._lin(t, p["proj_in"])
         # --- attn1: self attention, shared with the reference images in the up blocks
         n = L.layernorm(h, p["ln1"].g, p["ln1"].b)
-        qkv = self._lin(n, p["qkv"])                                   # [B*S, 3C]: q | k | v
+        shared_layer = self.consume_refs and ref is not None
+        # AdaIN statistics of V (mean / M2 per 32-token slab and channel) ride in the epilogue of this projection
+        want_stats = (capture and self.emit_v_stats) or (shared_layer and self.use_adain and ref.v_partial is not None)
+        part = None
+        if want_stats and FUSED_ADAIN_STATS and L.col_partial_supported(B * S, 3 * C, 2 * C):
+            part = torch.empty((B * S // 32, C, 2), dtype=torch.float32, device=x.device)
+        qkv = self._lin(n, p["qkv"], col_partial=part, col_begin=2 * C)    # [B*S, 3C]: q | k | v
         if capture:
-            self.captured.append(RefKV(buf=qkv, k_off=C, v_off=2 * C, n_ref=0, s_ref=S))
+            self.captured.append(RefKV(buf=qkv, k_off=C, v_off=2 * C, n_ref=0, s_ref=S, v_partial=part))
             if stop_after_kv:
                 return None        # nothing downstream of the last captured K/V is ever read (see forward_up)
         kw = {}
         own = True
-        shared_layer = self.consume_refs and ref is not None
         if shared_layer:
             kw.update(k_ref=ref.buf[:, ref.k_off:], v_ref=ref.buf[:, ref.v_off:], n_ref=ref.n_ref, s_ref=ref.s_ref)
             if self.use_adain:
-                sc, sh = L.adain_coeffs(qkv[:, 2 * C:], ref.buf[:, ref.v_off:], batch=B, s_own=S, n_ref=ref.n_ref,
-                                        s_ref=ref.s_ref, channels=C)
+                if part is not None and ref.v_partial is not None:
+                    sc, sh = L.adain_coeffs(None, None, batch=B, s_own=S, n_ref=ref.n_ref, s_ref=ref.s_ref, channels=C,
+                                            own_partial=part, ref_partial=ref.v_partial)
+                else:
+                    sc, sh = L.adain_coeffs(qkv[:, 2 * C:], ref.buf[:, ref.v_off:], batch=B, s_own=S, n_ref=ref.n_ref,
+                                            s_ref=ref.s_ref, channels=C)
                 kw.update(adain_scale=sc, adain_shift=sh)
             own = self.train_input
         if own:

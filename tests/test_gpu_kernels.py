@@ -439,6 +439,63 @@ def test_adain_coeffs_including_zeroed_slot(L):
     assert torch.allclose(sh[1, 2], sm[1, 0], rtol=0, atol=1e-6)
 
 
+# the QKV projection shapes of the nine shared layers (C = 320 / 640 / 1280; B = 1 main pass, B*N = 4 reference pass, a
+# B = 8 step) and forced kernel variants, so that every epilogue that can emit the column moments is exercised
+@pytest.mark.parametrize("M,C,kw", [
+    (4096, 320, {}), (1024, 640, {}), (256, 1280, {}),                       # one tile per CTA / split-K cluster (B = 1)
+    (16384, 320, {}), (4096, 640, {}), (1024, 1280, {}),                     # persistent 160- / 256-wide tiles (B*N = 4)
+    (32768, 320, {}), (8192, 1280, {}),                                      # B = 8 step
+    (4096, 640, dict(cta_pair=2)), (2048, 320, dict(cta_pair=2)),            # CTA-pair kernel, 256- and 160-wide tiles
+    (512, 640, dict(split_k=2)), (256, 1280, dict(split_k=4, tile_n=64)),     # split-K epilogue (8-column statistics)
+    (1024, 320, dict(no_persistent=2, tile_n=64)), (2048, 640, dict(no_persistent=2, tile_n=128, m_sub=0)),
+])
+def test_gemm_epilogue_emits_adain_column_moments(L, M, C, kw):
+    """ir_conv_gemm(col_partial=...): (mean, M2) per (32-token slab, V column) of the stored outputs, and ir_adain_coeffs
+    from those moments == ir_adain_coeffs from a pass over V == fp32 torch (unbiased std, eps on the std)."""
+    g = _gen(41)
+    x = torch.randn(M, C, device="cuda", generator=g).half()
+    w = (torch.randn(3 * C, C, device="cuda", generator=g) / math.sqrt(C)).half()
+    part = torch.full((M // 32, C, 2), float("nan"), device="cuda")
+    assert L.col_partial_supported(M, 3 * C, 2 * C)
+    args = dict(batch=1, h_in=1, w_in=M, c_in=C, **kw)
+    qkv = L.conv_gemm(x, w, col_partial=part, col_begin=2 * C, **args)
+    assert torch.equal(qkv, L.conv_gemm(x, w, **args))                         # the statistics do not disturb the outputs
+    assert torch.isfinite(part).all()                                          # every (slab, column) slot was written
+    v = qkv[:, 2 * C:].float().view(M // 32, 32, C)
+    mean = v.mean(1)
+    m2 = ((v - mean[:, None]) ** 2).sum(1)
+    assert float((part[..., 0] - mean).abs().max()) <= 1e-5
+    assert rel_l2(part[..., 1], m2) <= 1e-4
+    again = torch.empty_like(part)
+    L.conv_gemm(x, w, col_partial=again, col_begin=2 * C, **args)
+    assert torch.equal(again, part)                                            # fixed reduction tree: deterministic
+
+
+@pytest.mark.parametrize("B,N,S,C", [(1, 4, 4096, 320), (2, 3, 1024, 640), (1, 8, 256, 1280)])
+def test_adain_coeffs_from_epilogue_moments(L, B, N, S, C):
+    g = _gen(42)
+    xo = (torch.randn(B * S, C, device="cuda", generator=g) * 1.5 + 0.3).half()
+    xr = (torch.randn(B * N * S, C, device="cuda", generator=g) * 0.7 - 0.2).half()
+    w = (torch.randn(3 * C, C, device="cuda", generator=g) / math.sqrt(C)).half()
+    po = torch.empty((B * S // 32, C, 2), device="cuda")
+    pr = torch.empty((B * N * S // 32, C, 2), device="cuda")
+    qo = L.conv_gemm(xo, w, batch=1, h_in=1, w_in=B * S, c_in=C, col_partial=po, col_begin=2 * C)
+    qr = L.conv_gemm(xr, w, batch=1, h_in=1, w_in=B * N * S, c_in=C, col_partial=pr, col_begin=2 * C)
+    # pad the last reference slot of the last identity exactly like the pipeline does: V rows and their moments zeroed
+    qr.view(B, N, S, 3 * C)[B - 1, N - 1, :, C:].zero_()
+    pr.view(B, N, -1)[B - 1, N - 1].zero_()
+    sc, sh = L.adain_coeffs(None, None, batch=B, s_own=S, n_ref=N, s_ref=S, channels=C, own_partial=po, ref_partial=pr)
+    sc2, sh2 = L.adain_coeffs(qo[:, 2 * C:], qr[:, 2 * C:], batch=B, s_own=S, n_ref=N, s_ref=S, channels=C)
+    assert rel_l2(sc, sc2) <= 2e-5 and rel_l2(sh, sh2) <= 2e-5
+    vo = qo[:, 2 * C:].float().view(B, S, C)
+    vr = qr[:, 2 * C:].float().view(B, N, S, C)
+    sm, ss = vo.mean(1), vo.std(1) + 1e-5
+    cm, cs = vr.mean(2), vr.std(2) + 1e-5
+    ref_sc = ss[:, None] / cs
+    assert rel_l2(sc, ref_sc) <= 2e-5
+    assert rel_l2(sh, sm[:, None] - cm * ref_sc) <= 2e-5
+
+
 @pytest.mark.parametrize("B,H,Ch,Cs,bs,ss", [(2, 8, 128, 64, 1.4, 0.9), (1, 16, 1280, 640, 1.6, 0.2), (2, 32, 64, 32, 1.0, 1.0), (1, 8, 1280, 1280, 1.4, 0.9)])
 def test_concat_freeu(L, B, H, Ch, Cs, bs, ss):
     g = _gen(11)
