@@ -279,6 +279,26 @@ int ir_image_out(const void* y, int y_row_stride, float lo, float hi, void* out,
 int ir_vae_sample(const void* moments, int m_row_stride, const float* eps, float scale, float* out, int batch, int c,
                   int hw, ir_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Host pre / post-processing of the reference entry on the GPU (byte / integer work, bit-exact with the reference):
+ * ir_resample_u8_pass — one separable pass of Pillow's 8-bit resampling (Image.resize(..., LANCZOS), which
+ *   torchvision's Resize(512, LANCZOS) of face_replace/inference/test.py:54-56 calls), restricted to the CenterCrop(512)
+ *   window (:57):  out[o, j, c] = clip8((2^21 + sum_t kk[first + o, t] * in[bounds[first + o].lo + t, j, c]) >> 22), c = 0..2.
+ *   in: uint8, element (a, j, c) at in + a * in_stride_axis + j * in_stride_other + c (bytes); bounds: int32 [n, 2] =
+ *   (first tap, tap count), kk: int32 [n, ksize] fixed-point weights, both computed on the host as Pillow's
+ *   precompute_coeffs / normalize_coeffs_8bpc do. out_f16_norm == 0: uint8 out (the 8-bit intermediate image of the
+ *   first pass); != 0: ToTensor + Normalize(0.5, 0.5) (:58-59) and the fp16 cast of :92 applied, fp16 out. Strides of
+ *   `out` are in elements: (o, j, c) at o * out_stride_axis + j * out_stride_other + c * out_stride_c.
+ * ir_u8_to_f16 — crop + normalise when no resize is needed: uint8 window [h, w, 3] (byte strides) -> fp16 NCHW [3, h, w].
+ * ir_image_out_u8 — vis_utils.tensor2im(unnorm=True) (face_replace/training/utils/vis_utils.py:14-23) on the fp16 NCHW
+ *   prediction [batch, 3, hw]: * 0.5, + 0.5 (each rounded to fp16), clamp [0, 1], * 255 (fp16), truncate -> uint8 [batch, hw, 3].
+ */
+int ir_resample_u8_pass(const void* in, long in_stride_axis, long in_stride_other, int n_out, int n_other, const int* bounds,
+                        const int* kk, int ksize, int first, void* out, long out_stride_axis, long out_stride_other,
+                        long out_stride_c, int out_f16_norm, ir_stream_t stream);
+int ir_u8_to_f16(const void* in, long in_stride_y, long in_stride_x, int h, int w, void* out, ir_stream_t stream);
+int ir_image_out_u8(const void* pred, void* out, int batch, int hw, ir_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

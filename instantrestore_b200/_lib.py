@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "ir_groupnorm", "ir_groupnorm_workspace_bytes", "ir_groupnorm_fused_supported", "ir_layernorm", "ir_adain_coeffs", "ir_adain_workspace_bytes",
     "ir_concat_freeu", "ir_upsample_nearest2x", "ir_latent_in", "ir_latent_out",
     "ir_softmax_rows", "ir_image_in", "ir_image_out", "ir_vae_sample",
+    "ir_resample_u8_pass", "ir_u8_to_f16", "ir_image_out_u8",
 ]
 
 
@@ -123,6 +124,10 @@ def load() -> C.CDLL:
                                  C.c_int, C.c_void_p]
     lib.ir_vae_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p]
+    lib.ir_resample_u8_pass.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_int, C.c_void_p]
+    lib.ir_u8_to_f16.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ir_image_out_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.ir_debug_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_uint] * 6 + [C.c_void_p]
     _lib = lib
     return lib
@@ -573,4 +578,38 @@ def vae_sample(moments: torch.Tensor, eps: torch.Tensor | None, scale: float, *,
     with on_device(moments):
         check(load().ir_vae_sample(ptr(moments), moments.stride(-2), ptr(eps), scale, ptr(out), batch, c, h * w, stream_ptr(moments.device)),
               "ir_vae_sample")
+    return out
+
+
+def resample_u8_pass(src: torch.Tensor, src_off: int, in_stride_axis: int, in_stride_other: int, n_out: int, n_other: int,
+                     bounds: torch.Tensor, kk: torch.Tensor, first: int, out: torch.Tensor, out_stride_axis: int,
+                     out_stride_other: int, out_stride_c: int, f16_norm: bool) -> None:
+    """One pass of Pillow's 8-bit resampling (see include/instantrestore_b200.h). `src`: CUDA uint8, read from byte
+    offset `src_off`; `bounds` int32 [n, 2], `kk` int32 [n, ksize] on the device."""
+    assert src.dtype == torch.uint8 and src.is_cuda and bounds.dtype == torch.int32 and kk.dtype == torch.int32
+    with on_device(src):
+        _run("ir_resample_u8_pass", f"o{n_out}_j{n_other}_k{kk.shape[1]}", 0.0, 3.0 * n_out * n_other * (kk.shape[1] + (2 if f16_norm else 1)),
+             load().ir_resample_u8_pass, src.data_ptr() + src_off, in_stride_axis, in_stride_other, n_out, n_other, ptr(bounds), ptr(kk),
+             kk.shape[1], first, ptr(out), out_stride_axis, out_stride_other, out_stride_c, int(f16_norm), stream_ptr(src.device),
+             keep=(src, bounds, kk, out))
+
+
+def u8_to_f16(src: torch.Tensor, src_off: int, stride_y: int, stride_x: int, h: int, w: int, out: torch.Tensor) -> None:
+    """uint8 window [h, w, 3] (byte strides, starting at byte src_off) -> normalised fp16 NCHW [3, h, w]."""
+    assert src.dtype == torch.uint8 and src.is_cuda and out.dtype == torch.float16
+    with on_device(src):
+        _run("ir_u8_to_f16", f"hw{h * w}", 0.0, 9.0 * h * w, load().ir_u8_to_f16, src.data_ptr() + src_off, stride_y, stride_x, h, w,
+             ptr(out), stream_ptr(src.device), keep=(src, out))
+
+
+def image_out_u8(pred: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """tensor2im(unnorm=True) of the reference on the GPU: fp16 NCHW prediction [B, 3, H, W] -> uint8 [B, H, W, 3]."""
+    if pred.dtype != torch.float16 or not pred.is_cuda or not pred.is_contiguous() or pred.shape[1] != 3:
+        raise TypeError("image_out_u8: expected a contiguous CUDA fp16 [B, 3, H, W] tensor")
+    b, _, hh, ww = pred.shape
+    if out is None:
+        out = torch.empty((b, hh, ww, 3), dtype=torch.uint8, device=pred.device)
+    with on_device(pred):
+        _run("ir_image_out_u8", f"b{b}_hw{hh * ww}", 0.0, 9.0 * b * hh * ww, load().ir_image_out_u8, ptr(pred), ptr(out), b, hh * ww,
+             stream_ptr(pred.device), keep=(pred, out))
     return out

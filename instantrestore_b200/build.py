@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libinstantrestore_b200.so"
-SOURCES = ["ir_host.cu", "ir_gemm.cu", "ir_attn.cu", "ir_norm.cu", "ir_misc.cu", "ir_debug.cu"]
+SOURCES = ["ir_host.cu", "ir_gemm.cu", "ir_attn.cu", "ir_norm.cu", "ir_misc.cu", "ir_image.cu", "ir_debug.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
