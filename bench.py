@@ -291,27 +291,33 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     L.load()
 
-    # weights: rank 0 draws the checkpoint, one broadcast replicates it (no collective after this point)
+    # weights: rank 0 draws the checkpoint and prepares it (LoRA merge, folding, fp16 packing); the other ranks build the
+    # same engine structure from placeholder tensors at the same time, then ONE device-to-device broadcast per dtype
+    # ships the prepared arena (no collective after this point)
     t0 = time.perf_counter()
-    sd_main = synthetic_unet_state_dict(seed=0, lora_rank=a.lora_rank) if rank == 0 else None
-    sd_ref = synthetic_unet_state_dict(seed=0) if rank == 0 else None
-    sd_vae = sd_ovae = None
-    if not a.latent_only and rank == 0:
-        sd_vae = synthetic_vae_state_dict(seed=100, lora_rank=a.lora_rank_vae)
-        sd_ovae = synthetic_vae_state_dict(seed=100)
-    t_bcast = time.perf_counter()
-    sd_main = D.broadcast_state_dict(sd_main, src=0)
-    sd_ref = D.broadcast_state_dict(sd_ref, src=0)
-    if not a.latent_only:
-        sd_vae = D.broadcast_state_dict(sd_vae, src=0)
-        sd_ovae = D.broadcast_state_dict(sd_ovae, src=0)
-    t_bcast = time.perf_counter() - t_bcast
+    sds = None
+    if rank == 0:
+        sds = [synthetic_unet_state_dict(seed=0, lora_rank=a.lora_rank), synthetic_unet_state_dict(seed=0)]
+        if not a.latent_only:
+            sds += [synthetic_vae_state_dict(seed=100, lora_rank=a.lora_rank_vae), synthetic_vae_state_dict(seed=100)]
+    if world > 1:
+        metas = D.broadcast_meta(sds, src=0)
+        if rank != 0:
+            sds = [D.placeholder_state_dict(m) for m in metas]
+    sd_main, sd_ref = sds[0], sds[1]
+    sd_vae, sd_ovae = (sds[2], sds[3]) if not a.latent_only else (None, None)
     cap = synthetic_caption()
     flags = ModelFlags(use_adain=not a.no_adain, train_input=bool(a.train_input), lora_rank_unet=a.lora_rank)
     if a.latent_only:
         eng = RestoreEngine(sd_main, sd_ref, cap, flags, device=dev, use_cuda_graph=not a.no_graph)
     else:
         eng = RestorePipeline(sd_main, sd_ref, sd_vae, sd_ovae, cap, flags, device=dev, use_cuda_graph=not a.no_graph)
+    torch.cuda.synchronize()
+    D.barrier()
+    t_bcast = time.perf_counter()
+    arena = D.broadcast_engine(eng, src=0, device=dev)
+    torch.cuda.synchronize()
+    t_bcast = time.perf_counter() - t_bcast
     t_setup = time.perf_counter() - t0
     cur = torch.cuda.current_stream(dev)
 
@@ -459,7 +465,8 @@ def run_ours(a):
         "data": "synthetic",
         "config": config_dict(a),
         "run": {"cuda_graph": not a.no_graph, "requests_in_flight": n_streams, "setup_s": round(t_setup, 1),
-                "weight_broadcast_s": round(t_bcast, 2), "timed_region_s": round(ms_total * 1e-3, 3)},
+                "weight_broadcast_s": round(t_bcast, 3), "weight_arena_bytes": arena["bytes"], "weight_arena_tensors": arena["tensors"],
+                "timed_region_s": round(ms_total * 1e-3, 3)},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h,
                 "ms_per_step": ms_e2e / a.steps, "requests_in_flight": n_fly},

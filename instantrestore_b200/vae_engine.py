@@ -87,7 +87,10 @@ class VaeEngine:
             wpq = v.weight("post_quant_conv")[:, :, 0, 0]
             w_in = torch.einsum("omkl,mi->oikl", d.weight("conv_in"), wpq)
             self.d_conv_in = _Conv(w_in, d.bias("conv_in"), dev, c_in_pad=64)
-            self.d_latent_shift = torch.linalg.solve(wpq.double(), v.bias("post_quant_conv").double()).float().to(dev)
+            if torch.any(wpq):
+                self.d_latent_shift = torch.linalg.solve(wpq.double(), v.bias("post_quant_conv").double()).float().to(dev)
+            else:   # placeholder weights (dist.placeholder_state_dict): the prepared value arrives by dist.broadcast_engine
+                self.d_latent_shift = torch.zeros(wpq.shape[0], dtype=torch.float32, device=dev)
             self.d_mid = self._load_mid(d.sub("mid_block"))
             self.d_up = []
             for i in range(len(boc)):
