@@ -223,7 +223,7 @@ class Predictor:
     # ------------------------------------------------------------------------------------------ batched / pipelined entry
     def _stage(self, slot: int, images: List[Image.Image]) -> List[torch.Tensor]:
         """PIL images -> uint8 HWC tensors on the device through this slot's pinned staging buffer (one async H2D each)."""
-        arrs = [np.asarray(im.convert("RGB"), dtype=np.uint8) for im in images]
+        arrs = [np.array(im.convert("RGB"), dtype=np.uint8) for im in images]
         total = sum(a.size for a in arrs)
         buf = self._pinned.get(("in", slot))
         if buf is None or buf.numel() < total:

@@ -273,12 +273,21 @@ def test_predictor_entry_on_a_synthetic_checkpoint(tmp_path):
     c_t = image_to_tensor(inp)[None].half().float().cuda()
     cond = torch.stack([image_to_tensor(r) for r in refs])[None].half().float().cuda()
     gold = ImageRestorePipeline(lat, vae, ovae).forward(c_t, cond, eps_main, eps_ref, noise_main, noise_ref)[0]
-    gold_u8 = np.asarray(inference_tensor2im(gold))
+    gold_u8 = np.asarray(inference_tensor2im(gold.half()))     # the reference's tensor2im runs on the fp16 prediction (test.py:82-83)
     got = np.asarray(img)
     diff = np.abs(got.astype(np.int32) - gold_u8.astype(np.int32))
     err = float(np.linalg.norm((got.astype(np.float64) - gold_u8) / 127.5) / np.linalg.norm(gold_u8 / 127.5 - 1.0))
     print(f"Predictor vs oracle (uint8 images): rel-L2 {err:.3e}, max |d| {diff.max()} levels, mean |d| {diff.mean():.3f} levels")
     assert err <= 6e-3 and diff.mean() <= 0.6
+    # pipelined entry: 5 requests, 3 in flight (uint8 staging, GPU transform / packing); results come back in order and
+    # differ from the single call only through the fresh normal draws of every forward
+    many = list(pred.predict_many([(inp, refs), (tgt, refs), (inp, refs), (tgt, refs), (inp, refs)], in_flight=3))
+    assert len(many) == 5 and all(m.size == (512, 512) for m in many)
+    d_same = np.abs(np.asarray(many[0]).astype(np.int32) - got.astype(np.int32)).mean()
+    d_other = np.abs(np.asarray(many[1]).astype(np.int32) - got.astype(np.int32)).mean()
+    d_again = np.abs(np.asarray(many[4]).astype(np.int32) - np.asarray(many[0]).astype(np.int32)).mean()
+    print(f"predict_many: same request {d_same:.2f} / {d_again:.2f} levels apart (noise draws), different request {d_other:.2f}")
+    assert d_same < d_other and d_again < d_other
     # calc_attn_probs=True (test.py:93-108): one dense map per shared layer, (B, H, S, N_ref * S), rows sum to 1
     img2, _, probs = pred.predict(inp, refs, calc_attn_probs=True)
     assert len(probs) == 9 and probs[0].shape == (1, 4, 256, 2 * 256) and probs[-1].shape == (1, 1, 4096, 2 * 4096)
