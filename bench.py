@@ -412,7 +412,9 @@ def run_ours(a):
                 if i >= n_fly:
                     done[j].synchronize()                      # result i - n_fly is on the host; its buffers are free again
                 with torch.cuda.stream(self.streams[i % self.n_streams]):
-                    ins = [t.to(dev, non_blocking=True) for t in self.host]
+                    # pinned host tensors go straight into the public call: one asynchronous H2D copy each, into the
+                    # graph's static input buffers
+                    ins = self.host if not a.latent_only else [t.to(dev, non_blocking=True) for t in self.host]
                     out = self.call(ins, i % self.n_streams)
                     host_outs[j].copy_(out, non_blocking=True)
                     done[j].record()
@@ -437,7 +439,7 @@ def run_ours(a):
             dev_ms = e0.elapsed_time(e1) / k
             t0 = time.perf_counter()
             for _ in range(k):
-                ins = [t.to(dev, non_blocking=True) for t in self.host]
+                ins = self.host if not a.latent_only else [t.to(dev, non_blocking=True) for t in self.host]
                 self.host_out.copy_(self.call(ins, 0), non_blocking=True)
                 torch.cuda.synchronize()
             host_ms = (time.perf_counter() - t0) * 1e3 / k

@@ -283,21 +283,29 @@ class RestorePipeline:
         if face_embeds is not None:
             raise NotImplementedError("condition_on_face_embeds is False in the released configs")
         dev = self.dev
-        c_t = c_t.to(dev)
+        # Inputs may live on the host (pinned memory for an asynchronous copy): on the graph path they are copied ONCE,
+        # straight into the graph's static input buffers on the current stream.
         if c_t.dtype not in (torch.float16, torch.float32):
             c_t = c_t.float()
         B, _, H, W = c_t.shape
         h, w = H // 8, W // 8
+        if H % 8 or W % 8 or (h & (h - 1)) or (w & (w - 1)) or h < 8 or w < 8:
+            raise ValueError(f"image size {H}x{W}: the conv kernels need sides of 8 x a power of two (64 ... 1024); "
+                             "the reference entry always feeds 512 x 512 (test.py:54-57)")
         cond = None
         if conditioning_images is not None and self.flags.use_shared_attention:
-            cond = conditioning_images.to(dev, c_t.dtype)
+            cond = conditioning_images if conditioning_images.dtype == c_t.dtype else conditioning_images.to(c_t.dtype)
         N = 0 if cond is None else cond.shape[1]
+        if N > 16:
+            raise ValueError(f"{N} conditioning images per identity: ir_shared_attn_fwd takes at most 16 reference chunks "
+                             "(the released configs use max_conditioning_images = 4)")
         rnd = lambda *s: torch.randn(*s, device=dev, dtype=torch.float32, generator=self._gen)
-        eps_main = rnd(B, 4, h, w) if eps_main is None else eps_main.to(dev, torch.float32)
-        noise_main = rnd(B, 4, h, w) if noise_main is None else noise_main.to(dev, torch.float32)
+        f32 = lambda t: t if t.dtype == torch.float32 else t.float()
+        eps_main = rnd(B, 4, h, w) if eps_main is None else f32(eps_main)
+        noise_main = rnd(B, 4, h, w) if noise_main is None else f32(noise_main)
         if cond is not None:
-            eps_ref = rnd(B * N, 4, h, w) if eps_ref is None else eps_ref.to(dev, torch.float32)
-            noise_ref = rnd(B * N, 4, h, w) if noise_ref is None else noise_ref.to(dev, torch.float32)
+            eps_ref = rnd(B * N, 4, h, w) if eps_ref is None else f32(eps_ref)
+            noise_ref = rnd(B * N, 4, h, w) if noise_ref is None else f32(noise_ref)
         else:
             eps_ref = noise_ref = None
         valid = None
@@ -305,13 +313,14 @@ class RestorePipeline:
             valid = [int(v) for v in valid_indices]
             if all(v >= N for v in valid):
                 valid = None
-        ins = dict(c_t=c_t.contiguous(), cond=None if cond is None else cond.contiguous(), eps_main=eps_main.contiguous(),
-                   eps_ref=eps_ref, noise_main=noise_main.contiguous(), noise_ref=noise_ref)
+        ins = dict(c_t=c_t, cond=cond, eps_main=eps_main, eps_ref=eps_ref, noise_main=noise_main, noise_ref=noise_ref)
+        on_dev = lambda d: {k: (None if v is None else v.to(dev).contiguous()) for k, v in d.items()}
         if return_self_attention_maps or not self.use_cuda_graph:
             # attention maps: eager (no graph), the 9 shared layers also build the dense (B, H, S, S_k) softmax matrix the
             # reference exposes as SharedAttnProcessor.attention_probs (pix2pix_turbo.py:338-341)
             main = self.engine.main
             main.save_attention_probs = bool(return_self_attention_maps)
+            ins = on_dev(ins)
             try:
                 out = self._step(ins["c_t"], ins["cond"], ins["eps_main"], ins["eps_ref"], ins["noise_main"], ins["noise_ref"], valid)
                 maps = list(main.attention_probs) if return_self_attention_maps else None
@@ -322,7 +331,7 @@ class RestorePipeline:
         g = self._graphs.get(key)
         if g is None:
             with L.scratch_namespace(("graph", id(self), len(self._graphs))):
-                g = self._capture(ins, valid)
+                g = self._capture(on_dev(ins), valid)
             self._graphs[key] = g
         for k, v in ins.items():
             if v is not None:
