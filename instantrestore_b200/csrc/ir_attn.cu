@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  pdl_wait();     // barriers / TMEM are set up; everything below reads what the previous kernels wrote
   if (ADAIN) {
     // stage the AdaIN affine of every reference for this (batch, head): sAd[r][0][d] = scale, sAd[r][1][d] = shift
     const int C = p.heads * kD;
@@ -406,6 +407,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     }
 
     // ---------------------------------------------------------------- epilogue
+    pdl_launch_dependents();
     const int qrow = (2 * pair + i) * kQT + row;
     if (n_tiles > 0) {
       if (!ADAIN) {
@@ -469,6 +471,8 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restri
                                                            __half* __restrict__ out, int out_stride) {
   const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z, row = threadIdx.x;
   const int qrow = qt * kQT + row;
+  pdl_launch_dependents();
+  pdl_wait();
   if (qrow >= s_q) return;
   const size_t unit0 = ((static_cast<size_t>(b) * heads + head) * n_qt + qt) * n_splits;
   float M = -INFINITY;
@@ -654,16 +658,16 @@ extern "C" int ir_shared_attn_fwd(const ir_shared_attn_params* p, ir_stream_t st
     attr_done = true;
   }
   dim3 grid(pairs * n_splits, p->heads, p->batch);
-  if (adain) shared_attn_kernel<true><<<grid, kAttnThreads, kAttnSmem, stream>>>(kp);
-  else shared_attn_kernel<false><<<grid, kAttnThreads, kAttnSmem, stream>>>(kp);
+  if (adain) IR_LAUNCH(shared_attn_kernel<true>, grid, kAttnThreads, kAttnSmem, stream, kp);
+  else IR_LAUNCH(shared_attn_kernel<false>, grid, kAttnThreads, kAttnSmem, stream, kp);
   IR_CUDA_LAUNCH_CHECK("shared_attn launch");
   if (want_mass) {
     attn_mass_kernel<<<dim3(p->heads, p->batch), 256, 0, stream>>>(kp.mass_ws, 2 * pairs * kQT, p->s_q, kp.n_chunks, p->heads, p->chunk_mass);
     IR_CUDA_LAUNCH_CHECK("attn_mass launch");
   }
   if (n_splits > 1) {
-    attn_combine_kernel<<<dim3(2 * pairs, p->heads, p->batch), 128, 0, stream>>>(kp.part_o, kp.part_ml, n_splits, 2 * pairs, p->heads,
-                                                                                 p->s_q, kp.out, kp.out_stride);
+    IR_LAUNCH(attn_combine_kernel, dim3(2 * pairs, p->heads, p->batch), 128, 0, stream, kp.part_o, kp.part_ml, n_splits, 2 * pairs, p->heads,
+              p->s_q, kp.out, kp.out_stride);
     IR_CUDA_LAUNCH_CHECK("attn_combine launch");
   }
   return 0;

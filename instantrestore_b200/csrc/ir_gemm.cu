@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // set-up above overlapped the previous kernel's tail; no global access before this point
 
   const int mt = blockIdx.x;
   const int nt = blockIdx.y;
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
   // ------------------------------------------------------------------ epilogue (all 128 threads, thread == row)
   mbar_wait(accum_bar, 0);
   tc_fence_after();
+  pdl_launch_dependents();    // only the epilogue is left: the next kernel may set itself up
 
   const int row = warp * 32 + lane;
   const long grow = static_cast<long>(mt) * kBM + row;
@@ -588,6 +590,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -661,6 +664,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int ms = tile / n_tiles_n, nt = tile - ms * n_tiles_n;
       const int as = local & 1;
+      if (tile + static_cast<int>(gridDim.x) >= total_tiles) pdl_launch_dependents();   // this CTA's last tile
       // prefetch this thread's residual values while the tile is still being accumulated: a short-K tile would
       // otherwise pay one HBM round trip per 32-column chunk after the accumulator is ready
       constexpr int kMaxChunks = (BN == 160 ? 3 : (BN / 2 + 31) / 32);
@@ -793,6 +797,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
   cluster_sync_all();                           // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -864,6 +869,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++local) {
       const int mp = tile / n_tiles_n, nt = tile - mp * n_tiles_n;
       const int as = local & 1;
+      if (tile + tile_step >= total_tiles) pdl_launch_dependents();                     // this cluster's last tile
       const long grow = (static_cast<long>(mp) * 2 + rank) * kBM + row;
       const bool row_ok = grow < p.M;
       uint4 resid[RESID ? kChunks : 1][4];
@@ -927,7 +933,7 @@ static int launch_pair_r(const GemmKParams& kp, cudaStream_t stream) {
   }
   const long tiles = static_cast<long>((kp.m_tiles + 1) / 2) * (kp.N / BN);
   const int grid = 2 * static_cast<int>(tiles < 74 ? tiles : 74);
-  conv_gemm_pair_kernel<BN, STAGES, RESID><<<grid, kPersistThreads, smem, stream>>>(kp);
+  IR_LAUNCH((conv_gemm_pair_kernel<BN, STAGES, RESID>), grid, kPersistThreads, smem, stream, kp);   // cluster dims are compiled in
   IR_CUDA_LAUNCH_CHECK("conv_gemm_pair launch");
   return 0;
 }
@@ -1024,6 +1030,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
   if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -1113,6 +1120,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
       const int img = ms / per_img, rem = ms - img * per_img;
       const int h0 = (rem / tiles_w) * 2 + static_cast<int>(rank), w0 = (rem % tiles_w) << 7;
       const int as = local & 1;
+      if (tile + tile_step >= total_tiles) pdl_launch_dependents();                     // last tile of this CTA / pair
       const long grow0 = (static_cast<long>(img) * p.img_h + h0) * p.img_w + w0 + row;
       uint4 resid[RESID ? MSUB : 1][RESID ? kChunks : 1][4];
       if (RESID) {
@@ -1169,24 +1177,9 @@ static int launch_halo_r(const GemmKParams& kp, cudaStream_t stream) {
     attr_done = true;
   }
   const long tiles = static_cast<long>(kp.bn) * (kp.img_h / 2) * (kp.img_w / 128) * (kp.N / BN);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(kPersistThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  if (PAIR) {
-    cfg.gridDim = dim3(2 * static_cast<unsigned>(tiles < 74 ? tiles : 74));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  } else {
-    cfg.gridDim = dim3(static_cast<unsigned>(tiles < 148 ? tiles : 148));
-  }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3_halo_kernel<BN, PAIR, RESID>, kp);
+  const unsigned grid = PAIR ? 2 * static_cast<unsigned>(tiles < 74 ? tiles : 74) : static_cast<unsigned>(tiles < 148 ? tiles : 148);
+  cudaError_t e = launch_kernel(conv3_halo_kernel<BN, PAIR, RESID>, dim3(grid), dim3(kPersistThreads), smem, stream,
+                                dim3(PAIR ? 2 : 1, 1, 1), kp);
   if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "conv3_halo launch: %s", cudaGetErrorString(e));
   IR_CUDA_LAUNCH_CHECK("conv3_halo launch");
   return 0;
@@ -1210,7 +1203,7 @@ static int launch_persistent_r(const GemmKParams& kp, cudaStream_t stream) {
   }
   const long tiles = static_cast<long>((kp.m_tiles + MSUB - 1) / MSUB) * ((kp.N + BN - 1) / BN);
   const int grid = static_cast<int>(tiles < 148 ? tiles : 148);
-  conv_gemm_persistent_kernel<BN, STAGES, MSUB, RESID><<<grid, kPersistThreads, smem, stream>>>(kp);
+  IR_LAUNCH((conv_gemm_persistent_kernel<BN, STAGES, MSUB, RESID>), grid, kPersistThreads, smem, stream, kp);
   IR_CUDA_LAUNCH_CHECK("conv_gemm_persistent launch");
   return 0;
 }
@@ -1233,25 +1226,8 @@ static int launch(const GemmKParams& kp, int m_tiles, cudaStream_t stream) {
     attr_done = true;
   }
   dim3 grid(m_tiles, (kp.N + BN - 1) / BN, kp.split);
-  if (kp.split == 1) {
-    conv_gemm_kernel<BN, STAGES><<<grid, 128, smem, stream>>>(kp);
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(128);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = kp.split;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, STAGES>, kp);
-    if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "conv_gemm cluster launch (split %d): %s", kp.split, cudaGetErrorString(e));
-  }
+  cudaError_t e = launch_kernel(conv_gemm_kernel<BN, STAGES>, grid, dim3(128), smem, stream, dim3(1, 1, kp.split), kp);
+  if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "conv_gemm launch (split %d): %s", kp.split, cudaGetErrorString(e));
   IR_CUDA_LAUNCH_CHECK("conv_gemm launch");
   return 0;
 }

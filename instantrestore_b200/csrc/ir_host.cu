@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -13,6 +14,14 @@ namespace ir {
 
 static thread_local char g_err[512] = "ok";
 static std::atomic<unsigned long long> g_launches{0};
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("IR_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

@@ -37,6 +37,39 @@ struct PerDeviceOnce {
   }
 };
 
+// IR_PDL=0 in the environment switches programmatic dependent launch off (A-B measurement). Read once.
+bool pdl_enabled();
+
+// Kernel launch with an optional thread-block cluster and the programmatic-stream-serialization attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, dim3 cluster,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster.x * cluster.y * cluster.z > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster.x;
+    attr[n].val.clusterDim.y = cluster.y;
+    attr[n].val.clusterDim.z = cluster.z;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define IR_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)ir::launch_kernel(kernel, dim3(grid), dim3(block), smem, stream, dim3(1, 1, 1), __VA_ARGS__)
+
 #define IR_CUDA_LAUNCH_CHECK(what)                                                      \
   do {                                                                                  \
     ir::count_launch();                                                                 \

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256) colstats_kernel(const __half* __restrict_
                                                        int s_own, const __half* __restrict__ v_ref, int ref_stride,
                                                        int ref_col_off, int n_ref, int s_ref, int channels, int slabs,
                                                        float2* __restrict__ ws) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[2][32][64 + 1];
   const int cb = blockIdx.x, slab = blockIdx.y;
   const int chunk = blockIdx.z % (1 + n_ref), b = blockIdx.z / (1 + n_ref);
@@ -105,6 +107,8 @@ __device__ __forceinline__ void colstats_merge(const float2* __restrict__ ws, si
 __global__ void adain_finalize_kernel(const float2* __restrict__ ws, int n_ref, int channels, int slabs, int s_own,
                                       int s_ref, float eps, float* __restrict__ scale, float* __restrict__ shift,
                                       int total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = i % channels;
@@ -126,6 +130,8 @@ __global__ void adain_finalize_kernel(const float2* __restrict__ ws, int n_ref, 
 __global__ void adain_from_partials_kernel(const float2* __restrict__ own_partial, const float2* __restrict__ ref_partial,
                                            int n_ref, int channels, int s_own, int s_ref, float eps,
                                            float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float2 style[32];
   const int c = blockIdx.x * 32 + threadIdx.x, k = threadIdx.y, b = blockIdx.y;
   const int rows = k == 0 ? s_own : s_ref;
@@ -161,6 +167,8 @@ __global__ void adain_from_partials_kernel(const float2* __restrict__ own_partia
 __global__ void __launch_bounds__(256) concat_kernel(const __half* __restrict__ hidden, const __half* __restrict__ skip,
                                                      int c_hidden, int c_skip, float bscale, int copy_skip,
                                                      __half* __restrict__ out, long rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c_tot = c_hidden + c_skip;
   const int vec_per_row = (copy_skip ? c_tot : c_hidden) >> 3;
   const long total = rows * vec_per_row;
@@ -197,6 +205,8 @@ __global__ void __launch_bounds__(256) concat_kernel(const __half* __restrict__ 
 // grid = (c_skip/32, batch); block = 256 = 8 pixel groups x 32 channels. fp32 throughout.
 __global__ void __launch_bounds__(256) freeu_skip_kernel(const __half* __restrict__ skip, int h, int w, int c_skip,
                                                          int c_hidden, float s, __half* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][32][7];
   __shared__ float coef[32][7];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -253,6 +263,8 @@ __global__ void __launch_bounds__(256) freeu_skip_kernel(const __half* __restric
 // ------------------------------------------------------------------------------------------------ upsample
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ out, int h,
                                                          int w, int c, long total_vec) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vec_per_px = c >> 3;
   const int ow = 2 * w, oh = 2 * h;
   for (long v = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; v < total_vec; v += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -270,6 +282,8 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restric
 // ------------------------------------------------------------------------------------------------ latents
 __global__ void latent_in_kernel(const float* __restrict__ x, const float* __restrict__ noise, float a, float s,
                                  __half* __restrict__ out, int c, int hw, int c_pad, long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
   const int ch = static_cast<int>(i % c_pad);
@@ -286,6 +300,8 @@ __global__ void latent_in_kernel(const float* __restrict__ x, const float* __res
 __global__ void latent_out_kernel(const __half* __restrict__ eps, int eps_stride, const float* __restrict__ x,
                                   const float* __restrict__ noise, float a, float s, float* __restrict__ out, int c,
                                   int hw, long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;  // NCHW index
   if (i >= total) return;
   const int p = static_cast<int>(i % hw);
@@ -300,6 +316,8 @@ __global__ void latent_out_kernel(const __half* __restrict__ eps, int eps_stride
 // ------------------------------------------------------------------------------------------------ VAE helpers
 // In-place row softmax, one CTA (256 threads) per row; the row (<= 8192 fp16) is held in registers between passes.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, int cols, int row_stride, float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   __shared__ float bc;
   __half* xr = x + static_cast<size_t>(blockIdx.x) * row_stride;
@@ -372,6 +390,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
 
 // Row softmax for rows longer than 8192 columns: three passes over global memory (max, sum, write).
 __global__ void __launch_bounds__(256) softmax_rows_long_kernel(__half* __restrict__ x, int cols, int row_stride, float scale_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
   __shared__ float bc;
   __half* xr = x + static_cast<size_t>(blockIdx.x) * row_stride;
@@ -437,6 +457,8 @@ __global__ void __launch_bounds__(256) softmax_rows_long_kernel(__half* __restri
 
 template <typename T>
 __global__ void image_in_kernel(const T* __restrict__ x, __half* __restrict__ out, int c, int hw, int c_pad, long total_px) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one thread per pixel: reads c planes (coalesced across threads), writes c_pad halfs (16-byte stores)
   const long px = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
   if (px >= total_px) return;
@@ -456,6 +478,8 @@ __global__ void image_in_kernel(const T* __restrict__ x, __half* __restrict__ ou
 template <typename T>
 __global__ void image_out_kernel(const __half* __restrict__ y, int stride, float lo, float hi, T* __restrict__ out, int c,
                                  int hw, long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;   // NCHW index
   if (i >= total) return;
   const int p = static_cast<int>(i % hw);
@@ -468,6 +492,8 @@ __global__ void image_out_kernel(const __half* __restrict__ y, int stride, float
 
 __global__ void vae_sample_kernel(const __half* __restrict__ mom, int stride, const float* __restrict__ eps, float scale,
                                   float* __restrict__ out, int c, int hw, long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;   // NCHW index
   if (i >= total) return;
   const int p = static_cast<int>(i % hw);
@@ -523,7 +549,7 @@ extern "C" int ir_adain_coeffs(const ir_adain_coeffs_params* p, ir_stream_t stre
       return set_error(IR_ERR_SHAPE, "ir_adain_coeffs: slab moments need s_own %% 32 == 0, s_ref %% 32 == 0, n_ref <= 31 (s_own=%d s_ref=%d n_ref=%d)", p->s_own, p->s_ref, p->n_ref);
     if ((reinterpret_cast<uintptr_t>(p->own_partial) | reinterpret_cast<uintptr_t>(p->ref_partial)) & 7)
       return set_error(IR_ERR_ALIGN, "ir_adain_coeffs: partial pointers must be 8-byte aligned");
-    adain_from_partials_kernel<<<dim3(p->channels / 32, p->batch), dim3(32, 1 + p->n_ref), 0, static_cast<cudaStream_t>(stream_)>>>(
+    IR_LAUNCH(adain_from_partials_kernel, dim3(p->channels / 32, p->batch), dim3(32, 1 + p->n_ref), 0, static_cast<cudaStream_t>(stream_), 
         static_cast<const float2*>(p->own_partial), static_cast<const float2*>(p->ref_partial), p->n_ref, p->channels, p->s_own, p->s_ref,
         p->eps, p->scale, p->shift);
     IR_CUDA_LAUNCH_CHECK("adain_from_partials launch");
@@ -536,12 +562,12 @@ extern "C" int ir_adain_coeffs(const ir_adain_coeffs_params* p, ir_stream_t stre
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int slabs = adain_slabs(p->batch, p->n_ref, p->channels, p->s_own < p->s_ref ? p->s_own : p->s_ref);
   dim3 grid(p->channels / 64, slabs, (1 + p->n_ref) * p->batch);
-  colstats_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(p->v_own), p->own_row_stride, p->v_col_off, p->s_own,
+  IR_LAUNCH(colstats_kernel, grid, 256, 0, stream, static_cast<const __half*>(p->v_own), p->own_row_stride, p->v_col_off, p->s_own,
                                             static_cast<const __half*>(p->v_ref), p->ref_row_stride, p->ref_col_off, p->n_ref,
                                             p->s_ref, p->channels, slabs, static_cast<float2*>(p->workspace));
   IR_CUDA_LAUNCH_CHECK("colstats launch");
   const int total = p->batch * p->n_ref * p->channels;
-  adain_finalize_kernel<<<(total + 127) / 128, 128, 0, stream>>>(static_cast<const float2*>(p->workspace), p->n_ref, p->channels,
+  IR_LAUNCH(adain_finalize_kernel, (total + 127) / 128, 128, 0, stream, static_cast<const float2*>(p->workspace), p->n_ref, p->channels,
                                                                  slabs, p->s_own, p->s_ref, p->eps, p->scale, p->shift, total);
   IR_CUDA_LAUNCH_CHECK("adain_finalize launch");
   return 0;
@@ -558,13 +584,13 @@ extern "C" int ir_concat_freeu(const ir_concat_freeu_params* p, ir_stream_t stre
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long rows = static_cast<long>(p->batch) * p->h * p->w;
   const long total = rows * ((filt ? p->c_hidden : p->c_hidden + p->c_skip) >> 3);
-  concat_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __half*>(p->hidden), static_cast<const __half*>(p->skip),
+  IR_LAUNCH(concat_kernel, grid_for(total, 256), 256, 0, stream, static_cast<const __half*>(p->hidden), static_cast<const __half*>(p->skip),
                                                           p->c_hidden, p->c_skip, p->backbone_scale, filt ? 0 : 1,
                                                           static_cast<__half*>(p->out), rows);
   IR_CUDA_LAUNCH_CHECK("concat launch");
   if (filt) {
     dim3 grid(p->c_skip / 32, p->batch);
-    freeu_skip_kernel<<<grid, 256, 0, stream>>>(static_cast<const __half*>(p->skip), p->h, p->w, p->c_skip, p->c_hidden,
+    IR_LAUNCH(freeu_skip_kernel, grid, 256, 0, stream, static_cast<const __half*>(p->skip), p->h, p->w, p->c_skip, p->c_hidden,
                                                 p->skip_scale, static_cast<__half*>(p->out));
     IR_CUDA_LAUNCH_CHECK("freeu_skip launch");
   }
@@ -577,7 +603,7 @@ extern "C" int ir_upsample_nearest2x(const void* x, void* out, int batch, int h,
   if (int rc = check_arch()) return rc;
   if (c % 8 != 0 || batch <= 0 || h <= 0 || w <= 0) return set_error(IR_ERR_SHAPE, "ir_upsample_nearest2x: c=%d", c);
   const long total_vec = static_cast<long>(batch) * 4 * h * w * (c >> 3);
-  upsample2x_kernel<<<grid_for(total_vec, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+  IR_LAUNCH(upsample2x_kernel, grid_for(total_vec, 256), 256, 0, static_cast<cudaStream_t>(stream_), 
       static_cast<const __half*>(x), static_cast<__half*>(out), h, w, c, total_vec);
   IR_CUDA_LAUNCH_CHECK("upsample launch");
   return 0;
@@ -590,7 +616,7 @@ extern "C" int ir_latent_in(const float* x, const float* noise, float a, float s
   if (int rc = check_arch()) return rc;
   if (c_pad < c || c_pad % 8 != 0) return set_error(IR_ERR_SHAPE, "ir_latent_in: c_pad=%d", c_pad);
   const long total = static_cast<long>(batch) * hw * c_pad;
-  latent_in_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+  IR_LAUNCH(latent_in_kernel, static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_), 
       x, noise, a, s, static_cast<__half*>(out), c, hw, c_pad, total);
   IR_CUDA_LAUNCH_CHECK("latent_in launch");
   return 0;
@@ -602,7 +628,7 @@ extern "C" int ir_latent_out(const void* eps, int eps_row_stride, const float* x
   if (!eps || !x || !out || a == 0.f) return set_error(IR_ERR_ARG, "ir_latent_out: NULL argument");
   if (int rc = check_arch()) return rc;
   const long total = static_cast<long>(batch) * c * hw;
-  latent_out_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+  IR_LAUNCH(latent_out_kernel, static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_), 
       static_cast<const __half*>(eps), eps_row_stride, x, noise, a, s, out, c, hw, total);
   IR_CUDA_LAUNCH_CHECK("latent_out launch");
   return 0;
@@ -616,10 +642,10 @@ extern "C" int ir_softmax_rows(void* x, int rows, int cols, int row_stride, floa
     return set_error(IR_ERR_SHAPE, "ir_softmax_rows: rows=%d cols=%d stride=%d (cols %% 8 == 0)", rows, cols, row_stride);
   if (reinterpret_cast<uintptr_t>(x) & 15) return set_error(IR_ERR_ALIGN, "ir_softmax_rows: pointer not 16-byte aligned");
   if (cols <= 8192)
-    softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<__half*>(x), cols, row_stride,
+    IR_LAUNCH(softmax_rows_kernel, rows, 256, 0, static_cast<cudaStream_t>(stream_), static_cast<__half*>(x), cols, row_stride,
                                                                               scale * 1.4426950408889634f);
   else
-    softmax_rows_long_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<__half*>(x), cols, row_stride,
+    IR_LAUNCH(softmax_rows_long_kernel, rows, 256, 0, static_cast<cudaStream_t>(stream_), static_cast<__half*>(x), cols, row_stride,
                                                                                    scale * 1.4426950408889634f);
   IR_CUDA_LAUNCH_CHECK("softmax_rows launch");
   return 0;
@@ -633,8 +659,8 @@ extern "C" int ir_image_in(const void* x, int x_is_fp32, void* out, int batch, i
   const long total_px = static_cast<long>(batch) * hw;
   const int blocks = static_cast<int>((total_px + 255) / 256);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (x_is_fp32) image_in_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<__half*>(out), c, hw, c_pad, total_px);
-  else image_in_kernel<__half><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(x), static_cast<__half*>(out), c, hw, c_pad, total_px);
+  if (x_is_fp32) IR_LAUNCH(image_in_kernel<float>, blocks, 256, 0, stream, static_cast<const float*>(x), static_cast<__half*>(out), c, hw, c_pad, total_px);
+  else IR_LAUNCH(image_in_kernel<__half>, blocks, 256, 0, stream, static_cast<const __half*>(x), static_cast<__half*>(out), c, hw, c_pad, total_px);
   IR_CUDA_LAUNCH_CHECK("image_in launch");
   return 0;
 }
@@ -648,8 +674,8 @@ extern "C" int ir_image_out(const void* y, int y_row_stride, float lo, float hi,
   const long total = static_cast<long>(batch) * c * hw;
   const int blocks = static_cast<int>((total + 255) / 256);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (out_is_fp32) image_out_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(y), y_row_stride, lo, hi, static_cast<float*>(out), c, hw, total);
-  else image_out_kernel<__half><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(y), y_row_stride, lo, hi, static_cast<__half*>(out), c, hw, total);
+  if (out_is_fp32) IR_LAUNCH(image_out_kernel<float>, blocks, 256, 0, stream, static_cast<const __half*>(y), y_row_stride, lo, hi, static_cast<float*>(out), c, hw, total);
+  else IR_LAUNCH(image_out_kernel<__half>, blocks, 256, 0, stream, static_cast<const __half*>(y), y_row_stride, lo, hi, static_cast<__half*>(out), c, hw, total);
   IR_CUDA_LAUNCH_CHECK("image_out launch");
   return 0;
 }
@@ -661,7 +687,7 @@ extern "C" int ir_vae_sample(const void* moments, int m_row_stride, const float*
   if (int rc = check_arch()) return rc;
   if (m_row_stride < 2 * c || batch <= 0 || c <= 0 || hw <= 0) return set_error(IR_ERR_SHAPE, "ir_vae_sample: c=%d stride=%d", c, m_row_stride);
   const long total = static_cast<long>(batch) * c * hw;
-  vae_sample_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+  IR_LAUNCH(vae_sample_kernel, static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_), 
       static_cast<const __half*>(moments), m_row_stride, eps, scale, out, c, hw, total);
   IR_CUDA_LAUNCH_CHECK("vae_sample launch");
   return 0;

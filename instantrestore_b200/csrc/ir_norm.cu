@@ -43,6 +43,8 @@ __device__ __forceinline__ void merge_moments(float& n_a, float& mean_a, float& 
 // partial[((b * slabs + slab) * groups + g)] = (mean, M2); the element count follows from the slab index.
 __global__ void __launch_bounds__(256) gn_partial_kernel(const __half* __restrict__ x, int row_stride, int hw, int channels,
                                                          int groups, int rows_per_slab, float2* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];                 // [row group][channels][2]: per-channel (sum, sumsq) of this slab
   const int slab = blockIdx.x, b = blockIdx.y, slabs = gridDim.x;
   const int vpr = channels >> 3;                // 16-byte vectors per row
@@ -124,6 +126,8 @@ __device__ __forceinline__ void merge_opt(float& n_a, float& mean_a, float& m2_a
 __global__ void __launch_bounds__(256) gn_merge_kernel(const float2* __restrict__ partial, int groups, int slabs,
                                                        int rows_per_slab, int hw, int cpg, float eps,
                                                        float2* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_n[8], s_mean[8], s_m2[8];
   const int g = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -166,6 +170,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int silu, __half* __restrict__ out, int out_stride) {
   const int b = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
   const int cpg = channels / groups;
   const int vpr = channels >> 3;
   const int lanes = vpr < 256 ? vpr : 256;
@@ -244,6 +250,8 @@ __global__ void __launch_bounds__(256) gn_fused_kernel(const __half* __restrict_
   __shared__ float2 s_part[64];          // this CTA's (mean, M2) per group of the slice (read by the cluster)
   __shared__ float2 s_stat[64];          // merged (mean, rstd) per group of the slice
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const int V = slice_ch >> 3;                    // 16-byte vectors per row of the slice
   const int rgroups = 256 / V;                    // rows in flight per sweep
   const int v = tid % V, rg = tid / V;
@@ -371,6 +379,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
                                                         float eps, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __half* __restrict__ out,
                                                         int out_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -440,8 +450,8 @@ int ir::launch_gn_partial(const void* x, int row_stride, int batch, int hw, int 
   const int slabs = (hw + rows_per_slab - 1) / rows_per_slab;
   const int vpr = channels >> 3;
   const int rgroups = vpr < 256 ? 256 / vpr : 1;
-  gn_partial_kernel<<<dim3(slabs, batch), 256, static_cast<size_t>(rgroups) * channels * 2 * sizeof(float), stream>>>(
-      static_cast<const __half*>(x), row_stride, hw, channels, groups, rows_per_slab, static_cast<float2*>(partial));
+  IR_LAUNCH(gn_partial_kernel, dim3(slabs, batch), 256, static_cast<size_t>(rgroups) * channels * 2 * sizeof(float), stream,
+            static_cast<const __half*>(x), row_stride, hw, channels, groups, rows_per_slab, static_cast<float2*>(partial));
   IR_CUDA_LAUNCH_CHECK("gn_partial launch");
   return 0;
 }
@@ -500,21 +510,10 @@ extern "C" int ir_groupnorm_fused_supported(int batch, int hw, int channels, int
 
 template <int KMAX>
 static cudaError_t launch_gn_fused(const ir_groupnorm_params* p, const GnFusedPlan& pl, cudaStream_t stream) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(pl.cl, p->channels / pl.slice_ch, p->batch);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = pl.cl;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pl.cl > 1 ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, ir::gn_fused_kernel<KMAX>, static_cast<const __half*>(p->x), p->x_row_stride, p->hw,
-                            p->channels, p->groups, pl.slice_ch, pl.rows, pl.cl, p->eps, p->gamma, p->beta, p->silu,
-                            static_cast<__half*>(p->out), p->out_row_stride);
+  return ir::launch_kernel(ir::gn_fused_kernel<KMAX>, dim3(pl.cl, p->channels / pl.slice_ch, p->batch), dim3(256), 0, stream,
+                       dim3(pl.cl, 1, 1), static_cast<const __half*>(p->x), p->x_row_stride, p->hw,
+                       p->channels, p->groups, pl.slice_ch, pl.rows, pl.cl, p->eps, p->gamma, p->beta, p->silu,
+                       static_cast<__half*>(p->out), p->out_row_stride);
 }
 
 extern "C" size_t ir_groupnorm_workspace_bytes(int batch, int groups) {
@@ -560,7 +559,7 @@ extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
     gn_plan(p->batch, p->hw, &slabs, &rps);
     if (int rc = launch_gn_partial(p->x, p->x_row_stride, p->batch, p->hw, p->channels, p->groups, rps, partial, stream)) return rc;
   }
-  gn_merge_kernel<<<dim3(p->groups, p->batch), 256, 0, stream>>>(partial, p->groups, slabs, rps, p->hw, p->channels / p->groups, p->eps, stats);
+  IR_LAUNCH(gn_merge_kernel, dim3(p->groups, p->batch), 256, 0, stream, partial, p->groups, slabs, rps, p->hw, p->channels / p->groups, p->eps, stats);
   IR_CUDA_LAUNCH_CHECK("gn_merge launch");
   // apply: ~8 CTAs per SM in total, >= 4 * rgroups rows per CTA so the unrolled loop is used
   int row_blocks = (148 * 8 + p->batch - 1) / p->batch;
@@ -568,9 +567,9 @@ extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
   int rpb = (p->hw + row_blocks - 1) / row_blocks;
   if (rpb < min_rows) rpb = min_rows;
   row_blocks = (p->hw + rpb - 1) / rpb;
-  gn_apply_kernel<<<dim3(row_blocks, p->batch), 256, 0, stream>>>(
-      static_cast<const __half*>(p->x), p->x_row_stride, p->hw, p->channels, p->groups, rpb, stats, p->gamma, p->beta, p->silu,
-      static_cast<__half*>(p->out), p->out_row_stride);
+  IR_LAUNCH(gn_apply_kernel, dim3(row_blocks, p->batch), 256, 0, stream,
+            static_cast<const __half*>(p->x), p->x_row_stride, p->hw, p->channels, p->groups, rpb, stats, p->gamma, p->beta, p->silu,
+            static_cast<__half*>(p->out), p->out_row_stride);
   IR_CUDA_LAUNCH_CHECK("gn_apply launch");
   return 0;
 }
@@ -590,11 +589,11 @@ extern "C" int ir_layernorm(const ir_layernorm_params* p, ir_stream_t stream_) {
   const __half* xp = static_cast<const __half*>(p->x);
   __half* op = static_cast<__half*>(p->out);
   if (p->channels <= 512)
-    layernorm_kernel<2><<<blocks, 256, 0, stream>>>(xp, p->x_row_stride, p->rows, p->channels, p->eps, p->gamma, p->beta, op, p->out_row_stride);
+    IR_LAUNCH(layernorm_kernel<2>, blocks, 256, 0, stream, xp, p->x_row_stride, p->rows, p->channels, p->eps, p->gamma, p->beta, op, p->out_row_stride);
   else if (p->channels <= 1280)
-    layernorm_kernel<5><<<blocks, 256, 0, stream>>>(xp, p->x_row_stride, p->rows, p->channels, p->eps, p->gamma, p->beta, op, p->out_row_stride);
+    IR_LAUNCH(layernorm_kernel<5>, blocks, 256, 0, stream, xp, p->x_row_stride, p->rows, p->channels, p->eps, p->gamma, p->beta, op, p->out_row_stride);
   else
-    layernorm_kernel<10><<<blocks, 256, 0, stream>>>(xp, p->x_row_stride, p->rows, p->channels, p->eps, p->gamma, p->beta, op, p->out_row_stride);
+    IR_LAUNCH(layernorm_kernel<10>, blocks, 256, 0, stream, xp, p->x_row_stride, p->rows, p->channels, p->eps, p->gamma, p->beta, op, p->out_row_stride);
   IR_CUDA_LAUNCH_CHECK("layernorm launch");
   return 0;
 }

@@ -270,6 +270,16 @@ __device__ __forceinline__ void dsmem_st_f4(uint32_t addr, float a, float b, flo
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Programmatic dependent launch (every launch of the step carries cudaLaunchAttributeProgrammaticStreamSerialization,
+// also inside the captured CUDA graph): the NEXT kernel of the stream may start its prologue (barrier init, TMEM
+// allocation, descriptor prefetch, block scheduling) once every CTA of this one has executed launch_dependents; it
+// blocks in pdl_wait() until this grid has completed and its writes are visible. Every kernel executes pdl_wait()
+// before its first global-memory access (reads of predecessor outputs AND writes to buffers a predecessor may still
+// read), so completion is transitive along the stream. Heavy kernels trigger late (last-tile epilogue): dependents that
+// are resident but blocked hold SM resources other streams could use. No-ops when launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // register reallocation between warp roles (warp-collective; counts are multiples of 8)
 template <int N>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }

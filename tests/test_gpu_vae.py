@@ -279,15 +279,17 @@ def test_predictor_entry_on_a_synthetic_checkpoint(tmp_path):
     err = float(np.linalg.norm((got.astype(np.float64) - gold_u8) / 127.5) / np.linalg.norm(gold_u8 / 127.5 - 1.0))
     print(f"Predictor vs oracle (uint8 images): rel-L2 {err:.3e}, max |d| {diff.max()} levels, mean |d| {diff.mean():.3f} levels")
     assert err <= 6e-3 and diff.mean() <= 0.6
-    # pipelined entry: 5 requests, 3 in flight (uint8 staging, GPU transform / packing); results come back in order and
-    # differ from the single call only through the fresh normal draws of every forward
-    many = list(pred.predict_many([(inp, refs), (tgt, refs), (inp, refs), (tgt, refs), (inp, refs)], in_flight=3))
-    assert len(many) == 5 and all(m.size == (512, 512) for m in many)
-    d_same = np.abs(np.asarray(many[0]).astype(np.int32) - got.astype(np.int32)).mean()
-    d_other = np.abs(np.asarray(many[1]).astype(np.int32) - got.astype(np.int32)).mean()
-    d_again = np.abs(np.asarray(many[4]).astype(np.int32) - np.asarray(many[0]).astype(np.int32)).mean()
-    print(f"predict_many: same request {d_same:.2f} / {d_again:.2f} levels apart (noise draws), different request {d_other:.2f}")
-    assert d_same < d_other and d_again < d_other
+    # pipelined entry: 5 requests, 3 in flight (uint8 staging through pinned memory, GPU transform / packing). With the
+    # pipeline's noise generator re-seeded, the results are bit-identical to one request at a time (no aliasing between
+    # the in-flight slots), and the first one reproduces the single predict() call above.
+    reqs = [(inp, refs), (tgt, refs), (inp, refs), (tgt, refs), (inp, refs)]
+    pred.net._gen.manual_seed(0)
+    many = [np.asarray(m) for m in pred.predict_many(reqs, in_flight=3)]
+    pred.net._gen.manual_seed(0)
+    seq = [np.asarray(m) for m in pred.predict_many(reqs, in_flight=1)]
+    assert len(many) == 5 and all(m.shape == (512, 512, 3) for m in many)
+    assert np.array_equal(many[0], got)
+    assert all(np.array_equal(a, b) for a, b in zip(many, seq))
     # calc_attn_probs=True (test.py:93-108): one dense map per shared layer, (B, H, S, N_ref * S), rows sum to 1
     img2, _, probs = pred.predict(inp, refs, calc_attn_probs=True)
     assert len(probs) == 9 and probs[0].shape == (1, 4, 256, 2 * 256) and probs[-1].shape == (1, 1, 4096, 2 * 4096)

@@ -15,7 +15,9 @@ run() {  # name tool timeout pytest-args...
   cat $OUT/${TAG}_san_$n.txt
 }
 run norms_memcheck memcheck 900 tests/test_gpu_kernels.py -k "$SMALL"
-run norms_racecheck racecheck 900 tests/test_gpu_kernels.py -k "$SMALL"
+# racecheck does not model tcgen05.alloc's shared-memory write (it reports it against the read that follows the barrier +
+# tcgen05 fences), so the GEMM-launching tests are left out of this pass
+run norms_racecheck racecheck 900 tests/test_gpu_kernels.py -k "($SMALL) and not gemm_epilogue and not from_epilogue"
 run norms_synccheck synccheck 900 tests/test_gpu_kernels.py -k "groupnorm_single_launch"
 run gemm_memcheck memcheck 1200 tests/test_gpu_kernels.py -k "test_linear or test_geglu or test_conv3x3 or pass_a"
 run attn_memcheck memcheck 900 tests/test_gpu_kernels.py -k "shared_attention and not large"
