@@ -41,6 +41,11 @@ const char* ir_last_error_string(void);
 int ir_version(void);
 /* 0 when the current device is a B200-class (sm_100) GPU, IR_ERR_ARCH / IR_ERR_CUDA otherwise. */
 int ir_check_device(void);
+/* Programmatic dependent launch (cudaLaunchAttributeProgrammaticStreamSerialization) for every kernel launched or
+ * captured after the call: each kernel runs its set-up before griddepcontrol.wait, so consecutive kernels of one
+ * stream overlap tail and prologue. Shortens a single request's critical path; off by default because blocked
+ * dependents cost throughput when several requests are in flight. Returns the previous setting. Env: IR_PDL=1. */
+int ir_set_pdl(int enabled);
 /* Number of kernel launches issued (or captured into a CUDA graph) through this library since load. */
 unsigned long long ir_launch_count(void);
 

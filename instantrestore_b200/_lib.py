@@ -17,7 +17,7 @@ LIB_PATH = _PKG / "libinstantrestore_b200.so"
 IR_ACT_NONE, IR_ACT_GEGLU, IR_ACT_SILU = 0, 1, 2
 
 EXPORTED_SYMBOLS = [
-    "ir_last_error_string", "ir_version", "ir_check_device", "ir_launch_count", "ir_conv_gemm", "ir_shared_attn_fwd",
+    "ir_last_error_string", "ir_version", "ir_check_device", "ir_set_pdl", "ir_launch_count", "ir_conv_gemm", "ir_shared_attn_fwd",
     "ir_shared_attn_workspace_bytes",
     "ir_groupnorm", "ir_groupnorm_workspace_bytes", "ir_groupnorm_fused_supported", "ir_layernorm", "ir_adain_coeffs", "ir_adain_workspace_bytes",
     "ir_concat_freeu", "ir_upsample_nearest2x", "ir_latent_in", "ir_latent_out",
@@ -136,6 +136,11 @@ def load() -> C.CDLL:
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"{what} failed ({rc}): {load().ir_last_error_string().decode()}")
+
+
+def set_pdl(enabled: bool) -> bool:
+    """Programmatic dependent launch for the launches / graph captures that follow; returns the previous setting."""
+    return bool(load().ir_set_pdl(int(bool(enabled))))
 
 
 def launch_count() -> int:

@@ -37,7 +37,7 @@ struct PerDeviceOnce {
   }
 };
 
-// IR_PDL=0 in the environment switches programmatic dependent launch off (A-B measurement). Read once.
+// Programmatic dependent launch for the launches that follow (ir_set_pdl / IR_PDL=1; default off, see ir_host.cu).
 bool pdl_enabled();
 
 // Kernel launch with an optional thread-block cluster and the programmatic-stream-serialization attribute.
