@@ -40,18 +40,22 @@ def main():
     for k in KEYS:
         if k in d:
             lines.append(f"{k} = {d[k][0]} {d[k][1]}")
+    def num(k):
+        v, u = d[k]
+        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+    dur_us = float(d["gpu__time_duration.sum"][0].replace(",", "")) * {"us": 1, "ms": 1e3, "ns": 1e-3, "s": 1e6}.get(d["gpu__time_duration.sum"][1], 1)
+    dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+    lines.append(f"derived: dram read+write = {dram / 1e6:.2f} MB per launch, {dram / dur_us / 1e3:.1f} GB/s achieved under ncu "
+                 f"(of the measured 6545 GB/s copy peak: {dram / dur_us / 1e3 / 6545:.3f})")
     out.write_text("\n".join(lines) + "\n")
     print("\n".join(lines))
     if len(sys.argv) > 3:
         tp = out.parent / "ncu_traffic.json"
         db = json.loads(tp.read_text()) if tp.exists() else {}
 
-        def num(k):
-            v, u = d[k]
-            return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         db[sys.argv[3]] = {
             "dram_read_bytes": num("dram__bytes_read.sum"), "dram_write_bytes": num("dram__bytes_write.sum"),
-            "duration_us_under_ncu": float(d["gpu__time_duration.sum"][0]) * {"us": 1, "ms": 1e3, "ns": 1e-3}.get(d["gpu__time_duration.sum"][1], 1),
+            "duration_us_under_ncu": dur_us, "dram_gbs_under_ncu": dram / dur_us / 1e3,
             "tensor_pipe_active_pct": float(d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"][0]),
             "l2_to_sm_bytes": num("l1tex__m_xbar2l1tex_read_bytes.sum") if "l1tex__m_xbar2l1tex_read_bytes.sum" in d else None,
             "report": str(out),
