@@ -295,6 +295,9 @@ def run_ours(a):
     # same engine structure from placeholder tensors at the same time, then ONE device-to-device broadcast per dtype
     # ships the prepared arena (no collective after this point)
     t0 = time.perf_counter()
+    if world > 1:   # N processes share the host cores: rank 0 (draws + prepares the checkpoint) keeps most of them, the
+        cores = os.cpu_count() or 1          # receivers only fold placeholder tensors
+        torch.set_num_threads(max(4, cores - 2 * (world - 1)) if rank == 0 else 2)
     sds = None
     if rank == 0:
         sds = [synthetic_unet_state_dict(seed=0, lora_rank=a.lora_rank), synthetic_unet_state_dict(seed=0)]
