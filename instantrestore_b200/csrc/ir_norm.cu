@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) gn_merge_kernel(const float2* __restrict_
 // fixed 8-channel vectors (its 16 affine coefficients live in registers) and walks the rows of its CTA's row range
 // with 4 sixteen-byte loads in flight: no per-element index math, no shared-memory lookups.
 // grid = (row blocks, batch).
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, int x_stride, int hw, int channels,
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __half* __restrict__ x, int x_stride, int hw, int channels,
                                                        int groups, int rows_per_block, const float2* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int silu, __half* __restrict__ out, int out_stride) {
@@ -207,14 +207,30 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
       return make_uint4(pack_half2(f[0], f[1]), pack_half2(f[2], f[3]), pack_half2(f[4], f[5]), pack_half2(f[6], f[7]));
     };
     int r = r0 + rg;
-    for (; r + 3 * rgroups < r1; r += 4 * rgroups) {
+    // software pipeline: the four loads of the NEXT sweep are in flight while this sweep runs its 64 MUFU ops and its
+    // stores (ncu r02h: long-scoreboard stalls 16 per issue, 0.65 of the copy bandwidth without it)
+    if (r + 3 * rgroups < r1) {
       uint4 u[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         u[k] = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r + k * rgroups) * x_stride + c0);
+      for (;;) {
+        const int rn = r + 4 * rgroups;
+        const bool more = rn + 3 * rgroups < r1;
+        uint4 nx[4];
+        if (more) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        *reinterpret_cast<uint4*>(ob + static_cast<size_t>(r + k * rgroups) * out_stride + c0) = apply8(u[k]);
+          for (int k = 0; k < 4; ++k)
+            nx[k] = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(rn + k * rgroups) * x_stride + c0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(ob + static_cast<size_t>(r + k * rgroups) * out_stride + c0) = apply8(u[k]);
+        r = rn;
+        if (!more) break;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = nx[k];
+      }
     }
     for (; r < r1; r += rgroups) {
       const uint4 u = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(r) * x_stride + c0);
@@ -561,8 +577,9 @@ extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
   }
   IR_LAUNCH(gn_merge_kernel, dim3(p->groups, p->batch), 256, 0, stream, partial, p->groups, slabs, rps, p->hw, p->channels / p->groups, p->eps, stats);
   IR_CUDA_LAUNCH_CHECK("gn_merge launch");
-  // apply: ~8 CTAs per SM in total, >= 4 * rgroups rows per CTA so the unrolled loop is used
-  int row_blocks = (148 * 8 + p->batch - 1) / p->batch;
+  // apply: one wave of 4 resident CTAs per SM (64 registers: two sweeps of four 16-byte loads per thread in flight),
+  // >= 4 * rgroups rows per CTA so the pipelined loop is used
+  int row_blocks = (148 * 4 + p->batch - 1) / p->batch;
   int min_rows = 4 * rgroups;
   int rpb = (p->hw + row_blocks - 1) / row_blocks;
   if (rpb < min_rows) rpb = min_rows;
