@@ -123,42 +123,63 @@ __global__ void adain_finalize_kernel(const float2* __restrict__ ws, int n_ref, 
 }
 
 // AdaIN affine from the 32-row slab moments the QKV GEMM epilogues wrote (ir_conv_gemm.col_partial): no pass over V.
-// grid = (channels / 32, batch), block = (32 channels, 1 + n_ref chunks): thread (c, k) merges the slabs of chunk k
-// (k = 0: the image's own V = the style; k >= 1: reference k - 1 = the content) for its channel in slab order (Chan, equal
-// counts), the style statistics go through shared memory, threads k >= 1 write scale / shift.
+// grid = (channels / 32, batch), block = (32 channels, `lanes` slab lanes, 1 + n_ref chunks): thread (c, l, k) merges
+// every lanes-th slab of chunk k (k = 0: the image's own V = the style; k >= 1: reference k - 1 = the content) for its
+// channel (Chan), lane 0 merges the lanes in fixed order, the style statistics go through shared memory, threads
+// (c, 0, k >= 1) write scale / shift. The serial chain is slabs / lanes merges (32 for 4096 tokens).
 //   own_partial [batch, s_own / 32, channels], ref_partial [batch, n_ref, s_ref / 32, channels]  (mean, M2)
-__global__ void adain_from_partials_kernel(const float2* __restrict__ own_partial, const float2* __restrict__ ref_partial,
-                                           int n_ref, int channels, int s_own, int s_ref, float eps,
-                                           float* __restrict__ scale, float* __restrict__ shift) {
+__global__ void __launch_bounds__(1024) adain_from_partials_kernel(const float2* __restrict__ own_partial,
+                                                                   const float2* __restrict__ ref_partial, int n_ref, int channels,
+                                                                   int s_own, int s_ref, float eps, float* __restrict__ scale,
+                                                                   float* __restrict__ shift) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float2 style[32];
-  const int c = blockIdx.x * 32 + threadIdx.x, k = threadIdx.y, b = blockIdx.y;
+  __shared__ float s_n[1024], s_mean[1024], s_m2[1024];
+  __shared__ float2 chunk_stat[32][32];          // [chunk][channel] (mean, std)
+  const int tx = threadIdx.x, lane = threadIdx.y, k = threadIdx.z, lanes = blockDim.y;
+  const int c = blockIdx.x * 32 + tx, b = blockIdx.y;
   const int rows = k == 0 ? s_own : s_ref;
   const int slabs = rows >> 5;
   const float2* src = (k == 0 ? own_partial + static_cast<size_t>(b) * slabs * channels
                               : ref_partial + (static_cast<size_t>(b) * n_ref + (k - 1)) * slabs * channels) + c;
-  float n_a = 32.f, mean_a = 0.f, m2_a = 0.f;
-  {
-    const float2 pm = __ldg(src);
-    mean_a = pm.x; m2_a = pm.y;
-  }
-  for (int sl = 1; sl < slabs; ++sl) {
-    const float2 pm = __ldg(src + static_cast<size_t>(sl) * channels);
-    const float n = n_a + 32.f, d = pm.x - mean_a, f = 32.f / n;
+  float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
+  auto merge = [&](float n_b, float mean_b, float m2_b) {
+    if (n_b <= 0.f) return;
+    if (n_a == 0.f) { n_a = n_b; mean_a = mean_b; m2_a = m2_b; return; }
+    const float n = n_a + n_b, d = mean_b - mean_a, f = __fdividef(n_b, n);
     mean_a = fmaf(d, f, mean_a);
-    m2_a = m2_a + pm.y + d * d * n_a * f;
+    m2_a = m2_a + m2_b + d * d * n_a * f;
     n_a = n;
+  };
+  int sl = lane;
+  for (; sl + 3 * lanes < slabs; sl += 4 * lanes) {          // four loads in flight ahead of the merge chain
+    float2 pm[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pm[j] = __ldg(src + static_cast<size_t>(sl + j * lanes) * channels);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) merge(32.f, pm[j].x, pm[j].y);
   }
-  const float sd = rows > 1 ? sqrtf(m2_a / (rows - 1)) : 0.f;      // unbiased, like torch.std
-  if (k == 0) style[threadIdx.x] = make_float2(mean_a, sd);
+  for (; sl < slabs; sl += lanes) {
+    const float2 pm = __ldg(src + static_cast<size_t>(sl) * channels);
+    merge(32.f, pm.x, pm.y);
+  }
+  const int slot = (k * lanes + lane) * 32 + tx;
+  s_n[slot] = n_a; s_mean[slot] = mean_a; s_m2[slot] = m2_a;
   __syncthreads();
-  if (k > 0) {
-    const float2 st = style[threadIdx.x];
-    const float a = (st.y + eps) / (sd + eps);
+  if (lane == 0) {
+    for (int l = 1; l < lanes; ++l) {                         // fixed order: deterministic
+      const int o = (k * lanes + l) * 32 + tx;
+      merge(s_n[o], s_mean[o], s_m2[o]);
+    }
+    chunk_stat[k][tx] = make_float2(mean_a, rows > 1 ? sqrtf(m2_a / (rows - 1)) : 0.f);   // unbiased, like torch.std
+  }
+  __syncthreads();
+  if (lane == 0 && k > 0) {
+    const float2 st = chunk_stat[0][tx], ct = chunk_stat[k][tx];
+    const float a = (st.y + eps) / (ct.y + eps);
     const size_t i = (static_cast<size_t>(b) * n_ref + (k - 1)) * channels + c;
     scale[i] = a;
-    shift[i] = st.x - mean_a * a;
+    shift[i] = st.x - ct.x * a;
   }
 }
 
@@ -549,7 +570,9 @@ extern "C" int ir_adain_coeffs(const ir_adain_coeffs_params* p, ir_stream_t stre
       return set_error(IR_ERR_SHAPE, "ir_adain_coeffs: slab moments need s_own %% 32 == 0, s_ref %% 32 == 0, n_ref <= 31 (s_own=%d s_ref=%d n_ref=%d)", p->s_own, p->s_ref, p->n_ref);
     if ((reinterpret_cast<uintptr_t>(p->own_partial) | reinterpret_cast<uintptr_t>(p->ref_partial)) & 7)
       return set_error(IR_ERR_ALIGN, "ir_adain_coeffs: partial pointers must be 8-byte aligned");
-    IR_LAUNCH(adain_from_partials_kernel, dim3(p->channels / 32, p->batch), dim3(32, 1 + p->n_ref), 0, static_cast<cudaStream_t>(stream_), 
+    const int chunks = 1 + p->n_ref;
+    const int lanes = chunks <= 8 ? 4 : (chunks <= 16 ? 2 : 1);
+    IR_LAUNCH(adain_from_partials_kernel, dim3(p->channels / 32, p->batch), dim3(32, lanes, chunks), 0, static_cast<cudaStream_t>(stream_), 
         static_cast<const float2*>(p->own_partial), static_cast<const float2*>(p->ref_partial), p->n_ref, p->channels, p->s_own, p->s_ref,
         p->eps, p->scale, p->shift);
     IR_CUDA_LAUNCH_CHECK("adain_from_partials launch");
