@@ -513,6 +513,10 @@ def run_ours(a):
         c2 = s2.stop()
         result["sustained"] = {"value": world * B * k_sus / (ms_sus * 1e-3), "unit": UNIT, "steps": k_sus,
                                "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / k_sus, "clocks": c2}
+    if extras and rank == 0:
+        # the reference-facing entry itself: Predictor.predict_many over PIL images (uint8 staging through pinned memory,
+        # Lanczos resize + crop + normalise on the GPU, the step, uint8 packing on the GPU, PIL images out), wall clock
+        result["e2e_predictor"] = predictor_e2e(eng, a, max(10, a.steps))
     if a.cached_refs and not a.latent_only and not a.no_graph:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         cache = eng.extract_reference_kv(dev_in[1], eps_ref=dev_in[3], noise_ref=dev_in[5])
@@ -559,6 +563,28 @@ def run_ours(a):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def predictor_e2e(eng, a, n_req):
+    import numpy as np
+    import torch
+    from PIL import Image
+    from instantrestore_b200.inference import Predictor
+    pred = Predictor.from_pipeline(eng, max_conditioning_images=a.n_ref)
+    rng = np.random.default_rng(0)
+    out = {"unit": UNIT, "requests": n_req, "requests_in_flight": 3,
+           "what": "Predictor.predict_many(PIL images) -> PIL images, wall clock on rank 0; identities_per_request = 1, n_ref = %d" % a.n_ref}
+    for tag, (w, h) in (("inputs_512x512", (512, 512)), ("inputs_1024x768_lanczos", (1024, 768))):
+        mk = lambda: Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+        reqs = [(mk(), [mk() for _ in range(a.n_ref)]) for _ in range(4)]
+        list(pred.predict_many(reqs[:3], in_flight=3))                      # warm-up: graph slots, coefficient tables
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = sum(1 for _ in pred.predict_many((reqs[i % 4] for i in range(n_req)), in_flight=3))
+        dt = time.perf_counter() - t0
+        out[tag] = {"value": n / dt, "ms_per_request": dt / n * 1e3, "h2d_bytes_per_request": (1 + a.n_ref) * w * h * 3,
+                    "d2h_bytes_per_request": 512 * 512 * 3}
+    return out
 
 
 def gpu_eager_baseline(sd_main, sd_ref, sd_vae, sd_ovae, cap, a, dev):

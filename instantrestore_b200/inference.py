@@ -172,6 +172,22 @@ class Predictor:
         self.pre = GpuPreprocessor(self.device)
         self._pinned: dict = {}
 
+    @classmethod
+    def from_pipeline(cls, net: RestorePipeline, max_conditioning_images: int = 4, cfg: Any = None) -> "Predictor":
+        """A Predictor around an already built RestorePipeline (no checkpoint file): what a serving process does after it
+        has loaded / received the weights once. Same `predict` / `predict_many` behaviour as the checkpoint constructor."""
+        from .preprocess import GpuPreprocessor
+        self = cls.__new__(cls)
+        self.cfg = cfg
+        self.device = net.dev
+        self.face_replace_model = SimpleNamespace(net=net, cfg=None if cfg is None else cfg.model)
+        self.max_conditioning_images = max_conditioning_images
+        net.noise_timesteps = [249]
+        self.dtype = torch.float16
+        self.pre = GpuPreprocessor(self.device)
+        self._pinned = {}
+        return self
+
     @property
     def net(self) -> RestorePipeline:
         return self.face_replace_model.net
