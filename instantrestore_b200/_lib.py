@@ -12,7 +12,7 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libinstantrestore_b200.so"
+LIB_PATH = Path(os.environ.get("IR_LIB_PATH", _PKG / "libinstantrestore_b200.so"))     # IR_LIB_PATH: A-B a previous build
 
 IR_ACT_NONE, IR_ACT_GEGLU, IR_ACT_SILU = 0, 1, 2
 

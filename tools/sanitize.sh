@@ -21,3 +21,5 @@ run norms_racecheck racecheck 900 tests/test_gpu_kernels.py -k "($SMALL) and not
 run norms_synccheck synccheck 900 tests/test_gpu_kernels.py -k "groupnorm_single_launch"
 run gemm_memcheck memcheck 1200 tests/test_gpu_kernels.py -k "test_linear or test_geglu or test_conv3x3 or pass_a"
 run attn_memcheck memcheck 900 tests/test_gpu_kernels.py -k "shared_attention and not large"
+run image_memcheck memcheck 900 tests/test_preprocess.py
+run pipeline_memcheck memcheck 1500 tests/test_gpu_pipeline.py -k "tiny_pipeline or processors_drive"
