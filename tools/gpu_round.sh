@@ -36,7 +36,7 @@ ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_launches.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
   wc -l $OUT/${TAG}_launches.csv ;;
-caps)
+caps|capsattn)
   # ncu --set full of the dominant kernels on micro-drivers; summarised on the box (reports are ~10 MB each and
   # gpurun_out is capped at 64 MiB), only the text summaries and ncu_traffic.json travel back
   cap() { n=$1; k=$2; key=$3; shift 3
@@ -45,6 +45,11 @@ caps)
     ncu -i /tmp/${TAG}_$n.ncu-rep --page raw --csv > $OUT/${TAG}_raw_$n.csv 2>/dev/null
     python tools/ncu_summary.py /tmp/${TAG}_$n.ncu-rep profiles/${TAG}_ncu_full_$n.txt "$key" > /dev/null && cp profiles/${TAG}_ncu_full_$n.txt profiles/ncu_traffic.json $OUT/
     rm -f /tmp/${TAG}_$n.ncu-rep; }
+  if [ $w = capsattn ]; then
+  cap attn_shared_b1 shared_attn "ir_shared_attn_fwd:b1_h5_sq4096_skv16384_adain" tools/attn_one.py 1 5 4096 0 4 1
+  cap attn_shared_b8 shared_attn "ir_shared_attn_fwd:b8_h5_sq4096_skv16384_adain" tools/attn_one.py 8 5 4096 0 4 1
+  cap gn_apply_512 gn_apply "ir_groupnorm:b4_hw262144_c128" tools/norm_one.py gn 4 262144 128
+  else
   cap conv_halo_pair_512 conv "ir_conv_gemm:m65536_k4608_n512_ks3s1" tools/gemm_one.py conv3 4 128 512 512
   cap conv_halo_128 conv "ir_conv_gemm:m1048576_k1152_n128_ks3s1" tools/gemm_one.py conv3 4 512 128 128
   cap conv_pair160_320 conv "ir_conv_gemm:m131072_k2880_n320_ks3s1" tools/gemm_one.py conv3 32 64 320 320
@@ -57,7 +62,8 @@ caps)
   cap gn_apply_512 gn_apply "ir_groupnorm:b4_hw262144_c128" tools/norm_one.py gn 4 262144 128
   cap gn_partial_512 gn_partial "ir_groupnorm_partial:b4_hw262144_c128" tools/norm_one.py gn 4 262144 128
   cap gn_single_320 gn_fused "ir_groupnorm:b4_hw4096_c320_1launch" tools/norm_one.py gn 4 4096 320 2
-  cap layernorm_320 layernorm "ir_layernorm:r16384_c320" tools/norm_one.py ln 16384 320 ;;
+  cap layernorm_320 layernorm "ir_layernorm:r16384_c320" tools/norm_one.py ln 16384 320
+  fi ;;
 full)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-shared_attn} -s ${NCU_SKIP:-20} -c ${NCU_COUNT:-3} \
      -f -o $OUT/${TAG}_prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
