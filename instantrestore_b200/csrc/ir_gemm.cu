@@ -188,203 +188,6 @@ __device__ __forceinline__ void col_stats8(const float (&v)[8], const GemmKParam
   }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ GemmKParams p) {
-  constexpr int B_BYTES = BN * kBK * 2;
-  constexpr int STAGE_BYTES = kABytes + B_BYTES;
-  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  constexpr uint32_t IDESC = umma_idesc_f16(kBM, BN, 0, 0);
-
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tma_a[0]);
-    tma_prefetch_desc(&p.tma_b);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(accum_bar, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                 // set-up above overlapped the previous kernel's tail; no global access before this point
-
-  const int mt = blockIdx.x;
-  const int nt = blockIdx.y;
-  const int num_k_total = p.taps * p.kc_per_tap;
-  const int k_begin = blockIdx.z * p.kb_per_split;                    // split-K: this CTA's K-block range
-  const int k_end = min(k_begin + p.kb_per_split, num_k_total);
-  const int num_k = k_end - k_begin;
-
-  if (warp == 0) {
-    if (elect_one()) {   // elect.sync (not lane == 0): the compiler then keeps TMA / MMA operands in uniform registers
-      const int w0 = (mt % p.tiles_w) * p.bw;
-      const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
-      const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
-      int tap = k_begin / p.kc_per_tap, kc = k_begin % p.kc_per_tap;
-      int s = 0;
-      uint32_t ph = 1;
-      for (int ks = 0; ks < num_k; ++ks) {
-        mbar_wait(&empty_bar[s], ph);
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_4d(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], &full_bar[s], kc * kBK, w0 + p.tap_dx[tap],
-                    h0 + p.tap_dy[tap], n0);
-        tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], (k_begin + ks) * kBK, nt * BN);
-        if (++kc == p.kc_per_tap) {
-          kc = 0;
-          ++tap;
-        }
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (elect_one()) {
-      int s = 0;
-      uint32_t ph = 0;
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA)), b_lo0 = umma_desc_lo(smem_u32(sB));
-      for (int ks = 0; ks < num_k; ++ks) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_lo = a_lo0 + s * (kABytes >> 4), b_lo = b_lo0 + s * (B_BYTES >> 4);
-#pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) umma_f16_ss_lo(tmem_base, a_lo + 2 * k, b_lo + 2 * k, IDESC, (ks | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-      }
-      umma_commit(accum_bar);
-    }
-    __syncwarp();
-  }
-
-  // ------------------------------------------------------------------ epilogue (all 128 threads, thread == row)
-  mbar_wait(accum_bar, 0);
-  tc_fence_after();
-  pdl_launch_dependents();    // only the epilogue is left: the next kernel may set itself up
-
-  const int row = warp * 32 + lane;
-  const long grow = static_cast<long>(mt) * kBM + row;
-  const bool row_ok = grow < p.M;
-  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-
-  if (p.act == IR_ACT_GEGLU) {
-    // tile columns come in blocks of 128: [64 value | 64 gate]
-    if constexpr (BN % 128 == 0) {
-#pragma unroll 1
-      for (int blk = 0; blk < BN / 128; ++blk) {
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          uint32_t rv[32], rg[32];
-          tmem_ld32(taddr + blk * 128 + half * 32, rv);
-          tmem_ld32(taddr + blk * 128 + 64 + half * 32, rg);
-          tmem_ld_wait();
-          const int wcol = nt * BN + blk * 128 + half * 32;           // weight-row index of the value columns
-          const int ocol = (nt * BN + blk * 128) / 2 + half * 32;     // output column
-          if (row_ok) {
-            uint32_t packed[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float v0 = __uint_as_float(rv[i]), v1 = __uint_as_float(rv[i + 1]);
-              float g0 = __uint_as_float(rg[i]), g1 = __uint_as_float(rg[i + 1]);
-              if (p.bias) {
-                v0 += __ldg(p.bias + wcol + i);
-                v1 += __ldg(p.bias + wcol + i + 1);
-                g0 += __ldg(p.bias + wcol + 64 + i);
-                g1 += __ldg(p.bias + wcol + 64 + i + 1);
-              }
-              v0 = round_h(v0); v1 = round_h(v1); g0 = round_h(g0); g1 = round_h(g1);
-              packed[i / 2] = pack_half2(v0 * round_h(gelu_erf(g0)), v1 * round_h(gelu_erf(g1)));
-            }
-            uint4* dst = reinterpret_cast<uint4*>(p.out + grow * p.out_stride + ocol);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
-          }
-        }
-      }
-    }
-  } else if (p.split > 1) {
-    // ---- split-K: reduce-scatter the S partial tiles through distributed shared memory
-    const int S = p.split;
-    const int W = BN / S;                       // columns owned by each CTA of the cluster (multiple of 8)
-    const uint32_t my_rank = cluster_ctarank();
-    cluster_sync_all();                          // every CTA of the cluster has drained its pipeline buffers
-    const uint32_t recv_local = smem_u32(smem);  // [src][W/4][128 rows] float4, reuses the stage buffers
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(taddr + c0, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int col = c0 + q * 4;
-        const uint32_t owner = static_cast<uint32_t>(col / W);
-        const int c4 = (col - owner * W) >> 2;
-        const uint32_t off = ((my_rank * (W >> 2) + c4) * 128 + row) * 16;
-        dsmem_st_f4(dsmem_addr(recv_local + off, owner), __uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
-                    __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
-      }
-    }
-    cluster_sync_all();                          // all partial slices have landed in their owner's shared memory
-    const float4* recv = reinterpret_cast<const float4*>(smem);
-    if (row_ok) {
-#pragma unroll 1
-      for (int c8 = 0; c8 < W; c8 += 8) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        for (int src = 0; src < S; ++src) {       // fixed order: deterministic sum
-          const float4 a = recv[(src * (W >> 2) + (c8 >> 2)) * 128 + row];
-          const float4 b = recv[(src * (W >> 2) + (c8 >> 2) + 1) * 128 + row];
-          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-          v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-        }
-        const int gcol = nt * BN + static_cast<int>(my_rank) * W + c8;
-        epilogue_store<8>(v, p, grow, gcol);          // leaves the stored (bias added, fp16-rounded) values in v
-        if (p.col_partial && gcol >= p.col_begin) col_stats8(v, p, grow, gcol);   // M % 128 == 0: row_ok is uniform
-      }
-    }
-  } else {
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(taddr + c0, r);
-      tmem_ld_wait();
-      if (row_ok) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_store<32>(v, p, grow, nt * BN + c0);  // leaves the stored (bias added, fp16-rounded) values in v
-        if (p.col_partial && nt * BN + c0 >= p.col_begin && nt * BN + c0 < p.N) col_stats32(v, p, grow, nt * BN + c0);
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
-
 // GroupNorm pass A fused into the conv epilogue: (mean, M2) of one warp's 32 rows x 32 columns (= 32 / CPG whole groups)
 // of the fp16-rounded outputs. Per-lane group sums, then a reduce-scatter butterfly over the 32 lanes (each halving
 // step keeps half of the groups) — fixed summation tree, deterministic. The slab format is the one gn_merge_kernel
@@ -508,6 +311,284 @@ __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4
                            pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
   store_row64(op, packed, p.wide_io);
 }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ GemmKParams p) {
+  constexpr int B_BYTES = BN * kBK * 2;
+  constexpr int STAGE_BYTES = kABytes + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t IDESC = umma_idesc_f16(kBM, BN, 0, 0);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tma_a[0]);
+    tma_prefetch_desc(&p.tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // set-up above overlapped the previous kernel's tail; no global access before this point
+
+  const int mt = blockIdx.x;
+  const int nt = blockIdx.y;
+  const int num_k_total = p.taps * p.kc_per_tap;
+  const int k_begin = blockIdx.z * p.kb_per_split;                    // split-K: this CTA's K-block range
+  const int k_end = min(k_begin + p.kb_per_split, num_k_total);
+  const int num_k = k_end - k_begin;
+
+  if (warp == 0) {
+    if (elect_one()) {   // elect.sync (not lane == 0): the compiler then keeps TMA / MMA operands in uniform registers
+      const int w0 = (mt % p.tiles_w) * p.bw;
+      const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+      const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
+      int tap = k_begin / p.kc_per_tap, kc = k_begin % p.kc_per_tap;
+      int s = 0;
+      uint32_t ph = 1;
+      for (int ks = 0; ks < num_k; ++ks) {
+        mbar_wait(&empty_bar[s], ph);
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_4d(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], &full_bar[s], kc * kBK, w0 + p.tap_dx[tap],
+                    h0 + p.tap_dy[tap], n0);
+        tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], (k_begin + ks) * kBK, nt * BN);
+        if (++kc == p.kc_per_tap) {
+          kc = 0;
+          ++tap;
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA)), b_lo0 = umma_desc_lo(smem_u32(sB));
+      for (int ks = 0; ks < num_k; ++ks) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + s * (kABytes >> 4), b_lo = b_lo0 + s * (B_BYTES >> 4);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) umma_f16_ss_lo(tmem_base, a_lo + 2 * k, b_lo + 2 * k, IDESC, (ks | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ epilogue (all 128 threads, thread == row)
+  const int row = warp * 32 + lane;
+  const long grow = static_cast<long>(mt) * kBM + row;
+  const bool row_ok = grow < p.M;
+  // Vector epilogue (16-byte bias loads, residual already in registers) whenever the rows allow it. The residual of
+  // every chunk is fetched BEFORE waiting for the accumulator: the per-instruction stall samples of the single-identity
+  // GEMMs (tools/ncu_source.sh) had 40 % of the kernel's samples on the bias / residual loads of a chunk-by-chunk
+  // epilogue — four dependent HBM round trips after the MMAs were done.
+  constexpr int kEpiChunks = (BN + 31) / 32;
+  const bool fast = p.N % 32 == 0 && p.act != IR_ACT_GEGLU && (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+  const bool pre_res = fast && p.split == 1 && p.residual != nullptr && row_ok;
+  uint4 resid[kEpiChunks][4];
+  if (pre_res) {
+#pragma unroll
+    for (int ci = 0; ci < kEpiChunks; ++ci)
+      if (ci * 32 < BN && nt * BN + ci * 32 < p.N) load_row64(p.residual + grow * p.res_stride + nt * BN + ci * 32, resid[ci], p.wide_io);
+  }
+  mbar_wait(accum_bar, 0);
+  tc_fence_after();
+  pdl_launch_dependents();    // only the epilogue is left: the next kernel may set itself up
+
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+
+  if (p.act == IR_ACT_GEGLU) {
+    // tile columns come in blocks of 128: [64 value | 64 gate]
+    if constexpr (BN % 128 == 0) {
+#pragma unroll 1
+      for (int blk = 0; blk < BN / 128; ++blk) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t rv[32], rg[32];
+          tmem_ld32(taddr + blk * 128 + half * 32, rv);
+          tmem_ld32(taddr + blk * 128 + 64 + half * 32, rg);
+          tmem_ld_wait();
+          const int wcol = nt * BN + blk * 128 + half * 32;           // weight-row index of the value columns
+          const int ocol = (nt * BN + blk * 128) / 2 + half * 32;     // output column
+          if (row_ok) {
+            uint32_t packed[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float v0 = __uint_as_float(rv[i]), v1 = __uint_as_float(rv[i + 1]);
+              float g0 = __uint_as_float(rg[i]), g1 = __uint_as_float(rg[i + 1]);
+              if (p.bias) {
+                v0 += __ldg(p.bias + wcol + i);
+                v1 += __ldg(p.bias + wcol + i + 1);
+                g0 += __ldg(p.bias + wcol + 64 + i);
+                g1 += __ldg(p.bias + wcol + 64 + i + 1);
+              }
+              v0 = round_h(v0); v1 = round_h(v1); g0 = round_h(g0); g1 = round_h(g1);
+              packed[i / 2] = pack_half2(v0 * round_h(gelu_erf(g0)), v1 * round_h(gelu_erf(g1)));
+            }
+            uint4* dst = reinterpret_cast<uint4*>(p.out + grow * p.out_stride + ocol);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+          }
+        }
+      }
+    }
+  } else if (p.split > 1) {
+    // ---- split-K: reduce-scatter the S partial tiles through distributed shared memory
+    const int S = p.split;
+    const int W = BN / S;                       // columns owned by each CTA of the cluster (multiple of 8)
+    const uint32_t my_rank = cluster_ctarank();
+    const bool w_pow2 = (W & (W - 1)) == 0;
+    const int wshift = __ffs(W) - 1;
+    // This CTA's slice of the residual row and of the bias, fetched now and consumed after the exchange (they were
+    // eight dependent round trips at the very end of the kernel: one per 8-column group).
+    constexpr int kPreV = 8;                    // W <= 64
+    const int gcol0 = nt * BN + static_cast<int>(my_rank) * W;
+    const bool pre = fast && row_ok && W <= 8 * kPreV && gcol0 + W <= p.N && (gcol0 & 7) == 0;
+    uint4 rres[kPreV];
+    float4 rb[2 * kPreV];
+    if (pre) {
+#pragma unroll
+      for (int j = 0; j < kPreV; ++j) {
+        if (j * 8 < W) {
+          if (p.residual) rres[j] = __ldg(reinterpret_cast<const uint4*>(p.residual + grow * p.res_stride + gcol0 + j * 8));
+          if (p.bias) {
+            rb[2 * j] = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + j * 8));
+            rb[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + j * 8 + 4));
+          }
+        }
+      }
+    }
+    cluster_sync_all();                          // every CTA of the cluster has drained its pipeline buffers
+    const uint32_t recv_local = smem_u32(smem);  // [src][W/4][128 rows] float4, reuses the stage buffers
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int col = c0 + q * 4;
+        const uint32_t owner = static_cast<uint32_t>(w_pow2 ? col >> wshift : col / W);
+        const int c4 = (col - owner * W) >> 2;
+        const uint32_t off = ((my_rank * (W >> 2) + c4) * 128 + row) * 16;
+        dsmem_st_f4(dsmem_addr(recv_local + off, owner), __uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                    __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+      }
+    }
+    cluster_sync_all();                          // all partial slices have landed in their owner's shared memory
+    const float4* recv = reinterpret_cast<const float4*>(smem);
+    if (pre) {
+#pragma unroll
+      for (int j = 0; j < kPreV; ++j) {
+        if (j * 8 < W) {
+          const int c8 = j * 8;
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+          for (int src = 0; src < S; ++src) {       // fixed order: deterministic sum
+            const float4 a = recv[(src * (W >> 2) + (c8 >> 2)) * 128 + row];
+            const float4 b = recv[(src * (W >> 2) + (c8 >> 2) + 1) * 128 + row];
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+          }
+          // epilogue_store<8> with its operands already in registers: + bias, fp16 round, + residual, activation
+          if (p.bias) {
+            v[0] += rb[2 * j].x; v[1] += rb[2 * j].y; v[2] += rb[2 * j].z; v[3] += rb[2 * j].w;
+            v[4] += rb[2 * j + 1].x; v[5] += rb[2 * j + 1].y; v[6] += rb[2 * j + 1].z; v[7] += rb[2 * j + 1].w;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = round_h(v[i]);
+          if (p.residual) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&rres[j]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(h2[i]);
+              v[2 * i] += f.x;
+              v[2 * i + 1] += f.y;
+            }
+          }
+          if (p.act == IR_ACT_SILU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
+          }
+          const int gcol = gcol0 + c8;
+          *reinterpret_cast<uint4*>(p.out + grow * p.out_stride + gcol) =
+              make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+          if (p.col_partial && gcol >= p.col_begin) col_stats8(v, p, grow, gcol);   // M % 128 == 0: row_ok is uniform
+        }
+      }
+    } else if (row_ok) {
+#pragma unroll 1
+      for (int c8 = 0; c8 < W; c8 += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int src = 0; src < S; ++src) {       // fixed order: deterministic sum
+          const float4 a = recv[(src * (W >> 2) + (c8 >> 2)) * 128 + row];
+          const float4 b = recv[(src * (W >> 2) + (c8 >> 2) + 1) * 128 + row];
+          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+          v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        const int gcol = nt * BN + static_cast<int>(my_rank) * W + c8;
+        epilogue_store<8>(v, p, grow, gcol);          // leaves the stored (bias added, fp16-rounded) values in v
+        if (p.col_partial && gcol >= p.col_begin) col_stats8(v, p, grow, gcol);   // M % 128 == 0: row_ok is uniform
+      }
+    }
+  } else {
+#pragma unroll
+    for (int ci = 0; ci < kEpiChunks; ++ci) {       // unrolled: the prefetched residual stays in registers
+      const int c0 = ci * 32;
+      if (c0 < BN) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (fast && nt * BN + c0 < p.N) {
+            epilogue_store32_pre<true>(v, resid[ci], pre_res, p, grow, nt * BN + c0);
+          } else {
+            epilogue_store<32>(v, p, grow, nt * BN + c0);  // leaves the stored (bias added, fp16-rounded) values in v
+            if (p.col_partial && nt * BN + c0 >= p.col_begin && nt * BN + c0 < p.N) col_stats32(v, p, grow, nt * BN + c0);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 
 // ------------------------------------------------------------------------------------------------ persistent kernel
 constexpr int kPersistThreads = 320;   // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue (two warps per TMEM lane quarter)
@@ -1453,9 +1534,18 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
     if (static_cast<long>(m_tiles) * ((p->c_out + bn_tile - 1) / bn_tile) * 8 < 148 && bn_tile > 64) bn_tile = 64;
   }
   if (can_split && !wide_persistent && p->split_k == 0 && p->c_out % bn_tile == 0 && (bn_tile == 64 || bn_tile == 128)) {
+    // K split only while every CTA of the cluster keeps >= 16 K-blocks: below that the cluster launch, the two cluster
+    // barriers and the DSMEM exchange cost more than the idle SMs (tools/small_gemm_bench.py, device time per launch:
+    // m1024_k1280_n1280 15.5 us with a 2-way split vs 9.3 without, m1024_k640_n640 12.0 vs 7.3, m256_k1280_n3840 14.5 vs 8.5;
+    // the long-K 3x3 convolutions keep their split: m256_k11520_n1280 47.8 us unsplit vs 19.9 with 4 ways)
     const long tiles = static_cast<long>(m_tiles) * (p->c_out / bn_tile);
-    while (split < 8 && tiles * split < 148 && tiles * split * 2 <= 296 && num_k / (split * 2) >= 4) split *= 2;
+    while (split < 8 && tiles * split < 148 && tiles * split * 2 <= 296 && num_k / (split * 2) >= 16) split *= 2;
   }
+  // unsplit launches that fill less than half of the SMs: 64-wide tiles double the CTA count (m1024_k640_n640 7.3 -> 5.9 us,
+  // m256_k1280_n1280 8.6 -> 7.0, m256_k1280_n3840 8.5 -> 7.4, m4096_k320_n320 7.5 -> 6.6)
+  if (split == 1 && p->split_k == 0 && p->tile_n == 0 && !geglu && !wide_persistent && bn_tile > 64 && p->c_out % 64 == 0 &&
+      static_cast<long>(m_tiles) * ((p->c_out + bn_tile - 1) / bn_tile) < 74)
+    bn_tile = 64;
   if (split > 1 && (p->c_out % bn_tile != 0 || (bn_tile / split) % 8 != 0 || num_k < split))
     return set_error(IR_ERR_SHAPE, "ir_conv_gemm: split_k=%d incompatible with tile_n=%d, c_out=%d, k-blocks=%d", split, bn_tile, p->c_out, num_k);
   kp.split = split;

@@ -24,8 +24,9 @@ bench8)
 ab)
   # same-box A/B of an environment switch: AB_ENV="IR_GN_SINGLE_LAUNCH=0" tools/gpu_round.sh <tag> ab
   for B in 1 8; do for arm in "" "${AB_ENV:-IR_GN_SINGLE_LAUNCH=0}"; do
-    env $arm timeout 600 python bench.py --steps 20 --warmup 3 --batch $B --no-cpu-baseline --no-extras --no-trace > $OUT/${TAG}_ab_b${B}_${arm:-default}.json 2>> $OUT/${TAG}_ab.err
-    python -c "import json,sys; d=json.load(open('$OUT/${TAG}_ab_b${B}_${arm:-default}.json')); print('AB B=$B', '${arm:-default}', round(d['value'],2), 'images/s', round(d['ms_per_step'],3), 'ms', d['gpu_launches_per_step'], 'launches', d['clocks'])"
+    nm=$(echo "${arm:-default}" | tr '/' '_' | sed 's/.*instantrestore_b200_//')
+    env $arm timeout 600 python bench.py --steps 20 --warmup 3 --batch $B --no-cpu-baseline --no-extras --no-trace > $OUT/${TAG}_ab_b${B}_$nm.json 2>> $OUT/${TAG}_ab.err
+    python -c "import json,sys; d=json.load(open('$OUT/${TAG}_ab_b${B}_$nm.json')); print('AB B=$B', '$nm', round(d['value'],2), 'images/s', round(d['ms_per_step'],3), 'ms', d['gpu_launches_per_step'], 'launches', d['clocks'])"
   done; done ;;
 streams)
   for S in 2 3 4 5 6; do
