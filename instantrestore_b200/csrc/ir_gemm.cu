@@ -1501,8 +1501,9 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   // tile-N selection: exact divisors first, fewest wasted columns
   int bn_tile = p->tile_n;
   bool wide_persistent = false;   // 128 x 256 tiles on the persistent kernel: 96 B/clk of operand reads instead of 128
+  // (from 111 tiles = 3/4 of the SMs: m4096_k4608_n512 is 64 such tiles, 29.4 us; as 128-wide tiles with a 2-way K split 27.0)
   if (bn_tile == 0 && !geglu && p->c_out % 256 == 0 && p->split_k <= 1 && p->no_persistent != 1 &&
-      static_cast<long>(m_tiles) * (p->c_out / 256) >= 64) {
+      static_cast<long>(m_tiles) * (p->c_out / 256) >= 111) {
     bn_tile = 256;
     wide_persistent = true;
   }

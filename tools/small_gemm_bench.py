@@ -10,6 +10,8 @@ from instantrestore_b200 import _lib as L
 SHAPES = [  # (kind, M or (B, H), K / Cin, N / Cout, residual)
     ("lin", 4096, 640, 640, True), ("lin", 1024, 1280, 1280, True), ("lin", 256, 1280, 1280, True), ("lin", 1024, 640, 640, True),
     ("lin", 4096, 320, 320, True), ("lin", 16384, 320, 320, True), ("lin", 4096, 640, 1920, False), ("lin", 256, 1280, 3840, False),
+    ("lin", 4096, 512, 512, True), ("lin", 4096, 512, 4096, False), ("lin", 4096, 4096, 512, False), ("lin", 4096, 2560, 640, True),
+    ("lin", 1024, 5120, 1280, True), ("lin", 4096, 1920, 640, True), ("conv", (1, 64), 640, 640, True), ("conv", (1, 64), 960, 320, True),
     ("conv", (1, 16), 1280, 1280, True), ("conv", (1, 64), 512, 512, True), ("conv", (1, 32), 1280, 1280, True), ("conv", (1, 8), 1280, 1280, False),
 ]
 
