@@ -275,13 +275,15 @@ __device__ __forceinline__ void store_row64(__half* ptr, const uint4 (&r)[4], in
 }
 
 // epilogue_store<32> with the residual already in registers (prefetched before the accumulator was ready)
+// `sbias`: optional shared-memory copy of the 32 bias values of this chunk (halo kernel: staged once per N tile; the
+// broadcast LDG.128s otherwise queue behind the thread-per-row residual loads and output stores in L1TEX).
 template <bool COLS = false>
 __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4 (&res)[4], bool has_res, const GemmKParams& p,
-                                                     long grow, int gcol) {
+                                                     long grow, int gcol, const float* sbias = nullptr) {
   if (p.bias) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + q);
+      const float4 b4 = sbias ? reinterpret_cast<const float4*>(sbias)[q] : __ldg(reinterpret_cast<const float4*>(p.bias + gcol) + q);
       v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
     }
   }
@@ -1067,6 +1069,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
   uint64_t* tfull_bar = b_empty + NB;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sBias = reinterpret_cast<float*>(tmem_slot + 4);     // BN bias values of the current N tile (16-byte aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1196,12 +1199,20 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
     constexpr int kChunks = BN / 2 / 32;
     const int c_begin = half * (BN / 2);
     int local = 0;
+    int bias_nt = -1;                                         // N tile whose bias is staged in shared memory
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++local) {
       const int ms = tile / n_tiles_n, nt = tile - ms * n_tiles_n;
       const int img = ms / per_img, rem = ms - img * per_img;
       const int h0 = (rem / tiles_w) * 2 + static_cast<int>(rank), w0 = (rem % tiles_w) << 7;
       const int as = local & 1;
       if (tile + tile_step >= total_tiles) pdl_launch_dependents();                     // last tile of this CTA / pair
+      if (p.bias && nt != bias_nt) {                          // once per kernel for the 128- / 256-channel layers
+        const int e = static_cast<int>(threadIdx.x) - 64;     // 0 .. 255 over the eight epilogue warps
+        if (bias_nt >= 0) named_bar_sync(1, 256);             // every warp is done with the previous tile's values
+        if (e < BN / 4) reinterpret_cast<float4*>(sBias)[e] = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BN) + e);
+        named_bar_sync(1, 256);
+        bias_nt = nt;
+      }
       const long grow0 = (static_cast<long>(img) * p.img_h + h0) * p.img_w + w0 + row;
       uint4 resid[RESID ? MSUB : 1][RESID ? kChunks : 1][4];
       if (RESID) {
@@ -1228,7 +1239,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          epilogue_store32_pre(v, resid[RESID ? sub : 0][RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
+          epilogue_store32_pre(v, resid[RESID ? sub : 0][RESID ? ci : 0], RESID, p, grow, nt * BN + c0, p.bias ? sBias + c0 : nullptr);
         }
       }
       tc_fence_before();
@@ -1249,7 +1260,7 @@ template <int BN, bool PAIR, bool RESID>
 static int launch_halo_r(const GemmKParams& kp, cudaStream_t stream) {
   constexpr int msub = PAIR ? 1 : 2;
   constexpr int halo_slot = ((msub + 2) * kHaloW * 128 + 1023) / 1024 * 1024;
-  constexpr int smem = 2 * halo_slot + (PAIR ? 7 : 5) * 128 * kBK * 2 + 1024 + 256;
+  constexpr int smem = 2 * halo_slot + (PAIR ? 7 : 5) * 128 * kBK * 2 + 1024 + 256 + 1024;   // + the staged bias tile
   static PerDeviceOnce attr_once;   // function attributes are per device
   bool& attr_done = attr_once.slot();
   if (!attr_done) {
