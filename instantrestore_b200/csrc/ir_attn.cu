@@ -37,7 +37,10 @@ constexpr int kMaxRef = 16;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8, exact in fp16 / fp32 accumulation
 constexpr int kAttnThreads = 320;
 constexpr bool kPingPong = false;         // strict alternation of the two warpgroups on the exp pass
-constexpr int kPolyOf8 = 2;               // of every 8 exponentials, this many run on the FMA pipes instead of MUFU
+#ifndef IR_ATTN_POLY_OF8
+#define IR_ATTN_POLY_OF8 2
+#endif
+constexpr int kPolyOf8 = IR_ATTN_POLY_OF8;  // of every 8 exponentials, this many run on the FMA pipes instead of MUFU
 
 struct AttnKParams {
   CUtensorMap tma_q, tma_k_own, tma_v_own, tma_k_ref, tma_v_ref;
