@@ -175,3 +175,30 @@ def test_fused_groupnorm_statistics_shape_rules():
     # the VAE of the step: every GroupNorm input at 512x512 images qualifies
     for hw, c in [(512 * 512, 128), (256 * 256, 128), (256 * 256, 256), (128 * 128, 256), (128 * 128, 512), (64 * 64, 512)]:
         assert L.gn_partial_supported(hw, c)
+
+
+def test_single_launch_groupnorm_plan_rules():
+    """ir_groupnorm_fused_supported is host logic: tensors up to 12 MB whose rows split into whole groups x whole
+    16-byte vectors take the one-launch cluster kernel; the big VAE tensors keep the streaming path."""
+    import ctypes
+    from instantrestore_b200 import _lib
+    lib = _lib.load()
+    ok = lambda b, hw, c, g=32: bool(lib.ir_groupnorm_fused_supported(b, hw, c, g))
+    for shape in [(1, 4096, 320), (4, 4096, 320), (1, 4096, 960), (1, 1024, 1920), (1, 256, 2560), (1, 64, 1280), (2, 4096, 512),
+                  (1, 16384, 256), (3, 256, 64), (2, 48, 320)]:
+        assert ok(*shape), shape
+    for shape in [(1, 512 * 512, 128), (4, 256 * 256, 256), (32, 4096, 320), (5, 4096, 512), (1, 4097, 320)]:
+        assert not ok(*shape), shape
+    assert not ok(1, 4096, 324)            # channels % groups != 0
+    assert not ok(0, 4096, 320)
+
+
+def test_new_entry_points_reject_null_arguments_without_a_gpu():
+    import ctypes
+    from instantrestore_b200 import _lib
+    lib = _lib.load()
+    assert lib.ir_resample_u8_pass(None, 3, 3, 1, 1, None, None, 1, 0, None, 1, 1, 1, 0, None) == -5
+    assert lib.ir_u8_to_f16(None, 3, 3, 1, 1, None, None) == -5
+    assert lib.ir_image_out_u8(None, None, 1, 1, None) == -5
+    assert lib.ir_set_pdl(0) in (0, 1)
+    assert lib.ir_set_pdl(0) == 0
