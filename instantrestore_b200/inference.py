@@ -198,7 +198,7 @@ class Predictor:
     def _forward_batch(self, input_images: torch.Tensor, conditioning_images: torch.Tensor, face_embeds=None,
                        calc_attn_probs: bool = False):
         valid_indices = torch.ones(input_images.size(0), dtype=torch.int64) * self.max_conditioning_images
-        x_pred, _, maps = self.net.forward(input_images.to(self.device, self.dtype),
+        x_pred, _, maps = self.net.forward(input_images.to(self.device, self.dtype), face_embeds=face_embeds,
                                            conditioning_images=conditioning_images.to(self.device, self.dtype),
                                            valid_indices=valid_indices, return_self_attention_maps=calc_attn_probs)
         if calc_attn_probs:                                         # test.py:107-110

@@ -73,8 +73,6 @@ class RestoreEngine:
         self.spec = spec or UNetSpec()
         self.flags = flags
         self.dev = torch.device(device)
-        if flags.condition_on_face_embeds:
-            raise NotImplementedError("condition_on_face_embeds=True (FaceIDAttnProcessor) is not on the released path")
         self.main = UNetEngine(StateDictView(unet_sd), self.spec, noise_timestep, caption_enc, self.dev,
                                use_adain=flags.use_adain, train_input=flags.train_input,
                                consume_refs=flags.use_shared_attention)
@@ -88,7 +86,7 @@ class RestoreEngine:
         self._graphs: Dict[Tuple, dict] = {}
 
     # ------------------------------------------------------------------------------------------ eager step
-    def _step(self, enc, refs, noise_main, noise_ref, valid: Optional[Sequence[int]]):
+    def _step(self, enc, refs, noise_main, noise_ref, valid: Optional[Sequence[int]], face=None):
         B, _, H, W = enc.shape
         cur = torch.cuda.current_stream(self.dev)
         # main path prefix (noise, conv_in, down blocks, mid block) does not depend on the references: fork it onto a
@@ -97,7 +95,7 @@ class RestoreEngine:
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             x = L.latent_in(enc, noise_main, self.a_main, self.s_main)
-            state = self.main.forward_down_mid(x, B, H, W)
+            state = self.main.forward_down_mid(x, B, H, W, face)
         ref_kv = None
         if self.ref is not None and refs is not None:
             N = refs.shape[1]
@@ -122,41 +120,51 @@ class RestoreEngine:
     # ------------------------------------------------------------------------------------------ public
     @torch.no_grad()
     def forward_latents(self, enc_control: torch.Tensor, ref_latents: Optional[torch.Tensor], noise_main: torch.Tensor,
-                        noise_ref: Optional[torch.Tensor], valid_indices: Optional[Sequence[int]] = None) -> torch.Tensor:
+                        noise_ref: Optional[torch.Tensor], valid_indices: Optional[Sequence[int]] = None,
+                        face_embeds: Optional[torch.Tensor] = None) -> torch.Tensor:
         """enc_control (B,4,h,w), ref_latents (B,N,4,h,w), noise_main (B,4,h,w), noise_ref (B*N,4,h,w): fp32 CUDA
-        tensors. Returns the predicted clean latent x0 (B,4,h,w) fp32 (before the /scaling_factor of the VAE decode)."""
+        tensors; face_embeds (B, N_f, 512) when the checkpoint conditions on face embeddings (pix2pix_turbo.py:316-320).
+        Returns the predicted clean latent x0 (B,4,h,w) fp32 (before the /scaling_factor of the VAE decode)."""
+        face = None
+        if face_embeds is not None and self.main.face_kv is not None:
+            face = face_embeds.to(self.dev, torch.float16).contiguous()
+        elif self.main.face_kv is not None:
+            raise ValueError("this checkpoint conditions on face embeddings (FaceIDAttnProcessor): pass face_embeds=(B, N_f, 512)")
         valid = None
         if valid_indices is not None and ref_latents is not None:
             valid = [int(v) for v in valid_indices]
             if all(v >= ref_latents.shape[1] for v in valid):
                 valid = None
         if not self.use_cuda_graph:
-            return self._step(enc_control, ref_latents, noise_main, noise_ref, valid)
-        key = (tuple(enc_control.shape), None if ref_latents is None else tuple(ref_latents.shape), tuple(valid) if valid else None)
+            return self._step(enc_control, ref_latents, noise_main, noise_ref, valid, face)
+        key = (tuple(enc_control.shape), None if ref_latents is None else tuple(ref_latents.shape), tuple(valid) if valid else None,
+               None if face is None else tuple(face.shape))
         g = self._graphs.get(key)
         if g is None:
-            g = self._capture(enc_control, ref_latents, noise_main, noise_ref, valid)
+            g = self._capture(enc_control, ref_latents, noise_main, noise_ref, valid, face)
             self._graphs[key] = g
         g["enc"].copy_(enc_control, non_blocking=True)
         g["noise_main"].copy_(noise_main, non_blocking=True)
+        if face is not None:
+            g["face"].copy_(face, non_blocking=True)
         if ref_latents is not None:
             g["refs"].copy_(ref_latents, non_blocking=True)
             g["noise_ref"].copy_(noise_ref, non_blocking=True)
         g["graph"].replay()
         return g["out"]
 
-    def _capture(self, enc, refs, noise_main, noise_ref, valid):
+    def _capture(self, enc, refs, noise_main, noise_ref, valid, face=None):
         st = dict(enc=enc.clone(), noise_main=noise_main.clone(), refs=None if refs is None else refs.clone(),
-                  noise_ref=None if noise_ref is None else noise_ref.clone())
+                  noise_ref=None if noise_ref is None else noise_ref.clone(), face=None if face is None else face.clone())
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
-            self._step(st["enc"], st["refs"], st["noise_main"], st["noise_ref"], valid)   # warm-up: allocator, func attrs
+            self._step(st["enc"], st["refs"], st["noise_main"], st["noise_ref"], valid, st["face"])   # warm-up: allocator, func attrs
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            st["out"] = self._step(st["enc"], st["refs"], st["noise_main"], st["noise_ref"], valid)
+            st["out"] = self._step(st["enc"], st["refs"], st["noise_main"], st["noise_ref"], valid, st["face"])
         st["graph"] = graph
         return st
 
@@ -194,7 +202,7 @@ class RestorePipeline:
         self._gen = torch.Generator(device=self.dev)
         self._gen.manual_seed(0)
 
-    def _step(self, c_t, cond, eps_main, eps_ref, noise_main, noise_ref, valid):
+    def _step(self, c_t, cond, eps_main, eps_ref, noise_main, noise_ref, valid, face=None):
         B = c_t.shape[0]
         eng = self.engine
         cur = torch.cuda.current_stream(self.dev)
@@ -206,7 +214,7 @@ class RestorePipeline:
             skips = self.vae.skip_acts
             _, _, H, W = enc.shape
             x = L.latent_in(enc, noise_main, eng.a_main, eng.s_main)
-            state = eng.main.forward_down_mid(x, B, H, W)
+            state = eng.main.forward_down_mid(x, B, H, W, face)
         ref_kv = None
         if cond is not None and self.original_vae is not None:
             ref_kv = self._reference_kv(cond, eps_ref, noise_ref, valid, B)
@@ -280,9 +288,12 @@ class RestorePipeline:
         `ref_cache` (from extract_reference_kv) replaces `conditioning_images`: the reference path is skipped."""
         if ref_cache is not None:
             return self._forward_cached(c_t, ref_cache, eps_main, noise_main, slot)
-        if face_embeds is not None:
-            raise NotImplementedError("condition_on_face_embeds is False in the released configs")
         dev = self.dev
+        face = None
+        if self.engine.main.face_kv is not None:      # FaceIDAttnProcessor checkpoint (pix2pix_turbo.py:316-320)
+            if face_embeds is None:
+                raise ValueError("this checkpoint conditions on face embeddings: pass face_embeds=(B, N_f, 512)")
+            face = face_embeds.to(dev, torch.float16).contiguous() if face_embeds.device != dev or face_embeds.dtype != torch.float16 else face_embeds
         # Inputs may live on the host (pinned memory for an asynchronous copy): on the graph path they are copied ONCE,
         # straight into the graph's static input buffers on the current stream.
         if c_t.dtype not in (torch.float16, torch.float32):
@@ -313,7 +324,7 @@ class RestorePipeline:
             valid = [int(v) for v in valid_indices]
             if all(v >= N for v in valid):
                 valid = None
-        ins = dict(c_t=c_t, cond=cond, eps_main=eps_main, eps_ref=eps_ref, noise_main=noise_main, noise_ref=noise_ref)
+        ins = dict(c_t=c_t, cond=cond, eps_main=eps_main, eps_ref=eps_ref, noise_main=noise_main, noise_ref=noise_ref, face=face)
         on_dev = lambda d: {k: (None if v is None else v.to(dev).contiguous()) for k, v in d.items()}
         if return_self_attention_maps or not self.use_cuda_graph:
             # attention maps: eager (no graph), the 9 shared layers also build the dense (B, H, S, S_k) softmax matrix the
@@ -322,12 +333,13 @@ class RestorePipeline:
             main.save_attention_probs = bool(return_self_attention_maps)
             ins = on_dev(ins)
             try:
-                out = self._step(ins["c_t"], ins["cond"], ins["eps_main"], ins["eps_ref"], ins["noise_main"], ins["noise_ref"], valid)
+                out = self._step(ins["c_t"], ins["cond"], ins["eps_main"], ins["eps_ref"], ins["noise_main"], ins["noise_ref"], valid, ins["face"])
                 maps = list(main.attention_probs) if return_self_attention_maps else None
             finally:
                 main.save_attention_probs = False
             return out, None, maps
-        key = (tuple(c_t.shape), c_t.dtype, None if cond is None else tuple(cond.shape), tuple(valid) if valid else None, slot)
+        key = (tuple(c_t.shape), c_t.dtype, None if cond is None else tuple(cond.shape), tuple(valid) if valid else None,
+               None if face is None else tuple(face.shape), slot)
         g = self._graphs.get(key)
         if g is None:
             with L.scratch_namespace(("graph", id(self), len(self._graphs))):
@@ -378,7 +390,7 @@ class RestorePipeline:
 
     def _capture(self, ins, valid):
         st = {k: (None if v is None else v.clone()) for k, v in ins.items()}
-        args = lambda: (st["c_t"], st["cond"], st["eps_main"], st["eps_ref"], st["noise_main"], st["noise_ref"], valid)
+        args = lambda: (st["c_t"], st["cond"], st["eps_main"], st["eps_ref"], st["noise_main"], st["noise_ref"], valid, st["face"])
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):

@@ -122,6 +122,15 @@ class UNetEngine:
         emb = emb @ te.weight("linear_2").T + te.bias("linear_2")
         self._silu_emb = torch.nn.functional.silu(emb)[0]
 
+        # FaceIDAttnProcessor cross-attentions (reference attn_processors.py:100-180; cfg.condition_on_face_embeds):
+        # K = to_k_face_embed(face_projection(e)), V = to_v_face_embed(face_projection(e)) depend only on the face
+        # embeddings, so the two linears of every cross-attention fold into one [2C, 512] matrix and ALL of them run as
+        # ONE GEMM per step ([B*N_f, 512] x [sum 2C, 512]^T); each layer then reads its K | V columns in place.
+        self._face_parts: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        self._face_cols = 0
+        self.face_kv: Optional[_Lin] = None
+        self._face: Optional[torch.Tensor] = None
+        self._n_face = 0
         self.conv_in = _Conv(sd.weight("conv_in"), sd.bias("conv_in"), dev, c_in_pad=64)
         self.down = []
         for i, ch in enumerate(boc):
@@ -157,6 +166,9 @@ class UNetEngine:
             self.up.append((layers, us))
         self.norm_out = _Norm(sd, "conv_norm_out", dev)
         self.conv_out = _Conv(sd.weight("conv_out"), sd.bias("conv_out"), dev)
+        if self._face_parts:
+            self.face_kv = _Lin(torch.cat([w for w, _ in self._face_parts], 0), torch.cat([b for _, b in self._face_parts], 0), dev)
+        self._face_parts = []
 
     # ------------------------------------------------------------------------------------------ loading
     def _load_resnet(self, v: StateDictView):
@@ -178,8 +190,15 @@ class UNetEngine:
         k2 = (cap @ a2.weight("to_k").T).to(torch.float16).contiguous().to(dev)      # [n_ctx, C], constant
         v2 = (cap @ a2.weight("to_v").T).to(torch.float16).contiguous().to(dev)
         idx = geglu_interleave_index(ff.weight("net.0.proj").shape[0])
+        face_off = None
+        if a2.has("processor.face_projection.weight"):
+            wp, bp = a2.weight("processor.face_projection"), a2.bias("processor.face_projection")     # [W, 512], [W]
+            wk, wv = a2.weight("processor.to_k_face_embed"), a2.weight("processor.to_v_face_embed")   # [C, W]
+            self._face_parts.append((torch.cat([wk @ wp, wv @ wp], 0), torch.cat([wk @ bp, wv @ bp], 0)))
+            face_off = (self._face_cols, self._face_cols + ch)        # column offsets of this layer's K and V
+            self._face_cols += 2 * ch
         return dict(
-            heads=heads, ch=ch,
+            heads=heads, ch=ch, face_off=face_off,
             norm=_Norm(v, "norm", dev), proj_in=_Lin(v.weight("proj_in"), v.bias("proj_in"), dev),
             ln1=_Norm(b, "norm1", dev), qkv=_Lin(wqkv, None, dev), out1=_Lin(a1.weight("to_out.0"), a1.bias("to_out.0"), dev),
             ln2=_Norm(b, "norm2", dev), q2=_Lin(a2.weight("to_q"), None, dev), k2=k2, v2=v2,
@@ -255,8 +274,14 @@ class UNetEngine:
         # --- attn2: cross attention against the constant caption K/V
         n = L.layernorm(h, p["ln2"].g, p["ln2"].b)
         q = self._lin(n, p["q2"])
-        a = L.shared_attn(q, heads=heads, scale=scale, batch=B, s_q=S, k_own=p["k2"], v_own=p["v2"], s_own=self.n_ctx,
-                          own_shared=True)
+        if p["face_off"] is not None:       # keys / values from the face embeddings of this identity (N_f tokens)
+            if self._face is None:
+                raise ValueError("this checkpoint was trained with condition_on_face_embeds: forward(face_embeds=...) is required")
+            a = L.shared_attn(q, heads=heads, scale=scale, batch=B, s_q=S, k_own=self._face, v_own=self._face,
+                              k_own_col_off=p["face_off"][0], v_own_col_off=p["face_off"][1], s_own=self._n_face)
+        else:
+            a = L.shared_attn(q, heads=heads, scale=scale, batch=B, s_q=S, k_own=p["k2"], v_own=p["v2"], s_own=self.n_ctx,
+                              own_shared=True)
         h = self._lin(a, p["out2"], residual=h)
         # --- feed-forward (GEGLU fused into the first GEMM's epilogue)
         n = L.layernorm(h, p["ln3"].g, p["ln3"].b)
@@ -265,14 +290,21 @@ class UNetEngine:
         return self._lin(h, p["proj_out"], residual=x)
 
     # ------------------------------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, B: int, H: int, W: int, ref_kv: Optional[Sequence[RefKV]] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, B: int, H: int, W: int, ref_kv: Optional[Sequence[RefKV]] = None,
+                face_embeds: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x: fp16 channel-last latent [B*H*W, 64] (4 real channels). Returns the model output [B*H*W, 4] fp16."""
-        return self.forward_up(self.forward_down_mid(x, B, H, W), ref_kv)
+        return self.forward_up(self.forward_down_mid(x, B, H, W, face_embeds), ref_kv)
 
-    def forward_down_mid(self, x: torch.Tensor, B: int, H: int, W: int):
+    def forward_down_mid(self, x: torch.Tensor, B: int, H: int, W: int, face_embeds: Optional[torch.Tensor] = None):
         """conv_in, down blocks and mid block (reference unet.py:1042-1121): independent of the reference K/V, so the
-        pipeline runs it on a second stream while the reference UNet is still working."""
+        pipeline runs it on a second stream while the reference UNet is still working.
+        face_embeds: fp16 (B, N_f, 512) when the checkpoint's cross-attentions are FaceIDAttnProcessors."""
         self.captured = []
+        self._face, self._n_face = None, 0
+        if self.face_kv is not None and face_embeds is not None:
+            fe = face_embeds.reshape(-1, face_embeds.shape[-1])
+            self._n_face = face_embeds.shape[1]
+            self._face = self._lin(fe, self.face_kv)        # [B*N_f, sum 2C]: every cross-attention's K | V
         dbg = self.debug
         h = self._conv(x, self.conv_in, B, H, W)
         if dbg is not None:

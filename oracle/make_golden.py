@@ -153,6 +153,25 @@ def build_pipeline(RefUNet, ref_ap, cfg, flags, lora_rank, seed=0):
     return LatentRestorePipeline(ref_unet, ref_orig, cap, flags, processors=ref_ap)
 
 
+FACEID_CASE = ("unet_tiny_faceid", 2, 3, True, False, 4)     # name, batch, n_ref, use_adain, train_input, lora_rank
+
+
+def faceid_pipeline_case(RefUNet, ref_ap, write=True):
+    from oracle import synth
+    from oracle.unet import UNetConfig
+    name, batch, n_ref, use_adain, train_input, lora_rank = FACEID_CASE
+    tiny = UNetConfig.tiny()
+    flags = synth.ModelFlags(use_adain=use_adain, train_input=train_input, condition_on_face_embeds=True)
+    pipe = build_pipeline(RefUNet, ref_ap, tiny, flags, lora_rank)
+    synth.seed_face_processors(pipe.unet)
+    enc, refs, nm, nr = synth.latents(batch, n_ref, tiny.sample_size)
+    out = pipe.forward_latents(enc, refs, nm, nr, face_embeds=synth.face_embeddings(batch))
+    if write:
+        np.savez_compressed(GOLDEN / f"{name}.npz", x0=out.numpy(), meta=np.array([batch, n_ref, int(use_adain), int(train_input), lora_rank]))
+        print(name, tuple(out.shape), float(out.std()))
+    return out
+
+
 VAE_CASES = [  # name, use_shortcuts, lora_rank
     ("vae_tiny_plain", False, 0),
     ("vae_tiny_lora", False, 4),
@@ -254,6 +273,10 @@ def main():
                                 meta=np.array([batch, n_ref, int(use_adain), int(train_input), lora_rank]),
                                 valid=np.array(valid if valid is not None else [n_ref] * batch))
             print(name, tuple(out.shape), float(out.std()))
+
+        # 3a) the same with the cross-attentions conditioned on face embeddings (FaceIDAttnProcessor, cfg.condition_on_face_embeds;
+        #     reference pix2pix_turbo.py:316-320): 2 identities, 3 references, 4 face embeddings each
+        faceid_pipeline_case(RefUNet, ref_ap)
 
         # 3b) VAE alone through the reference's own patched forwards (models/model.py:15-63), and the whole image pipeline
         from oracle.vae import VaeConfig

@@ -56,7 +56,7 @@ class LatentRestorePipeline:
 
     @torch.no_grad()
     def forward_latents(self, enc_control: torch.Tensor, ref_latents: Optional[torch.Tensor], noise_main: torch.Tensor,
-                        noise_ref: Optional[torch.Tensor], valid_indices=None) -> torch.Tensor:
+                        noise_ref: Optional[torch.Tensor], valid_indices=None, face_embeds: Optional[torch.Tensor] = None) -> torch.Tensor:
         keys = values = None
         if ref_latents is not None and self.flags.use_shared_attention:
             if valid_indices is None:
@@ -64,7 +64,10 @@ class LatentRestorePipeline:
             keys, values = self.conditioning_keys_values(ref_latents, noise_ref, valid_indices)
         t = torch.tensor([self.noise_timestep], device=enc_control.device)
         noisy = self.sched.add_noise(enc_control, noise_main, t.long().repeat(enc_control.shape[0]))
-        cap = self.caption_enc.to(noisy.device).repeat(noisy.shape[0], 1, 1)
+        if self.flags.condition_on_face_embeds and face_embeds is not None:      # pix2pix_turbo.py:316-320
+            cap = face_embeds.to(noisy.device)
+        else:
+            cap = self.caption_enc.to(noisy.device).repeat(noisy.shape[0], 1, 1)
         pred = self.unet(noisy, t, encoder_hidden_states=cap,
                          cross_attention_kwargs={"ref_keys": keys, "ref_values": values})
         pred = getattr(pred, "sample", pred)

@@ -115,3 +115,19 @@ def images(batch: int, n_ref: int, size: int, latent: int, seed: int = 4321):
     noise_main = torch.randn(batch, 4, latent, latent, generator=g)
     noise_ref = torch.randn(batch * n_ref, 4, latent, latent, generator=g)
     return c_t, cond, eps_main, eps_ref, noise_main, noise_ref
+
+
+def seed_face_processors(unet, seed: int = 77):
+    """Deterministic weights for the FaceIDAttnProcessor modules register_attention_processor creates (the reference
+    leaves them at torch's default init; a trained checkpoint carries them as `...attn2.processor.*`)."""
+    for i, (name, proc) in enumerate(sorted(unet.attn_processors.items())):
+        if hasattr(proc, "face_projection"):
+            seeded_init_(proc, seed + i)
+    return unet
+
+
+def face_embeddings(batch: int, n_faces: int = 4, dim: int = 512, seed: int = 5) -> torch.Tensor:
+    """Stand-in for the normalised insightface embeddings of the reference images (test.py:117-126): unit-norm rows."""
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randn(batch, n_faces, dim, generator=g)
+    return e / e.norm(dim=-1, keepdim=True)

@@ -141,6 +141,50 @@ def test_tiny_pipeline_vs_reference_golden(case, graph, golden):
     assert err <= 1.5 * ref_err + 2e-4
 
 
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "cudagraph"])
+def test_faceid_pipeline_vs_reference_golden(graph, golden):
+    """Whole-step engine with FaceIDAttnProcessor cross-attentions (cfg.condition_on_face_embeds; reference
+    attn_processors.py:100-180, pix2pix_turbo.py:316-320): the two linears of every cross-attention are folded and all
+    16 K | V projections of the face embeddings run as ONE GEMM. Golden from the reference's own processors."""
+    from instantrestore_b200.pipeline import ModelFlags, RestoreEngine
+    from oracle import synth
+    from oracle.make_golden import FACEID_CASE
+    from oracle.pipeline import LatentRestorePipeline
+    from oracle.unet import UNetConfig
+    name, batch, n_ref, use_adain, train_input, lora_rank = FACEID_CASE
+    tiny = UNetConfig.tiny()
+    oflags = synth.ModelFlags(use_adain=use_adain, train_input=train_input, condition_on_face_embeds=True)
+    unet, orig = synth.make_unet(tiny, seed=0, lora_rank=lora_rank), synth.make_unet(tiny, seed=0)
+    opipe = LatentRestorePipeline(unet, orig, synth.caption_embedding(tiny.cross_attention_dim), oflags)   # registers the processors
+    synth.seed_face_processors(opipe.unet)
+    sd = unet.state_dict()
+    assert any(k.endswith("attn2.processor.face_projection.weight") for k in sd)          # the checkpoint layout the engine reads
+    eng = RestoreEngine(sd, orig.state_dict(), synth.caption_embedding(tiny.cross_attention_dim),
+                        ModelFlags(use_adain=use_adain, train_input=train_input, condition_on_face_embeds=True),
+                        spec=_spec_from(tiny), use_cuda_graph=graph)
+    enc, refs, nm, nr = (t.cuda() for t in synth.latents(batch, n_ref, tiny.sample_size))
+    faces = synth.face_embeddings(batch).cuda()
+    gold = torch.as_tensor(golden(name)["x0"])
+    out = eng.forward_latents(enc, refs, nm, nr, face_embeds=faces)
+    err = rel_l2(out, gold)
+    if graph:
+        out2 = eng.forward_latents(enc.clone(), refs.clone(), nm.clone(), nr.clone(), face_embeds=faces.clone())
+        assert torch.equal(out2, out)
+    for m in (unet, orig):
+        m.cuda()
+    opipe.caption_enc = opipe.caption_enc.cuda()
+    with torch.autocast("cuda", dtype=torch.float16):
+        ac = opipe.forward_latents(enc, refs, nm, nr, face_embeds=faces)
+    ref_err = rel_l2(ac.float(), gold)
+    print(f"{name}: ours {err:.3e}  reference-autocast {ref_err:.3e}")
+    assert err <= PIPE_TOL
+    assert err <= 1.5 * ref_err + 2e-4
+    other = eng.forward_latents(enc, refs, nm, nr, face_embeds=synth.face_embeddings(batch, seed=6).cuda())
+    assert rel_l2(other, gold) > 10 * PIPE_TOL                        # the embeddings are really consumed
+    with pytest.raises(ValueError):
+        eng.forward_latents(enc, refs, nm, nr)                        # a FaceID checkpoint needs face_embeds
+
+
 def test_full_width_pipeline_vs_reference_golden(golden):
     """SD-Turbo geometry, released final-model flags (AdaIN on, refs-only KV), B=1, N=4: BASELINE configs[1]."""
     from oracle import synth

@@ -107,6 +107,24 @@ def test_tiny_pipeline_matches_reference(case, golden):
     _close(out, golden(name)["x0"])
 
 
+def test_faceid_pipeline_matches_reference(golden):
+    """cfg.condition_on_face_embeds: the cross-attentions become FaceIDAttnProcessors fed with face embeddings
+    (reference attn_processors.py:100-180, pix2pix_turbo.py:316-320); golden from the reference's own processors."""
+    from oracle.make_golden import FACEID_CASE
+    name, batch, n_ref, use_adain, train_input, lora_rank = FACEID_CASE
+    tiny = UNetConfig.tiny()
+    flags = synth.ModelFlags(use_adain=use_adain, train_input=train_input, condition_on_face_embeds=True)
+    pipe = LatentRestorePipeline(synth.make_unet(tiny, seed=0, lora_rank=lora_rank), synth.make_unet(tiny, seed=0),
+                                 synth.caption_embedding(tiny.cross_attention_dim), flags)
+    synth.seed_face_processors(pipe.unet)
+    enc, refs, nm, nr = synth.latents(batch, n_ref, tiny.sample_size)
+    out = pipe.forward_latents(enc, refs, nm, nr, face_embeds=synth.face_embeddings(batch))
+    _close(out, golden(name)["x0"])
+    # the face embeddings matter: other embeddings give a clearly different result
+    other = pipe.forward_latents(enc, refs, nm, nr, face_embeds=synth.face_embeddings(batch, seed=6))
+    assert float((other - out).abs().max()) > 1e-3
+
+
 def test_processor_registration_numbering():
     """reference attn_processors.py:282-331: only up_blocks.*.attn1 get self_attn_idx 0..8 in module order."""
     tiny = UNetConfig.tiny()
