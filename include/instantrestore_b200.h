@@ -106,6 +106,14 @@ typedef struct {
                         epilogue (no residual / activation), M % 128 == 0, c_out % 32 == 0, col_begin % 32 == 0. Hand it to
                         ir_adain_coeffs.own_partial / ref_partial */
   int col_begin;
+  int upsample2x; /* != 0: nearest-neighbour 2x upsampling followed by the 3x3 stride-1 convolution (diffusers Upsample2D:
+                     F.interpolate(scale_factor=2.0, mode="nearest") + conv; reference block.py:2366,2476 and the VAE decoder's
+                     upsamplers) WITHOUT materialising the upsampled tensor: each of the four output sub-pixel phases
+                     (py, px) is a 2x2 convolution on the low-resolution input whose taps are sums of the 3x3 taps that land
+                     on the same input pixel (4/9 of the multiply-adds). h_in, w_in are the LOW-resolution sizes; out is
+                     [batch, 2*h_in, 2*w_in, c_out]; w is the phase-folded matrix [4 phases (py*2+px)][c_out][2x2 taps (a*2+b)][c_in]
+                     with tap (a, b) of phase (py, px) reading input pixel (y + py - 1 + a, x + px - 1 + b). Needs ksize 3,
+                     stride 1, no residual / GEGLU / col_partial; never runs on the halo kernel */
 } ir_conv_gemm_params;
 int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
 

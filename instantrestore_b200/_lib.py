@@ -34,7 +34,7 @@ class ConvGemmParams(C.Structure):
         ("res_row_stride", C.c_int), ("act", C.c_int), ("out", C.c_void_p), ("out_row_stride", C.c_int),
         ("tile_n", C.c_int), ("split_k", C.c_int), ("m_sub", C.c_int), ("no_persistent", C.c_int), ("pad_hi_only", C.c_int),
         ("cta_pair", C.c_int), ("gn_partial", C.c_void_p), ("gn_groups", C.c_int), ("halo", C.c_int), ("wide_io", C.c_int),
-        ("col_partial", C.c_void_p), ("col_begin", C.c_int),
+        ("col_partial", C.c_void_p), ("col_begin", C.c_int), ("upsample2x", C.c_int),
     ]
 
 
@@ -314,11 +314,18 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
               stride: int = 1, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
               act: int = IR_ACT_NONE, out: torch.Tensor | None = None, tile_n: int = 0, split_k: int = 0,
               a_row_stride: int | None = None, pad_hi_only: bool = False, no_persistent: int = 0, m_sub: int = 0, cta_pair: int = 0, halo: int = 0, gn_partial: torch.Tensor | None = None,
-              gn_groups: int = 32, wide_io: int = 0, col_partial: torch.Tensor | None = None, col_begin: int = 0) -> torch.Tensor:
+              gn_groups: int = 32, wide_io: int = 0, col_partial: torch.Tensor | None = None, col_begin: int = 0,
+              upsample2x: bool = False) -> torch.Tensor:
     """a: fp16 channel-last [batch*h_in*w_in, >=c_in]; w: fp16 [c_out, ksize*ksize*c_in].
     gn_partial: fp32 [batch * (h_out*w_out/32) * gn_groups * 2] (gn_partial_numel) to receive pass A of the next GroupNorm.
-    col_partial: fp32 [M/32, c_out - col_begin, 2] to receive per-(32-row slab, column) (mean, M2) of the outputs (AdaIN)."""
+    col_partial: fp32 [M/32, c_out - col_begin, 2] to receive per-(32-row slab, column) (mean, M2) of the outputs (AdaIN).
+    upsample2x: nearest-2x upsampling + 3x3 convolution as four 2x2 sub-pixel convolutions on the low-resolution input;
+    w is then fold_upsample_weight(...) = [4*c_out, 4*c_in] and the result has 4*batch*h_in*w_in rows."""
     _h(a, "a"); _h(w, "w"); _f(bias, "bias"); _f(gn_partial, "gn_partial"); _f(col_partial, "col_partial")
+    if upsample2x:
+        return _conv_gemm_up2x(a, w, batch=batch, h_in=h_in, w_in=w_in, c_in=c_in, ksize=ksize, stride=stride, bias=bias,
+                               out=out, tile_n=tile_n, split_k=split_k, a_row_stride=a_row_stride, no_persistent=no_persistent,
+                               cta_pair=cta_pair, gn_partial=gn_partial, gn_groups=gn_groups, wide_io=wide_io)
     c_out = w.shape[0]
     assert w.shape[1] == ksize * ksize * c_in and w.is_contiguous(), (w.shape, ksize, c_in)
     m = batch * (h_in // stride) * (w_in // stride)
@@ -339,6 +346,29 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
              2.0 * (m * c_in * (1 if ksize == 1 else stride * stride) + c_out * k_tot + m * n_out
                     + (m * n_out if residual is not None else 0)),
              load().ir_conv_gemm, C.byref(p), stream_ptr(a.device), keep=(a, w, bias, residual, out, gn_partial, col_partial))
+    return out
+
+
+def _conv_gemm_up2x(a, w, *, batch, h_in, w_in, c_in, ksize, stride, bias, out, tile_n, split_k, a_row_stride, no_persistent,
+                    cta_pair, gn_partial, gn_groups, wide_io):
+    assert ksize == 3 and stride == 1, "upsample2x folds into a 3x3 stride-1 convolution"
+    assert w.shape[0] % 4 == 0 and w.shape[1] == 4 * c_in and w.is_contiguous(), (w.shape, c_in)
+    c_out = w.shape[0] // 4
+    m = 4 * batch * h_in * w_in                        # output pixels
+    if out is None:
+        out = torch.empty((m, c_out), dtype=torch.float16, device=a.device)
+    p = ConvGemmParams(
+        a=ptr(a), batch=batch, h_in=h_in, w_in=w_in, c_in=c_in,
+        a_row_stride=a_row_stride if a_row_stride is not None else a.stride(-2),
+        ksize=3, stride=1, w=ptr(w), c_out=c_out, bias=ptr(bias), residual=None, res_row_stride=0,
+        act=IR_ACT_NONE, out=ptr(out), out_row_stride=out.stride(-2), tile_n=tile_n, split_k=split_k,
+        pad_hi_only=0, no_persistent=int(no_persistent), m_sub=0, cta_pair=cta_pair, halo=0, gn_partial=ptr(gn_partial),
+        gn_groups=gn_groups, wide_io=wide_io or _NARROW_IO, col_partial=None, col_begin=0, upsample2x=1)
+    k_tot = 4 * c_in                                   # executed multiply-adds: 4/9 of the 3x3 convolution on the upsampled tensor
+    with on_device(a):
+        _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks3s1_up2x", 2.0 * m * k_tot * c_out,
+             2.0 * (m // 4 * c_in + 4 * c_out * k_tot + m * c_out),
+             load().ir_conv_gemm, C.byref(p), stream_ptr(a.device), keep=(a, w, bias, out, gn_partial))
     return out
 
 

@@ -43,9 +43,14 @@ struct GemmKParams {
   int kc_per_tap, taps;
   int tiles_w, tiles_h;
   int bw, bh, bn;
-  int8_t tap_map[9], tap_dx[9], tap_dy[9];
+  int8_t tap_map[16], tap_dx[16], tap_dy[16];   // upsample mode: [phase * 4 + tap]
   int split, kb_per_split;
   int m_tiles;
+  // nearest-2x upsample folded into the convolution (ir_conv_gemm_params.upsample2x): M tiles [phase * mtp, (phase+1) * mtp)
+  // belong to output sub-pixel phase (py, px) = (phase / 2, phase % 2); M, the tile boxes and `grow` are low-resolution
+  // quantities, the weight rows of phase ph start at ph * N, and low-resolution pixel row grow = (b*H + y)*W + x is stored
+  // at output pixel (b, 2y + py, 2x + px) = row 4*grow - 2*x + py*2W + px.
+  int up, mtp, up_wmask, up_w2;
   int img_h, img_w;     // halo kernel: output (= input) image size
   float2* gn_partial;   // optional: per-(image, 32-row slab, group) (mean, M2) of the stored outputs (GroupNorm pass A)
   int gn_cpg, gn_hw, gn_groups;
@@ -78,8 +83,13 @@ __device__ __forceinline__ float round_h(float x) { return __half2float(__float2
 
 // Epilogue for NC (8, 16 or 32) consecutive output columns of one row: + bias, fp16 round, + residual, activation,
 // 16-byte stores. v[] holds the fp32 accumulators.
+__device__ __forceinline__ long out_row(const GemmKParams& p, long grow, int phase) {
+  if (!p.up) return grow;
+  return 4 * grow - 2 * (grow & p.up_wmask) + (phase >> 1) * p.up_w2 + (phase & 1);
+}
+
 template <int NC>
-__device__ __forceinline__ void epilogue_store(float (&v)[NC], const GemmKParams& p, long grow, int gcol) {
+__device__ __forceinline__ void epilogue_store(float (&v)[NC], const GemmKParams& p, long grow, int gcol, int phase = 0) {
   if (gcol >= p.N) return;
   const bool full = (gcol + NC <= p.N);
   if (p.bias) {
@@ -112,7 +122,7 @@ __device__ __forceinline__ void epilogue_store(float (&v)[NC], const GemmKParams
 #pragma unroll
     for (int i = 0; i < NC; ++i) v[i] = silu(v[i]);
   }
-  __half* op = p.out + grow * p.out_stride + gcol;
+  __half* op = p.out + out_row(p, grow, phase) * p.out_stride + gcol;
   if (full) {
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
@@ -232,12 +242,14 @@ __device__ __forceinline__ void gn_stats_chunk(const float (&v)[32], int lane, f
   }
 }
 
-__device__ __forceinline__ void gn_stats32(const float (&v)[32], const GemmKParams& p, long grow, int gcol) {
+template <bool UPOK = true>
+__device__ __forceinline__ void gn_stats32(const float (&v)[32], const GemmKParams& p, long grow, int gcol, int phase) {
   const int lane = threadIdx.x & 31;
   const int w0 = static_cast<int>(grow) - lane;          // first row of this warp's 32-row slab (all of one image)
   const int img = w0 / p.gn_hw;
-  const int slab = (w0 - img * p.gn_hw) >> 5;
-  float2* dst = p.gn_partial + (static_cast<size_t>(img) * (p.gn_hw >> 5) + slab) * p.gn_groups + gcol / p.gn_cpg;
+  const int spi = p.gn_hw >> 5;                          // slabs per image (upsample mode: per image and phase)
+  const int slab = ((w0 - img * p.gn_hw) >> 5) + (UPOK ? phase * spi : 0);    // any bijection onto the image's slab slots will do
+  float2* dst = p.gn_partial + (static_cast<size_t>(img) * (UPOK && p.up ? 4 * spi : spi) + slab) * p.gn_groups + gcol / p.gn_cpg;
   if (p.gn_cpg == 4) gn_stats_chunk<4>(v, lane, dst);
   else if (p.gn_cpg == 8) gn_stats_chunk<8>(v, lane, dst);
   else gn_stats_chunk<16>(v, lane, dst);
@@ -277,9 +289,9 @@ __device__ __forceinline__ void store_row64(__half* ptr, const uint4 (&r)[4], in
 // epilogue_store<32> with the residual already in registers (prefetched before the accumulator was ready)
 // `sbias`: optional shared-memory copy of the 32 bias values of this chunk (halo kernel: staged once per N tile; the
 // broadcast LDG.128s otherwise queue behind the thread-per-row residual loads and output stores in L1TEX).
-template <bool COLS = false>
+template <bool COLS = false, bool UPOK = true>
 __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4 (&res)[4], bool has_res, const GemmKParams& p,
-                                                     long grow, int gcol, const float* sbias = nullptr) {
+                                                     long grow, int gcol, const float* sbias = nullptr, int phase = 0) {
   if (p.bias) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -303,9 +315,9 @@ __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = silu(round_h(v[i]));
   }
-  if (p.gn_partial) gn_stats32(v, p, grow, gcol);
+  if (p.gn_partial) gn_stats32<UPOK>(v, p, grow, gcol, phase);
   if (COLS && p.col_partial && gcol >= p.col_begin) col_stats32(v, p, grow, gcol);   // only instantiated without a residual
-  __half* op = p.out + grow * p.out_stride + gcol;
+  __half* op = p.out + (UPOK ? out_row(p, grow, phase) : grow) * p.out_stride + gcol;
   uint4 packed[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
@@ -355,7 +367,11 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                 // set-up above overlapped the previous kernel's tail; no global access before this point
 
-  const int mt = blockIdx.x;
+  int mt = blockIdx.x, phase = 0;
+  if (p.up) {                 // upsample mode: blockIdx.x runs over phase-major M tiles
+    phase = mt / p.mtp;
+    mt -= phase * p.mtp;
+  }
   const int nt = blockIdx.y;
   const int num_k_total = p.taps * p.kc_per_tap;
   const int k_begin = blockIdx.z * p.kb_per_split;                    // split-K: this CTA's K-block range
@@ -367,7 +383,8 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
       const int w0 = (mt % p.tiles_w) * p.bw;
       const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
       const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
-      int tap = k_begin / p.kc_per_tap, kc = k_begin % p.kc_per_tap;
+      int tap = k_begin / p.kc_per_tap + phase * 4, kc = k_begin % p.kc_per_tap;
+      const int b_row = nt * BN + phase * p.N;
       int s = 0;
       uint32_t ph = 1;
       for (int ks = 0; ks < num_k; ++ks) {
@@ -375,7 +392,7 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
         mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
         tma_load_4d(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], &full_bar[s], kc * kBK, w0 + p.tap_dx[tap],
                     h0 + p.tap_dy[tap], n0);
-        tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], (k_begin + ks) * kBK, nt * BN);
+        tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], (k_begin + ks) * kBK, b_row);
         if (++kc == p.kc_per_tap) {
           kc = 0;
           ++tap;
@@ -541,7 +558,7 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
             for (int i = 0; i < 8; ++i) v[i] = silu(v[i]);
           }
           const int gcol = gcol0 + c8;
-          *reinterpret_cast<uint4*>(p.out + grow * p.out_stride + gcol) =
+          *reinterpret_cast<uint4*>(p.out + out_row(p, grow, phase) * p.out_stride + gcol) =
               make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
           if (p.col_partial && gcol >= p.col_begin) col_stats8(v, p, grow, gcol);   // M % 128 == 0: row_ok is uniform
         }
@@ -559,7 +576,7 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
           v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
         }
         const int gcol = nt * BN + static_cast<int>(my_rank) * W + c8;
-        epilogue_store<8>(v, p, grow, gcol);          // leaves the stored (bias added, fp16-rounded) values in v
+        epilogue_store<8>(v, p, grow, gcol, phase);   // leaves the stored (bias added, fp16-rounded) values in v
         if (p.col_partial && gcol >= p.col_begin) col_stats8(v, p, grow, gcol);   // M % 128 == 0: row_ok is uniform
       }
     }
@@ -576,9 +593,9 @@ __global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if (fast && nt * BN + c0 < p.N) {
-            epilogue_store32_pre<true>(v, resid[ci], pre_res, p, grow, nt * BN + c0);
+            epilogue_store32_pre<true>(v, resid[ci], pre_res, p, grow, nt * BN + c0, nullptr, phase);
           } else {
-            epilogue_store<32>(v, p, grow, nt * BN + c0);  // leaves the stored (bias added, fp16-rounded) values in v
+            epilogue_store<32>(v, p, grow, nt * BN + c0, phase);  // leaves the stored (bias added, fp16-rounded) values in v
             if (p.col_partial && nt * BN + c0 >= p.col_begin && nt * BN + c0 < p.N) col_stats32(v, p, grow, nt * BN + c0);
           }
         }
@@ -682,15 +699,18 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
       uint32_t ph = 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int ms = tile / n_tiles_n, nt = tile - ms * n_tiles_n;
+        int phase = 0;                          // upsample mode (MSUB == 1 there): M tiles are phase-major
+        if constexpr (MSUB == 1) { if (p.up) phase = ms / p.mtp; }
+        const int b_row = nt * BN + phase * p.N;
         int w0[MSUB], h0[MSUB], n0[MSUB];
 #pragma unroll
         for (int sub = 0; sub < MSUB; ++sub) {
-          const int mt = ms * MSUB + sub;       // may run past m_tiles: out-of-range boxes are zero fill
+          const int mt = ms * MSUB + sub - phase * p.mtp;   // may run past m_tiles: out-of-range boxes are zero fill
           w0[sub] = (mt % p.tiles_w) * p.bw;
           h0[sub] = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
           n0[sub] = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
         }
-        int tap = 0, kc = 0;
+        int tap = phase * 4, kc = 0;
         for (int ks = 0; ks < num_k; ++ks) {
           mbar_wait(&empty_bar[s], ph);
           mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -698,7 +718,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
           for (int sub = 0; sub < MSUB; ++sub)
             tma_load_4d(sA + (s * MSUB + sub) * kABytes, &p.tma_a[p.tap_map[tap]], &full_bar[s], kc * kBK,
                         w0[sub] + p.tap_dx[tap], h0[sub] + p.tap_dy[tap], n0[sub]);
-          tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], ks * kBK, nt * BN);
+          tma_load_2d(sB + s * B_BYTES, &p.tma_b, &full_bar[s], ks * kBK, b_row);
           if (++kc == p.kc_per_tap) {
             kc = 0;
             ++tap;
@@ -788,9 +808,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
         const int c_begin = half == 0 ? 0 : (BN == 160 ? 96 : BN / 2);
         const int c_end = half == 0 ? (BN == 160 ? 96 : BN / 2) : BN;
         const bool fast = p.N % 32 == 0 && (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+        int phase = 0;
+        if constexpr (MSUB == 1) { if (p.up) phase = ms / p.mtp; }   // never MSUB == 2 in upsample mode
 #pragma unroll
         for (int sub = 0; sub < MSUB; ++sub) {
-          const long grow = (static_cast<long>(ms) * MSUB + sub) * kBM + row;
+          const long grow = (static_cast<long>(ms) * MSUB + sub - phase * p.mtp) * kBM + row;
           const bool row_ok = grow < p.M;
           const uint32_t taddr = tmem_base + (as * MSUB + sub) * ACC_COLS + lane_addr;
 #pragma unroll
@@ -804,8 +826,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                if (fast && nt * BN + c0 < p.N) epilogue_store32_pre<!RESID>(v, resid[RESID ? sub : 0][RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
-                else epilogue_store<32>(v, p, grow, nt * BN + c0);
+                if (fast && nt * BN + c0 < p.N) epilogue_store32_pre<!RESID, !RESID && MSUB == 1>(v, resid[RESID ? sub : 0][RESID ? ci : 0], RESID, p, grow, nt * BN + c0, nullptr, phase);
+                else epilogue_store<32>(v, p, grow, nt * BN + c0, phase);
               }
             }
           }
@@ -889,18 +911,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
       uint32_t ph = 1;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int mp = tile / n_tiles_n, nt = tile - mp * n_tiles_n;
-        const int mt = mp * 2 + static_cast<int>(rank);      // may run past m_tiles: out-of-range boxes are zero fill
+        int mt = mp * 2 + static_cast<int>(rank);            // may run past m_tiles: out-of-range boxes are zero fill
+        int phase = 0;                                       // upsample mode: mtp is even, both CTAs share the phase
+        if (p.up) {
+          phase = mt / p.mtp;
+          mt -= phase * p.mtp;
+        }
+        const int b_row = nt * BN + phase * p.N + static_cast<int>(rank) * (BN / 2);
         const int w0 = (mt % p.tiles_w) * p.bw;
         const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
         const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.bn;
-        int tap = 0, kc = 0;
+        int tap = phase * 4, kc = 0;
         for (int ks = 0; ks < num_k; ++ks) {
           mbar_wait(&empty_bar[s], ph);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
           const uint32_t leader_full = dsmem_addr(smem_u32(&full_bar[s]), 0);
           tma_load_4d_pair(sA + s * kABytes, &p.tma_a[p.tap_map[tap]], leader_full, kc * kBK, w0 + p.tap_dx[tap],
                            h0 + p.tap_dy[tap], n0);
-          tma_load_2d_pair(sB + s * B_BYTES, &p.tma_b, leader_full, ks * kBK, nt * BN + static_cast<int>(rank) * (BN / 2));
+          tma_load_2d_pair(sB + s * B_BYTES, &p.tma_b, leader_full, ks * kBK, b_row);
           if (++kc == p.kc_per_tap) {
             kc = 0;
             ++tap;
@@ -953,7 +981,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
       const int mp = tile / n_tiles_n, nt = tile - mp * n_tiles_n;
       const int as = local & 1;
       if (tile + tile_step >= total_tiles) pdl_launch_dependents();                     // this cluster's last tile
-      const long grow = (static_cast<long>(mp) * 2 + rank) * kBM + row;
+      int phase = 0;
+      if (p.up) phase = (mp * 2) / p.mtp;
+      const long grow = (static_cast<long>(mp) * 2 + rank - phase * p.mtp) * kBM + row;
       const bool row_ok = grow < p.M;
       uint4 resid[RESID ? kChunks : 1][4];
       if (RESID && row_ok) {
@@ -988,8 +1018,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1) 
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-              if (fast) epilogue_store32_pre<!RESID>(v, resid[RESID ? ci : 0], RESID, p, grow, nt * BN + c0);
-              else epilogue_store<32>(v, p, grow, nt * BN + c0);
+              if (fast) epilogue_store32_pre<!RESID, !RESID>(v, resid[RESID ? ci : 0], RESID, p, grow, nt * BN + c0, nullptr, phase);
+              else epilogue_store<32>(v, p, grow, nt * BN + c0, phase);
             }
           }
         }
@@ -1239,7 +1269,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          epilogue_store32_pre(v, resid[RESID ? sub : 0][RESID ? ci : 0], RESID, p, grow, nt * BN + c0, p.bias ? sBias + c0 : nullptr);
+          epilogue_store32_pre<false, false>(v, resid[RESID ? sub : 0][RESID ? ci : 0], RESID, p, grow, nt * BN + c0, p.bias ? sBias + c0 : nullptr);
         }
       }
       tc_fence_before();
@@ -1340,7 +1370,7 @@ extern "C" int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream_) {
   const int rc = conv_gemm_dispatch(p, stream_, &stats_fused);
   if (rc != 0 || !p->gn_partial || stats_fused) return rc;
   // the kernel chosen for this shape (one tile per CTA / split-K) has no fused statistics: separate pass A
-  const int hw = (p->h_in / p->stride) * (p->w_in / p->stride);
+  const int hw = (p->h_in / p->stride) * (p->w_in / p->stride) * (p->upsample2x ? 4 : 1);
   return launch_gn_partial(p->out, p->out_row_stride, p->batch, hw, p->c_out, p->gn_groups, 32, p->gn_partial,
                            static_cast<cudaStream_t>(stream_));
 }
@@ -1365,10 +1395,13 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   if (p->residual && p->c_out % 8 == 0 && (p->res_row_stride % 8 != 0 || (reinterpret_cast<uintptr_t>(p->residual) & 15)))
     return set_error(IR_ERR_ALIGN, "ir_conv_gemm: residual pointer/stride not 16-byte aligned");
   if (geglu && (p->c_out % 128 != 0 || p->residual)) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: GEGLU needs c_out %% 128 == 0 and no residual");
+  const bool up = p->upsample2x != 0;
+  if (up && (p->ksize != 3 || p->stride != 1 || p->residual || geglu || p->col_partial || p->halo == 2 || p->m_sub > 1))
+    return set_error(IR_ERR_ARG, "ir_conv_gemm: upsample2x needs a 3x3 stride-1 convolution without residual / GEGLU / col_partial / forced halo");
 
   GemmKParams kp;
   memset(&kp, 0, sizeof(kp));
-  const int taps = p->ksize * p->ksize;
+  const int taps = up ? 4 : p->ksize * p->ksize;   // upsample mode: four phases of 2x2 taps on the low-resolution input
   const int h_out = p->h_in / p->stride, w_out = p->w_in / p->stride;
   if (p->stride == 2 && ((p->h_in | p->w_in) & 1)) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: stride 2 needs even h, w");
   const long M = static_cast<long>(p->batch) * h_out * w_out;
@@ -1392,9 +1425,10 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   // GroupNorm pass A on the outputs (optional): whole groups per 32-column chunk, whole 32-row slabs per image
   const bool fast_epilogue = p->c_out % 32 == 0 && (p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0);
   if (p->gn_partial) {
-    const int hw_out = h_out * w_out;
+    const int hw_out = h_out * w_out;             // upsample mode: per phase (the low-resolution image)
     const int cpg = p->gn_groups > 0 && p->c_out % p->gn_groups == 0 ? p->c_out / p->gn_groups : 0;
-    if (geglu || (cpg != 4 && cpg != 8 && cpg != 16) || hw_out % 128 != 0 || (reinterpret_cast<uintptr_t>(p->gn_partial) & 7))
+    // upsample mode: the epilogue's 32-row slabs are low-resolution pixels of ONE phase; any slab that stays inside an image will do
+    if (geglu || (cpg != 4 && cpg != 8 && cpg != 16) || (up ? hw_out % 32 != 0 : hw_out % 128 != 0) || (reinterpret_cast<uintptr_t>(p->gn_partial) & 7))
       return set_error(IR_ERR_SHAPE, "ir_conv_gemm: gn_partial needs c_out / gn_groups in {4, 8, 16}, h_out*w_out %% 128 == 0, no GEGLU (c_out=%d groups=%d hw=%d)",
                        p->c_out, p->gn_groups, hw_out);
     if (fast_epilogue) {
@@ -1422,7 +1456,7 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   // 64-channel slice instead of once per tap). 256-wide N tiles run on the CTA pair, 128-wide ones on a single CTA.
   if (p->halo < 0 || p->halo > 2) return set_error(IR_ERR_ARG, "ir_conv_gemm: halo=%d (0 = auto, 1 = off, 2 = force)", p->halo);
   {
-    const bool eligible = p->ksize == 3 && p->stride == 1 && p->w_in % 128 == 0 && p->h_in % 2 == 0 && !geglu &&
+    const bool eligible = !up && p->ksize == 3 && p->stride == 1 && p->w_in % 128 == 0 && p->h_in % 2 == 0 && !geglu &&
                           p->c_out % 128 == 0 && p->split_k <= 1 && p->tile_n == 0 && p->out_row_stride % 8 == 0 &&
                           (p->bias == nullptr || (reinterpret_cast<uintptr_t>(p->bias) & 15) == 0);
     if (p->halo == 2 && !eligible)
@@ -1473,6 +1507,23 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
                           static_cast<uint64_t>(p->batch)};
       uint64_t str[3] = {rs, rs * p->w_in, rs * p->w_in * p->h_in};
       if (int rc = make_tmap_f16(&kp.tma_a[0], p->a, 4, dims, str, box)) return rc;
+      if (up) {
+        // output pixel (2y + py, 2x + px) of conv3x3(nearest2x(in)) reads input rows {y - 1, y, y} (py = 0) or {y, y, y + 1}
+        // (py = 1) for ky = 0, 1, 2: two distinct rows py - 1 + a, a = 0, 1, whose taps were summed on the host (likewise
+        // in x). The upsampled image's zero border coincides with the low-resolution one: TMA zero fill is the padding.
+        for (int ph = 0; ph < 4; ++ph)
+          for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) {
+              kp.tap_map[ph * 4 + a * 2 + b] = 0;
+              kp.tap_dy[ph * 4 + a * 2 + b] = static_cast<int8_t>((ph >> 1) - 1 + a);
+              kp.tap_dx[ph * 4 + a * 2 + b] = static_cast<int8_t>((ph & 1) - 1 + b);
+            }
+        kp.up = 1;
+        kp.mtp = m_tiles;
+        kp.up_wmask = p->w_in - 1;
+        kp.up_w2 = 2 * p->w_in;
+        m_tiles *= 4;
+      } else
       for (int ky = 0; ky < 3; ++ky)
         for (int kx = 0; kx < 3; ++kx) {
           kp.tap_map[ky * 3 + kx] = 0;
@@ -1574,7 +1625,7 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   // pairs only the 256-wide tiles.
   int bn_pair = 0;
   if (p->cta_pair < 0 || p->cta_pair > 2) return set_error(IR_ERR_ARG, "ir_conv_gemm: cta_pair=%d (0 = auto, 1 = off, 2 = force)", p->cta_pair);
-  if (p->cta_pair != 1 && split == 1 && m_tiles >= 2) {
+  if (p->cta_pair != 1 && split == 1 && m_tiles >= 2 && !(up && (kp.mtp & 1))) {
     int cand = 0;
     if (p->c_out % 256 == 0 && (p->tile_n == 0 || p->tile_n == 256)) cand = 256;
     else if (p->c_out % 160 == 0 && !geglu && (p->tile_n == 0 || p->tile_n == 160)) cand = 160;
@@ -1594,7 +1645,7 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   const bool use_pair = bn_pair != 0;
 
   {
-    uint64_t dims[2] = {static_cast<uint64_t>(taps) * p->c_in, static_cast<uint64_t>(p->c_out)};
+    uint64_t dims[2] = {static_cast<uint64_t>(taps) * p->c_in, static_cast<uint64_t>(p->c_out) * (up ? 4 : 1)};
     uint64_t str[1] = {static_cast<uint64_t>(taps) * p->c_in * 2};
     uint32_t box[2] = {64, static_cast<uint32_t>(use_pair ? bn_pair / 2 : bn_tile)};
     if (int rc = make_tmap_f16(&kp.tma_b, p->w, 2, dims, str, box)) return rc;
@@ -1617,7 +1668,7 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   }
   if (persistent) {
     // 256 x 128 CTA tiles (two stacked M tiles sharing the weight boxes) when there are plenty of M tiles
-    const bool tall = bn_tile == 128 && !geglu && m_tiles >= 2 * 148 && num_k >= 16 && p->m_sub != 1;
+    const bool tall = bn_tile == 128 && !geglu && m_tiles >= 2 * 148 && num_k >= 16 && p->m_sub != 1 && !up;
     *stats_fused = kp.gn_partial != nullptr;
     switch (bn_tile) {
       case 64: return launch_persistent<64, 8, 1>(kp, stream);

@@ -19,10 +19,12 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from .weights import StateDictView, conv_weight_khwc, geglu_interleave_index
+from .weights import StateDictView, conv_weight_khwc, geglu_interleave_index, upsample_conv_weight
 
 
 FUSED_ADAIN_STATS = os.environ.get("IR_FUSED_ADAIN", "1") != "0"     # A-B measurement switch
+FOLD_UPSAMPLE = os.environ.get("IR_FOLD_UPSAMPLE", "1") != "0"       # A-B measurement switch (also read by vae_engine)
+UP_FOLD_MIN_ROWS = int(os.environ.get("IR_UP_FOLD_MIN_ROWS", "0"))   # measured ahead on every shape (tools/up_bench.py)
 
 
 @dataclass
@@ -61,12 +63,14 @@ class _Lin:
 
 
 class _Conv:
-    def __init__(self, w4: torch.Tensor, b: Optional[torch.Tensor], dev, stride: int = 1, c_in_pad: int = 0):
+    def __init__(self, w4: torch.Tensor, b: Optional[torch.Tensor], dev, stride: int = 1, c_in_pad: int = 0, upsample: bool = False):
         self.ksize = w4.shape[-1]
         self.stride = stride
         self.c_in = max(w4.shape[1], c_in_pad)
         self.c_out = w4.shape[0]
         self.w = conv_weight_khwc(w4, c_in_pad).to(dev)
+        # Upsample2D's convolution: also the phase-folded weights of the four 2x2 sub-pixel convolutions (ir_conv_gemm upsample2x)
+        self.w_up = upsample_conv_weight(w4).to(dev) if upsample and FOLD_UPSAMPLE else None
         self.b = None if b is None else b.to(torch.float32).contiguous().to(dev)
 
 
@@ -162,7 +166,7 @@ class UNetEngine:
             us = None
             if i != len(boc) - 1:
                 u = blk.sub("upsamplers.0")
-                us = _Conv(u.weight("conv"), u.bias("conv"), dev)
+                us = _Conv(u.weight("conv"), u.bias("conv"), dev, upsample=True)
             self.up.append((layers, us))
         self.norm_out = _Norm(sd, "conv_norm_out", dev)
         self.conv_out = _Conv(sd.weight("conv_out"), sd.bias("conv_out"), dev)
@@ -216,6 +220,14 @@ class UNetEngine:
     def _conv(self, x, cv: _Conv, B, H, W, residual=None):
         return L.conv_gemm(x, cv.w, batch=B, h_in=H, w_in=W, c_in=cv.c_in, ksize=cv.ksize, stride=cv.stride, bias=cv.b,
                            residual=residual)
+
+    def _upsample_conv(self, x, cv: _Conv, B, H, W):
+        """Upsample2D (nearest 2x + 3x3 conv; reference block.py:2366,2476). The upsampled tensor is never written: four 2x2
+        sub-pixel convolutions on x (4/9 of the multiply-adds; 1.7-2.3x faster than upsample + conv on every shape of the
+        step, tools/up_bench.py). IR_FOLD_UPSAMPLE=0 / IR_UP_FOLD_MIN_ROWS keep the materialised path for A/B runs."""
+        if cv.w_up is not None and B * H * W >= UP_FOLD_MIN_ROWS:
+            return L.conv_gemm(x, cv.w_up, batch=B, h_in=H, w_in=W, c_in=cv.c_in, ksize=3, bias=cv.b, upsample2x=True)
+        return self._conv(L.upsample_nearest2x(x, batch=B, h=H, w=W), cv, B, 2 * H, 2 * W)
 
     def _gn(self, x, n: _Norm, B, HW, eps, silu):
         return L.groupnorm(x, n.g, n.b, batch=B, hw=HW, groups=self.spec.norm_num_groups, eps=eps, silu=silu)
@@ -363,9 +375,8 @@ class UNetEngine:
                     if dbg is not None:
                         dbg[f"up_blocks.{i}.attentions.{j}"] = h
             if us is not None:
-                h = L.upsample_nearest2x(h, batch=B, h=H, w=W)
+                h = self._upsample_conv(h, us, B, H, W)
                 H, W = 2 * H, 2 * W
-                h = self._conv(h, us, B, H, W)
                 if dbg is not None:
                     dbg[f"up_blocks.{i}.upsamplers.0"] = h
         t = self._gn(h, self.norm_out, B, H * W, self.spec.norm_eps, True)

@@ -21,19 +21,23 @@ from typing import List, Optional
 import torch
 
 from . import _lib as L
-from .weights import StateDictView, conv_weight_khwc
+from .weights import StateDictView, conv_weight_khwc, upsample_conv_weight
 
 GN_EPS = 1e-6
 GROUPS = 32
 FUSED_GN_STATS = os.environ.get("IR_FUSED_GN", "1") != "0"     # A-B measurement switch
+FOLD_UPSAMPLE = os.environ.get("IR_FOLD_UPSAMPLE", "1") != "0"  # A-B measurement switch
+UP_FOLD_MIN_ROWS = int(os.environ.get("IR_UP_FOLD_MIN_ROWS", "0"))   # measured ahead on every shape (tools/up_bench.py)
 
 
 class _Conv:
     def __init__(self, w4: torch.Tensor, b: Optional[torch.Tensor], dev, stride: int = 1, c_in_pad: int = 0,
-                 pad_hi_only: bool = False):
+                 pad_hi_only: bool = False, upsample: bool = False):
         self.ksize, self.stride, self.pad_hi_only = w4.shape[-1], stride, pad_hi_only
         self.c_in, self.c_out = max(w4.shape[1], c_in_pad), w4.shape[0]
         self.w = conv_weight_khwc(w4, c_in_pad).to(dev)
+        # Upsample2D's convolution: also the phase-folded weights of the four 2x2 sub-pixel convolutions (ir_conv_gemm upsample2x)
+        self.w_up = upsample_conv_weight(w4).to(dev) if upsample and FOLD_UPSAMPLE else None
         self.b = None if b is None else b.to(torch.float32).contiguous().to(dev)
 
 
@@ -99,7 +103,7 @@ class VaeEngine:
                 us = None
                 if i != len(boc) - 1:
                     u = blk.sub("upsamplers.0")
-                    us = _Conv(u.weight("conv"), u.bias("conv"), dev)
+                    us = _Conv(u.weight("conv"), u.bias("conv"), dev, upsample=True)
                 self.d_up.append((res, us))
             self.d_norm_out = _Norm(d, "conv_norm_out", dev)
             self.d_conv_out = _Conv(d.weight("conv_out"), d.bias("conv_out"), dev)
@@ -146,6 +150,16 @@ class VaeEngine:
         out = L.conv_gemm(x, cv.w, batch=B, h_in=H, w_in=W, c_in=cv.c_in, ksize=cv.ksize, stride=cv.stride, bias=cv.b,
                           residual=residual, pad_hi_only=cv.pad_hi_only, gn_partial=part, gn_groups=GROUPS)
         return (out, part) if stats else out
+
+    def _upsample_conv(self, x, cv: _Conv, B, H, W):
+        """Upsample2D of the decoder (nearest 2x + 3x3 conv): the upsampled tensor is never written — four 2x2 sub-pixel
+        convolutions on the low-resolution x (4/9 of the multiply-adds), GroupNorm pass A of the result from the epilogue."""
+        if cv.w_up is None or B * H * W < UP_FOLD_MIN_ROWS:
+            return self._conv(L.upsample_nearest2x(x, batch=B, h=H, w=W), cv, B, 2 * H, 2 * W, stats=True)
+        part = self._partial(x, B, 4 * H * W, cv.c_out) if (H * W) % 32 == 0 else None
+        out = L.conv_gemm(x, cv.w_up, batch=B, h_in=H, w_in=W, c_in=cv.c_in, ksize=3, bias=cv.b, upsample2x=True,
+                          gn_partial=part, gn_groups=GROUPS)
+        return out, part
 
     def _lin(self, x, lin: _Lin, residual=None, stats_bhw=None):
         """stats_bhw = (B, hw): also emit the GroupNorm moments of the output, viewed as B images of hw pixels."""
@@ -228,9 +242,8 @@ class VaeEngine:
             for j, r in enumerate(res):
                 x, xs = self._resnet(x, r, B, H, W, xs, stats=(us is None or j + 1 < len(res)))
             if us is not None:
-                x = L.upsample_nearest2x(x, batch=B, h=H, w=W)
+                x, xs = self._upsample_conv(x, us, B, H, W)
                 H, W = 2 * H, 2 * W
-                x, xs = self._conv(x, us, B, H, W, stats=True)
         t = self._gn(x, self.d_norm_out, B, H * W, True, xs)
         y = self._conv(t, self.d_conv_out, B, H, W)                      # [B*HW, 3]
         return L.image_out(y, batch=B, c=y.shape[1], h=H, w=W, dtype=dtype)

@@ -79,6 +79,27 @@ def conv_weight_khwc(w: torch.Tensor, c_in_pad: int = 0) -> torch.Tensor:
     return w.reshape(co, -1).contiguous().to(torch.float16)
 
 
+def upsample_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """w: [C_out, C_in, 3, 3] of the 3x3 convolution that follows a nearest-2x upsampling (diffusers Upsample2D:
+    F.interpolate(scale_factor=2.0, mode="nearest") + conv; reference block.py:2366,2476 and the VAE decoder's upsamplers).
+    Returns the phase-folded fp16 matrix [4*C_out, 4*C_in] of ir_conv_gemm_params.upsample2x: for output sub-pixel phase
+    (py, px), tap (a, b) reads low-resolution pixel (y + py - 1 + a, x + px - 1 + b) and carries the SUM of the 3x3 taps
+    that land on that pixel — rows ky -> a: py=0: {0} -> 0, {1, 2} -> 1;  py=1: {0, 1} -> 0, {2} -> 1 (likewise kx -> b).
+    Sums are taken in fp32 and rounded to fp16 once."""
+    c_out, c_in = w.shape[:2]
+    w = w.to(torch.float32).permute(0, 2, 3, 1)          # [C_out, ky, kx, C_in]
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    out = w.new_zeros((4, c_out, 2, 2, c_in))
+    for py in (0, 1):
+        for px in (0, 1):
+            for a, kys in enumerate(groups[py]):
+                for b, kxs in enumerate(groups[px]):
+                    for ky in kys:
+                        for kx in kxs:
+                            out[py * 2 + px, :, a, b] += w[:, ky, kx]
+    return out.reshape(4 * c_out, 4 * c_in).contiguous().to(torch.float16)
+
+
 def geglu_interleave_index(n_total: int) -> torch.Tensor:
     """Row permutation for the GEGLU projection: per 128-row block, 64 value rows then their 64 gate rows."""
     half = n_total // 2

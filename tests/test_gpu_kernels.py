@@ -192,6 +192,88 @@ def test_conv3x3_halo(L, B, H, W, Ci, Co, use_res):
         assert rel_l2(out, L.conv_gemm(a, wk, halo=1, **kw)) <= 3e-4      # same products, different fp32 summation order
 
 
+UP_CASES = [  # B, H, W, Ci, Co, kw
+    (1, 8, 8, 64, 64, {}),                                  # one half-empty tile per phase, one tile per CTA
+    (2, 8, 8, 128, 192, {}),                                # c_out not a multiple of the tile: the last N tile of a phase is clipped
+    (3, 16, 8, 64, 128, {}),                                # non-square, odd tile count per phase
+    (1, 16, 16, 1280, 1280, {}),                            # UNet up_blocks.1 upsampler at one identity (split-K clusters)
+    (4, 8, 8, 1280, 1280, {}),                              # UNet up_blocks.0 upsampler of the four reference images
+    (1, 32, 32, 640, 640, {}),                              # UNet up_blocks.2 upsampler
+    (4, 32, 32, 640, 640, dict(cta_pair=2, split_k=1)),     # CTA-pair kernel, 160-wide tiles
+    (1, 64, 64, 512, 512, {}),                              # VAE decoder up_blocks.0 upsampler (CTA pair, 256-wide tiles)
+    (1, 128, 128, 256, 256, dict(cta_pair=2, split_k=1)),   # several 128-pixel tiles per image row
+    (2, 64, 64, 128, 256, dict(cta_pair=1, no_persistent=2)),   # persistent single-CTA kernel
+    (2, 32, 32, 128, 128, dict(cta_pair=1, no_persistent=1)),   # one tile per CTA, no split
+    (1, 16, 16, 640, 128, dict(split_k=4)),                 # forced 4-way K split
+    (5, 4, 4, 64, 64, {}),                                  # several images per tile, ragged last tile
+]
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co,kw", UP_CASES, ids=[f"b{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}" + "".join(f"_{k}{v}" for k, v in c[5].items()) for c in UP_CASES])
+def test_upsample2x_conv3x3(L, B, H, W, Ci, Co, kw):
+    """ir_conv_gemm(upsample2x=1): nearest-2x + 3x3 conv (diffusers Upsample2D; reference block.py:2366,2476) as four
+    2x2 sub-pixel convolutions on the low-resolution input, against F.interpolate + F.conv2d in fp32."""
+    from instantrestore_b200.weights import upsample_conv_weight
+    g = _gen(41)
+    x = torch.randn(B, Ci, H, W, device="cuda", generator=g).half()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Ci)).half()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    up = F.interpolate(x.float(), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
+    a = x.permute(0, 2, 3, 1).contiguous().reshape(-1, Ci)
+    w_up = upsample_conv_weight(w)
+    assert w_up.shape == (4 * Co, 4 * Ci)
+    out = L.conv_gemm(a, w_up, batch=B, h_in=H, w_in=W, c_in=Ci, ksize=3, bias=bias, upsample2x=True, **kw)
+    assert out.shape == (4 * B * H * W, Co)
+    assert rel_l2(out, ref) <= TOL
+    assert torch.equal(out, L.conv_gemm(a, w_up, batch=B, h_in=H, w_in=W, c_in=Ci, ksize=3, bias=bias, upsample2x=True, **kw))
+    # the materialised path (upsample kernel + 3x3 conv on the large tensor) computes the same products
+    if (2 * H) & (2 * H - 1) == 0 and (2 * W) & (2 * W - 1) == 0:
+        wk = w.permute(0, 2, 3, 1).contiguous().reshape(Co, 9 * Ci)
+        big = L.conv_gemm(L.upsample_nearest2x(a, batch=B, h=H, w=W), wk, batch=B, h_in=2 * H, w_in=2 * W, c_in=Ci, ksize=3, bias=bias)
+        assert rel_l2(out, big) <= 5e-4       # folded taps are rounded to fp16 once more
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co,kw", [
+    (2, 64, 64, 512, 512, {}),                              # CTA pair
+    (1, 128, 128, 256, 256, {}),
+    (2, 32, 32, 128, 256, dict(cta_pair=1, no_persistent=2)),   # persistent single-CTA kernel
+    (1, 8, 8, 128, 128, {}),                                # one tile per CTA: statistics from the separate pass
+])
+def test_upsample2x_conv_emits_groupnorm_pass_a(L, B, H, W, Ci, Co, kw):
+    """The folded upsampler's epilogue writes pass A of the next GroupNorm over the FULL-resolution image (slab slots are
+    per phase: any partition of an image's pixels into 32-pixel slabs gives the same merged moments)."""
+    from instantrestore_b200.weights import upsample_conv_weight
+    g = _gen(42)
+    a = torch.randn(B * H * W, Ci, device="cuda", generator=g).half()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Ci)).half()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    gamma, beta = torch.randn(Co, device="cuda", generator=g), torch.randn(Co, device="cuda", generator=g)
+    hw = 4 * H * W
+    part = torch.full((L.gn_partial_numel(B, hw),), float("nan"), device="cuda")
+    args = dict(batch=B, h_in=H, w_in=W, c_in=Ci, ksize=3, bias=bias, upsample2x=True, **kw)
+    w_up = upsample_conv_weight(w)
+    y = L.conv_gemm(a, w_up, gn_partial=part, **args)
+    assert torch.equal(y, L.conv_gemm(a, w_up, **args))
+    assert torch.isfinite(part).all()
+    fused = L.groupnorm(y, gamma, beta, batch=B, hw=hw, eps=1e-6, silu=True, partial_in=part, fused=1)
+    plain = L.groupnorm(y, gamma, beta, batch=B, hw=hw, eps=1e-6, silu=True, fused=1)
+    assert rel_l2(fused, plain) <= 2e-4
+    x = y.float().view(B, hw, Co).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(x, 32, gamma, beta, eps=1e-6)).permute(0, 2, 1).reshape(-1, Co)
+    assert rel_l2(fused, ref) <= TOL
+
+
+def test_upsample2x_rejects_unsupported_combinations(L):
+    a = torch.zeros(64, 64, device="cuda").half()
+    w = torch.zeros(256, 256, device="cuda").half()
+    r = torch.zeros(256, 64, device="cuda").half()
+    p = L.ConvGemmParams(a=L.ptr(a), batch=1, h_in=8, w_in=8, c_in=64, a_row_stride=64, ksize=3, stride=1, w=L.ptr(w), c_out=64,
+                         residual=L.ptr(r), res_row_stride=64, out=L.ptr(r), out_row_stride=64, upsample2x=1)
+    import ctypes as C
+    assert L.load().ir_conv_gemm(C.byref(p), None) != 0          # residual + upsample2x
+
+
 @pytest.mark.parametrize("kind,B,H,W,Ci,Co,kw", [
     ("conv", 2, 128, 128, 128, 128, {}),                    # halo kernel, single CTA
     ("conv", 1, 128, 128, 256, 256, {}),                    # halo kernel, CTA pair

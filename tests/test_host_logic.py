@@ -202,3 +202,37 @@ def test_new_entry_points_reject_null_arguments_without_a_gpu():
     assert lib.ir_image_out_u8(None, None, 1, 1, None) == -5
     assert lib.ir_set_pdl(0) in (0, 1)
     assert lib.ir_set_pdl(0) == 0
+
+
+def test_upsample_conv_weight_fold_matches_upsample_then_conv():
+    """weights.upsample_conv_weight: the four 2x2 sub-pixel kernels of nearest-2x + conv3x3 (diffusers Upsample2D; reference
+    block.py:2366,2476), applied on the low-resolution tensor with the tap offsets ir_conv_gemm uses, reproduce
+    F.interpolate + F.conv2d (fp64: the fold itself is exact)."""
+    import torch
+    import torch.nn.functional as F
+    from instantrestore_b200.weights import upsample_conv_weight
+    g = torch.Generator().manual_seed(0)
+    B, Ci, Co, H, W = 2, 3, 5, 4, 6
+    x = torch.randn(B, Ci, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(Co, Ci, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, padding=1)
+    folded = upsample_conv_weight(w)
+    assert folded.dtype == torch.float16 and folded.shape == (4 * Co, 4 * Ci)
+    # exact fold in fp64 (the product path rounds it to fp16): redo the sums here
+    wk = w.permute(0, 2, 3, 1)
+    rows = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    out = torch.zeros(B, Co, 2 * H, 2 * W, dtype=torch.float64)
+    xp = F.pad(x, (1, 1, 1, 1))                                   # zero border == TMA out-of-bounds fill
+    for py in (0, 1):
+        for px in (0, 1):
+            acc = torch.zeros(B, Co, H, W, dtype=torch.float64)
+            for a, kys in enumerate(rows[py]):
+                for b, kxs in enumerate(rows[px]):
+                    tap = sum(wk[:, ky, kx] for ky in kys for kx in kxs)               # [Co, Ci]
+                    dy, dx = py - 1 + a, px - 1 + b
+                    patch = xp[:, :, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W]
+                    acc += torch.einsum("oc,bchw->bohw", tap, patch)
+                    got = folded.view(4, Co, 2, 2, Ci)[py * 2 + px, :, a, b].double()
+                    assert torch.allclose(got, tap, atol=2e-3, rtol=2e-3)                # fp16 rounding of the fold
+            out[:, :, py::2, px::2] = acc
+    assert torch.allclose(out, ref, atol=1e-12)
