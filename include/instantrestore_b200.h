@@ -254,6 +254,8 @@ typedef struct {
   float backbone_scale;
   float skip_scale;
   void* out;
+  int two_pass; /* A-B measurement: 0 = auto (8x8 and 16x16 FreeU stages run as ONE launch with the skip planes in registers),
+                   1 = always the concat kernel followed by the two-pass filter kernel (same sums, results within an fp16 ulp) */
 } ir_concat_freeu_params;
 int ir_concat_freeu(const ir_concat_freeu_params* p, ir_stream_t stream);
 
@@ -280,6 +282,11 @@ int ir_latent_out(const void* eps, int eps_row_stride, const float* x, const flo
  *   (the VAE mid-block attention is single-head with head_dim 512: scores are materialised by ir_conv_gemm exactly as
  *   the reference's baddbmm does, diffusers Attention.get_attention_scores.)
  * ir_image_in  — fp16 or fp32 NCHW image [batch, c, hw] -> fp16 channel-last [batch, hw, c_pad] (zero-padded).
+ * ir_image_in_patches3x3 — the same image as 3x3 patches (zero padding 1) in ONE 64-wide K block per pixel:
+ *   out[b, y, x, (ky*3+kx)*c + ch] = image[b, ch, y+ky-1, x+kx-1], zero for k >= 9c (needs 9c <= 64). The 3 -> 128 channel
+ *   conv_in of the VAE encoder (diffusers Encoder.conv_in as patched by reference models/model.py:15-30) then is ir_conv_gemm
+ *   with ksize 1, c_in 64 and the weight laid out [c_out, (ky, kx, ch) padded to 64]: the 27 products per output
+ *   instead of 576 (a 3x3 convolution over 64 zero-padded channels).
  * ir_image_out — fp16 channel-last [batch, hw, >= c] (row stride y_row_stride) -> NCHW clamp(lo, hi), fp16 or fp32.
  * ir_vae_sample — DiagonalGaussianDistribution.sample() * scaling_factor with the normal draw injected:
  *   moments fp16 channel-last [batch, hw, >= 2c] (mean | logvar); out[b,c,hw] = (mean + exp(0.5*clamp(logvar,-30,20))
@@ -287,6 +294,7 @@ int ir_latent_out(const void* eps, int eps_row_stride, const float* x, const flo
  */
 int ir_softmax_rows(void* x, int rows, int cols, int row_stride, float scale, ir_stream_t stream);
 int ir_image_in(const void* x, int x_is_fp32, void* out, int batch, int c, int hw, int c_pad, ir_stream_t stream);
+int ir_image_in_patches3x3(const void* x, int x_is_fp32, void* out, int batch, int c, int h, int w, ir_stream_t stream);
 int ir_image_out(const void* y, int y_row_stride, float lo, float hi, void* out, int out_is_fp32, int batch, int c,
                  int hw, ir_stream_t stream);
 int ir_vae_sample(const void* moments, int m_row_stride, const float* eps, float scale, float* out, int batch, int c,

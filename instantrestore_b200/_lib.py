@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "ir_shared_attn_workspace_bytes",
     "ir_groupnorm", "ir_groupnorm_workspace_bytes", "ir_groupnorm_fused_supported", "ir_layernorm", "ir_adain_coeffs", "ir_adain_workspace_bytes",
     "ir_concat_freeu", "ir_upsample_nearest2x", "ir_latent_in", "ir_latent_out",
-    "ir_softmax_rows", "ir_image_in", "ir_image_out", "ir_vae_sample",
+    "ir_softmax_rows", "ir_image_in", "ir_image_in_patches3x3", "ir_image_out", "ir_vae_sample",
     "ir_resample_u8_pass", "ir_u8_to_f16", "ir_image_out_u8",
 ]
 
@@ -83,7 +83,7 @@ class ConcatFreeuParams(C.Structure):
     _fields_ = [
         ("hidden", C.c_void_p), ("skip", C.c_void_p), ("batch", C.c_int), ("h", C.c_int), ("w", C.c_int),
         ("c_hidden", C.c_int), ("c_skip", C.c_int), ("backbone_scale", C.c_float), ("skip_scale", C.c_float),
-        ("out", C.c_void_p),
+        ("out", C.c_void_p), ("two_pass", C.c_int),
     ]
 
 
@@ -120,6 +120,7 @@ def load() -> C.CDLL:
                                   C.c_int, C.c_int, C.c_void_p]
     lib.ir_softmax_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
     lib.ir_image_in.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.ir_image_in_patches3x3.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.ir_image_out.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p]
     lib.ir_vae_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -518,14 +519,14 @@ def adain_coeffs(v_own: torch.Tensor | None, v_ref: torch.Tensor | None, *, batc
 
 
 def concat_freeu(hidden: torch.Tensor, skip: torch.Tensor, *, batch: int, h: int, w: int, backbone_scale: float = 1.0,
-                 skip_scale: float = 1.0, out: torch.Tensor | None = None) -> torch.Tensor:
+                 skip_scale: float = 1.0, out: torch.Tensor | None = None, two_pass: bool = False) -> torch.Tensor:
     _h(hidden, "hidden"); _h(skip, "skip")
     assert hidden.is_contiguous() and skip.is_contiguous()
     ch, cs = hidden.shape[-1], skip.shape[-1]
     if out is None:
         out = torch.empty((batch * h * w, ch + cs), dtype=torch.float16, device=hidden.device)
     p = ConcatFreeuParams(hidden=ptr(hidden), skip=ptr(skip), batch=batch, h=h, w=w, c_hidden=ch, c_skip=cs,
-                          backbone_scale=backbone_scale, skip_scale=skip_scale, out=ptr(out))
+                          backbone_scale=backbone_scale, skip_scale=skip_scale, out=ptr(out), two_pass=int(two_pass))
     with on_device(hidden):
         _run("ir_concat_freeu", f"b{batch}_hw{h * w}_c{ch}+{cs}", 0.0, 4.0 * batch * h * w * (ch + cs),
              load().ir_concat_freeu, C.byref(p), stream_ptr(hidden.device), keep=(hidden, skip, out))
@@ -589,6 +590,20 @@ def image_in(x: torch.Tensor, *, c_pad: int = 64, out: torch.Tensor | None = Non
     with on_device(x):
         _run("ir_image_in", f"b{b}_hw{hh * ww}", 0.0, b * hh * ww * (c * x.element_size() + 2.0 * c_pad), load().ir_image_in,
              ptr(x), int(x.dtype == torch.float32), ptr(out), b, c, hh * ww, c_pad, stream_ptr(x.device), keep=(x, out))
+    return out
+
+
+def image_in_patches3x3(x: torch.Tensor, *, out: torch.Tensor | None = None) -> torch.Tensor:
+    """x: fp16/fp32 NCHW image batch (9 * channels <= 64) -> fp16 [B*H*W, 64]: the 3x3 patch of every pixel, (ky, kx, ch)
+    order, zero padded — the A operand of conv_in as a K = 64 GEMM (weights: weights.patch_conv_weight)."""
+    if not x.is_cuda or not x.is_contiguous() or x.dtype not in (torch.float16, torch.float32):
+        raise TypeError("image_in_patches3x3: expected a contiguous CUDA fp16/fp32 NCHW tensor")
+    b, c, hh, ww = x.shape
+    if out is None:
+        out = torch.empty((b * hh * ww, 64), dtype=torch.float16, device=x.device)
+    with on_device(x):
+        _run("ir_image_in_patches3x3", f"b{b}_hw{hh * ww}", 0.0, b * hh * ww * (c * x.element_size() + 2.0 * 64), load().ir_image_in_patches3x3,
+             ptr(x), int(x.dtype == torch.float32), ptr(out), b, c, hh, ww, stream_ptr(x.device), keep=(x, out))
     return out
 
 

@@ -1625,7 +1625,12 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   // pairs only the 256-wide tiles.
   int bn_pair = 0;
   if (p->cta_pair < 0 || p->cta_pair > 2) return set_error(IR_ERR_ARG, "ir_conv_gemm: cta_pair=%d (0 = auto, 1 = off, 2 = force)", p->cta_pair);
-  if (p->cta_pair != 1 && split == 1 && m_tiles >= 2 && !(up && (kp.mtp & 1))) {
+  // upsample mode: both CTAs of a pair must share the phase (even tiles per phase); with GroupNorm statistics in the
+  // epilogue the short-K folded convolutions (K = 4 c_in) are epilogue-bound and the single-CTA 128 x 256 persistent tiles
+  // are ahead of the pair's coupled epilogues (tools/up_bench.py: 512 -> 512 @128^2 -> 256^2 134.6 vs 149.7 us, 256 -> 256
+  // @256^2 -> 512^2 157.6 vs 164.0)
+  const bool up_no_pair = up && ((kp.mtp & 1) || (kp.gn_partial && p->cta_pair != 2));
+  if (p->cta_pair != 1 && split == 1 && m_tiles >= 2 && !up_no_pair) {
     int cand = 0;
     if (p->c_out % 256 == 0 && (p->tile_n == 0 || p->tile_n == 256)) cand = 256;
     else if (p->c_out % 160 == 0 && !geglu && (p->tile_n == 0 || p->tile_n == 160)) cand = 160;

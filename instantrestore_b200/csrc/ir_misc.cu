@@ -281,6 +281,96 @@ __global__ void __launch_bounds__(256) freeu_skip_kernel(const __half* __restric
   }
 }
 
+// The same in ONE launch for the two FreeU stages of the step (8 x 8 and 16 x 16 skips): blocks [0, n_filter) filter 32 skip
+// channels each with the thread's PPT = hw / 8 pixels held in registers (one read; every load in flight at once) and the
+// twiddles in shared-memory tables (the two-pass kernel above evaluates two sincospif per pixel and pass); the remaining
+// blocks copy / scale image b's hidden half. Same operations in the same order as concat_kernel + freeu_skip_kernel:
+// results equal up to fp32 contraction (an fp16 ulp). 29.5 -> <= 14 us per call on the 16 x 16 x (1280 + 1280) stage (tools/misc_bench.py, host-launch bound).
+template <int PPT>
+__global__ void __launch_bounds__(256) freeu_concat_kernel(const __half* __restrict__ hidden, const __half* __restrict__ skip, int h, int w,
+                                                           int c_skip, int c_hidden, float bscale, float s, __half* __restrict__ out,
+                                                           int n_filter) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int hw = h * w;
+  const int c_tot = c_hidden + c_skip;
+  if (static_cast<int>(blockIdx.x) >= n_filter) {
+    const int nb = gridDim.x - n_filter, cb = blockIdx.x - n_filter;
+    const int vec_per_row = c_hidden >> 3, total = hw * vec_per_row, half_c = c_hidden >> 1;
+    const __half* hp = hidden + static_cast<size_t>(b) * hw * c_hidden;
+    __half* op = out + static_cast<size_t>(b) * hw * c_tot;
+    for (int v = cb * 256 + threadIdx.x; v < total; v += nb * 256) {
+      const int row = v / vec_per_row;
+      const int c0 = (v - row * vec_per_row) << 3;
+      uint4 u = *reinterpret_cast<const uint4*>(hp + static_cast<size_t>(row) * c_hidden + c0);
+      if (bscale != 1.0f && c0 < half_c) {
+        __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __half22float2(h2[j]);
+          f.x *= bscale;
+          f.y *= bscale;
+          h2[j] = __floats2half2_rn(f.x, f.y);
+        }
+      }
+      *reinterpret_cast<uint4*>(op + static_cast<size_t>(row) * c_tot + c0) = u;
+    }
+    return;
+  }
+  __shared__ float red[8][32][7];
+  __shared__ float coef[32][7];
+  __shared__ float tab[4][64];       // cos, sin of 2 pi m / h; cos, sin of 2 pi n / w
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (static_cast<int>(threadIdx.x) < h) sincospif(2.0f * threadIdx.x / h, &tab[1][threadIdx.x], &tab[0][threadIdx.x]);
+  else if (threadIdx.x >= 64 && static_cast<int>(threadIdx.x) - 64 < w) sincospif(2.0f * (threadIdx.x - 64) / w, &tab[3][threadIdx.x - 64], &tab[2][threadIdx.x - 64]);
+  const int c = blockIdx.x * 32 + lane;
+  const __half* xp = skip + static_cast<size_t>(b) * hw * c_skip + c;
+  float x[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) x[j] = __half2float(xp[static_cast<size_t>(warp + 8 * j) * c_skip]);
+  __syncthreads();
+  float a00 = 0.f, a10r = 0.f, a10i = 0.f, a01r = 0.f, a01i = 0.f, a11r = 0.f, a11i = 0.f;
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int px = warp + 8 * j;
+    const int m = px / w, n = px - m * w;
+    const float cm = tab[0][m], sm = tab[1][m], cn = tab[2][n], sn = tab[3][n];
+    a00 += x[j];
+    a10r += x[j] * cm;
+    a10i += x[j] * sm;
+    a01r += x[j] * cn;
+    a01i += x[j] * sn;
+    a11r += x[j] * (cm * cn - sm * sn);
+    a11i += x[j] * (sm * cn + cm * sn);
+  }
+  float* rr = red[warp][lane];
+  rr[0] = a00; rr[1] = a10r; rr[2] = a10i; rr[3] = a01r; rr[4] = a01i; rr[5] = a11r; rr[6] = a11i;
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += red[q][lane][k];
+      coef[lane][k] = t;
+    }
+  }
+  __syncthreads();
+  const float k = (1.0f - s) / hw;
+  const float* cf = coef[lane];
+  __half* op = out + static_cast<size_t>(b) * hw * c_tot + c_hidden + c;
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int px = warp + 8 * j;
+    const int m = px / w, n = px - m * w;
+    const float cm = tab[0][m], sm = tab[1][m], cn = tab[2][n], sn = tab[3][n];
+    const float corr = cf[0] + (cf[1] * cm + cf[2] * sm) + (cf[3] * cn + cf[4] * sn) +
+                       (cf[5] * (cm * cn - sm * sn) + cf[6] * (sm * cn + cm * sn));
+    op[static_cast<size_t>(px) * c_tot] = __float2half_rn(x[j] - k * corr);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ upsample
 __global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ x, __half* __restrict__ out, int h,
                                                          int w, int c, long total_vec) {
@@ -496,6 +586,80 @@ __global__ void image_in_kernel(const T* __restrict__ x, __half* __restrict__ ou
   }
 }
 
+// 3x3 patches of a few-channel NCHW image as ONE 64-wide K block per pixel: out[px, (ky*3+kx)*c + ch] = x[b, ch, y+ky-1, x+kx-1]
+// (zero outside the image and for k >= 9c). The VAE's conv_in (3 -> 128 channels, reference models/model.py:17 /
+// diffusers Encoder.conv_in) then is a K = 64 GEMM instead of a 3x3 convolution over 64 zero-padded channels (K = 576, 27
+// useful): the same 27 products per output, a ninth of the tensor work and of the operand traffic of that layer.
+// Eight threads per pixel, one 16-byte store each: a warp writes 512 contiguous bytes.
+template <typename T>
+__global__ void __launch_bounds__(256) image_patches_kernel(const T* __restrict__ x, __half* __restrict__ out, int c, int h, int w, long total_px) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long t = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const long px = t >> 3;
+  if (px >= total_px) return;
+  const int part = static_cast<int>(t & 7);
+  const int hw = h * w;
+  const long b = px / hw;
+  const int p = static_cast<int>(px - b * hw);
+  const int y = p / w, xx = p - y * w;
+  const int kmax = 9 * c;
+  __half v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = part * 8 + j;
+    float f = 0.f;
+    if (k < kmax) {
+      const int tap = k / c, ch = k - tap * c;
+      const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
+      if (yy >= 0 && yy < h && xc >= 0 && xc < w) f = static_cast<float>(x[(b * c + ch) * hw + yy * w + xc]);
+    }
+    v[j] = __float2half_rn(f);
+  }
+  *reinterpret_cast<uint4*>(out + px * 64 + part * 8) = *reinterpret_cast<const uint4*>(v);
+}
+
+// The same for C channels known at compile time (the RGB image): one thread per pixel, so the 9C loads of a warp are
+// coalesced along the image row; the warp's 32 x 128 B of patches go through shared memory (144-byte rows: conflict-free
+// 16-byte accesses) and leave as eight fully coalesced 512-byte stores.
+template <typename T, int C>
+__global__ void __launch_bounds__(256) image_patches_rows_kernel(const T* __restrict__ x, __half* __restrict__ out, int h, int w, long total_px) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ __align__(16) uint8_t tile[8][32 * 144];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long px0 = (blockIdx.x * 8L + warp) * 32;        // first pixel of this warp (total_px % 32 == 0)
+  if (px0 >= total_px) return;
+  const long px = px0 + lane;
+  const int hw = h * w;
+  const long b = px / hw;
+  const int p = static_cast<int>(px - b * hw);
+  const int y = p / w, xx = p - y * w;
+  constexpr int K = 9 * C, KP = (K + 7) / 8 * 8;
+  __half v[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    float f = 0.f;
+    if (k < K) {
+      const int tap = k / C, ch = k % C;
+      const int yy = y + tap / 3 - 1, xc = xx + tap % 3 - 1;
+      if (yy >= 0 && yy < h && xc >= 0 && xc < w) f = static_cast<float>(x[(b * C + ch) * hw + yy * w + xc]);
+    }
+    v[k] = __float2half_rn(f);
+  }
+  uint8_t* mine = tile[warp] + lane * 144;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<uint4*>(mine + q * 16) = q < KP / 8 ? *reinterpret_cast<const uint4*>(&v[q * 8]) : make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(out + px0 * 64);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = j * 32 + lane;
+    dst[idx] = *reinterpret_cast<const uint4*>(tile[warp] + (idx >> 3) * 144 + (idx & 7) * 16);
+  }
+}
+
 template <typename T>
 __global__ void image_out_kernel(const __half* __restrict__ y, int stride, float lo, float hi, T* __restrict__ out, int c,
                                  int hw, long total) {
@@ -607,6 +771,22 @@ extern "C" int ir_concat_freeu(const ir_concat_freeu_params* p, ir_stream_t stre
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long rows = static_cast<long>(p->batch) * p->h * p->w;
   const long total = rows * ((filt ? p->c_hidden : p->c_hidden + p->c_skip) >> 3);
+  const int hw = p->h * p->w;
+  if (filt && !p->two_pass && (hw == 64 || hw == 256) && p->h <= 64 && p->w <= 64) {     // the step's two FreeU stages: one launch
+    const int n_filter = p->c_skip / 32;
+    const long vec = static_cast<long>(hw) * (p->c_hidden >> 3);
+    const int n_copy = static_cast<int>(vec / 1024 < 1 ? 1 : (vec / 1024 > 108 ? 108 : vec / 1024));
+    dim3 grid(n_filter + n_copy, p->batch);
+    if (hw == 64) {
+      IR_LAUNCH(freeu_concat_kernel<8>, grid, 256, 0, stream, static_cast<const __half*>(p->hidden), static_cast<const __half*>(p->skip), p->h, p->w,
+                p->c_skip, p->c_hidden, p->backbone_scale, p->skip_scale, static_cast<__half*>(p->out), n_filter);
+    } else {
+      IR_LAUNCH(freeu_concat_kernel<32>, grid, 256, 0, stream, static_cast<const __half*>(p->hidden), static_cast<const __half*>(p->skip), p->h, p->w,
+                p->c_skip, p->c_hidden, p->backbone_scale, p->skip_scale, static_cast<__half*>(p->out), n_filter);
+    }
+    IR_CUDA_LAUNCH_CHECK("freeu_concat launch");
+    return 0;
+  }
   IR_LAUNCH(concat_kernel, grid_for(total, 256), 256, 0, stream, static_cast<const __half*>(p->hidden), static_cast<const __half*>(p->skip),
                                                           p->c_hidden, p->c_skip, p->backbone_scale, filt ? 0 : 1,
                                                           static_cast<__half*>(p->out), rows);
@@ -685,6 +865,28 @@ extern "C" int ir_image_in(const void* x, int x_is_fp32, void* out, int batch, i
   if (x_is_fp32) IR_LAUNCH(image_in_kernel<float>, blocks, 256, 0, stream, static_cast<const float*>(x), static_cast<__half*>(out), c, hw, c_pad, total_px);
   else IR_LAUNCH(image_in_kernel<__half>, blocks, 256, 0, stream, static_cast<const __half*>(x), static_cast<__half*>(out), c, hw, c_pad, total_px);
   IR_CUDA_LAUNCH_CHECK("image_in launch");
+  return 0;
+}
+
+extern "C" int ir_image_in_patches3x3(const void* x, int x_is_fp32, void* out, int batch, int c, int h, int w, ir_stream_t stream_) {
+  using namespace ir;
+  if (!x || !out) return set_error(IR_ERR_ARG, "ir_image_in_patches3x3: NULL argument");
+  if (int rc = check_arch()) return rc;
+  if (batch <= 0 || c <= 0 || 9 * c > 64 || h <= 0 || w <= 0) return set_error(IR_ERR_SHAPE, "ir_image_in_patches3x3: c=%d (9c must fit one 64-wide K block)", c);
+  if (reinterpret_cast<uintptr_t>(out) & 15) return set_error(IR_ERR_ALIGN, "ir_image_in_patches3x3: out not 16-byte aligned");
+  const long total_px = static_cast<long>(batch) * h * w;
+  const long blocks = (total_px * 8 + 255) / 256;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (c == 3 && total_px % 32 == 0) {
+    const unsigned rblocks = static_cast<unsigned>((total_px / 32 + 7) / 8);
+    if (x_is_fp32) IR_LAUNCH((image_patches_rows_kernel<float, 3>), rblocks, 256, 0, stream, static_cast<const float*>(x), static_cast<__half*>(out), h, w, total_px);
+    else IR_LAUNCH((image_patches_rows_kernel<__half, 3>), rblocks, 256, 0, stream, static_cast<const __half*>(x), static_cast<__half*>(out), h, w, total_px);
+    IR_CUDA_LAUNCH_CHECK("image_patches_rows launch");
+    return 0;
+  }
+  if (x_is_fp32) IR_LAUNCH(image_patches_kernel<float>, static_cast<unsigned>(blocks), 256, 0, stream, static_cast<const float*>(x), static_cast<__half*>(out), c, h, w, total_px);
+  else IR_LAUNCH(image_patches_kernel<__half>, static_cast<unsigned>(blocks), 256, 0, stream, static_cast<const __half*>(x), static_cast<__half*>(out), c, h, w, total_px);
+  IR_CUDA_LAUNCH_CHECK("image_patches launch");
   return 0;
 }
 

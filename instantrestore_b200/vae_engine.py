@@ -21,12 +21,13 @@ from typing import List, Optional
 import torch
 
 from . import _lib as L
-from .weights import StateDictView, conv_weight_khwc, upsample_conv_weight
+from .weights import StateDictView, conv_weight_khwc, patch_conv_weight, upsample_conv_weight
 
 GN_EPS = 1e-6
 GROUPS = 32
 FUSED_GN_STATS = os.environ.get("IR_FUSED_GN", "1") != "0"     # A-B measurement switch
 FOLD_UPSAMPLE = os.environ.get("IR_FOLD_UPSAMPLE", "1") != "0"  # A-B measurement switch
+PATCH_CONV_IN = os.environ.get("IR_PATCH_CONV_IN", "1") != "0"  # A-B measurement switch
 UP_FOLD_MIN_ROWS = int(os.environ.get("IR_UP_FOLD_MIN_ROWS", "0"))   # measured ahead on every shape (tools/up_bench.py)
 
 
@@ -70,6 +71,10 @@ class VaeEngine:
         if encoder:
             e = v.sub("encoder")
             self.e_conv_in = _Conv(e.weight("conv_in"), e.bias("conv_in"), dev, c_in_pad=64)
+            # conv_in on 3x3 patches gathered by ir_image_in_patches3x3: a K = 64 GEMM (27 useful) instead of K = 576
+            self.e_conv_in_patch = None
+            if PATCH_CONV_IN and 9 * e.weight("conv_in").shape[1] <= 64:
+                self.e_conv_in_patch = _Lin(patch_conv_weight(e.weight("conv_in")), e.bias("conv_in"), dev)
             self.e_down = []
             for i in range(len(boc)):
                 blk = e.sub(f"down_blocks.{i}")
@@ -208,8 +213,10 @@ class VaeEngine:
         """images: (B,3,H,W) fp16/fp32 CUDA in [-1,1]; eps: (B,4,H/8,W/8) fp32 normal draw or None (posterior mode).
         Returns latent_dist.sample() * scaling_factor, fp32 NCHW. Records the skip activations (model.py:19-30)."""
         B, _, H, W = images.shape
-        x = L.image_in(images.contiguous())
-        x, xs = self._conv(x, self.e_conv_in, B, H, W, stats=True)
+        if self.e_conv_in_patch is not None:
+            x, xs = self._lin(L.image_in_patches3x3(images.contiguous()), self.e_conv_in_patch, stats_bhw=(B, H * W))
+        else:
+            x, xs = self._conv(L.image_in(images.contiguous()), self.e_conv_in, B, H, W, stats=True)
         skips = []
         for res, ds in self.e_down:
             skips.append((x, H, W))

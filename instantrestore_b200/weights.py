@@ -79,6 +79,15 @@ def conv_weight_khwc(w: torch.Tensor, c_in_pad: int = 0) -> torch.Tensor:
     return w.reshape(co, -1).contiguous().to(torch.float16)
 
 
+def patch_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """[C_out, C_in, 3, 3] with 9 * C_in <= 64 -> fp16 [C_out, 64]: (ky, kx, ch) order, zero padded — the weight of a 3x3
+    convolution applied to the patches ir_image_in_patches3x3 writes (one 64-wide K block)."""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3 and 9 * ci <= 64, w.shape
+    flat = w.permute(0, 2, 3, 1).reshape(co, 9 * ci)
+    return torch.nn.functional.pad(flat, (0, 64 - 9 * ci)).contiguous().to(torch.float16)
+
+
 def upsample_conv_weight(w: torch.Tensor) -> torch.Tensor:
     """w: [C_out, C_in, 3, 3] of the 3x3 convolution that follows a nearest-2x upsampling (diffusers Upsample2D:
     F.interpolate(scale_factor=2.0, mode="nearest") + conv; reference block.py:2366,2476 and the VAE decoder's upsamplers).

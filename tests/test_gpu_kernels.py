@@ -595,6 +595,30 @@ def test_concat_freeu(L, B, H, Ch, Cs, bs, ss):
         x = torch.fft.ifftn(torch.fft.ifftshift(xf * mask, dim=(-2, -1)), dim=(-2, -1)).real
     ref = torch.cat([hh, x.permute(0, 2, 3, 1).reshape(B, H * W, Cs)], -1)
     assert rel_l2(out.reshape(B, H * W, -1), ref) <= TOL
+    # the one-launch kernel of the 8 x 8 / 16 x 16 stages performs the two-pass kernels' operations in the same order
+    two = L.concat_freeu(hid.reshape(-1, Ch), sk.reshape(-1, Cs), batch=B, h=H, w=W, backbone_scale=bs, skip_scale=ss, two_pass=True)
+    assert rel_l2(two.reshape(B, H * W, -1), ref) <= TOL
+    assert float((out.float() - two.float()).abs().max()) <= 4e-3      # same sums; fp32 contraction may differ by an fp16 ulp
+
+
+@pytest.mark.parametrize("B,C,H,W,dt", [(1, 3, 16, 16, torch.float16), (2, 3, 8, 24, torch.float32), (1, 3, 128, 128, torch.float16), (3, 7, 4, 4, torch.float32),
+                                        (2, 3, 64, 32, torch.float32), (1, 3, 5, 7, torch.float16), (1, 3, 512, 512, torch.float16)])
+def test_image_patches_conv_in(L, B, C, H, W, dt):
+    """ir_image_in_patches3x3 + a K = 64 GEMM == the VAE encoder's conv_in (3x3, padding 1) on the NCHW image: patches are
+    exact copies (bit-exact against F.unfold), the GEMM within the kernel tolerance of F.conv2d."""
+    from instantrestore_b200.weights import patch_conv_weight
+    g = _gen(45)
+    img = (torch.rand(B, C, H, W, device="cuda", generator=g) * 2 - 1).to(dt)
+    patches = L.image_in_patches3x3(img)
+    assert patches.shape == (B * H * W, 64)
+    un = F.unfold(img.float(), 3, padding=1).view(B, C, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 9 * C)     # (tap, ch) order
+    assert torch.equal(patches[:, : 9 * C], un.half())
+    assert not patches[:, 9 * C:].any()
+    w = (torch.randn(128, C, 3, 3, device="cuda", generator=g) / math.sqrt(9 * C)).half()
+    bias = torch.randn(128, device="cuda", generator=g)
+    out = L.conv_gemm(patches, patch_conv_weight(w), batch=1, h_in=1, w_in=B * H * W, c_in=64, bias=bias)
+    ref = F.conv2d(img.half().float(), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, 128)
+    assert rel_l2(out, ref) <= TOL
 
 
 def test_upsample_is_exact(L):
