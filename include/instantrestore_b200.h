@@ -114,6 +114,10 @@ typedef struct {
                      [batch, 2*h_in, 2*w_in, c_out]; w is the phase-folded matrix [4 phases (py*2+px)][c_out][2x2 taps (a*2+b)][c_in]
                      with tap (a, b) of phase (py, px) reading input pixel (y + py - 1 + a, x + px - 1 + b). Needs ksize 3,
                      stride 1, no residual / GEGLU / col_partial; never runs on the halo kernel */
+  int tma_store; /* A-B measurement: 0 = auto, 1 = never, 2 = always the TMA-store epilogue of the persistent kernel (output
+                    tile packed into a swizzled shared-memory box, one cp.async.bulk.tensor store per 128 x 64 half tile
+                    instead of per-thread row stores; results are bit-identical). Needs 128-wide full N tiles
+                    (c_out % 128 == 0), no residual / GEGLU / upsample2x */
 } ir_conv_gemm_params;
 int ir_conv_gemm(const ir_conv_gemm_params* p, ir_stream_t stream);
 

@@ -34,7 +34,7 @@ class ConvGemmParams(C.Structure):
         ("res_row_stride", C.c_int), ("act", C.c_int), ("out", C.c_void_p), ("out_row_stride", C.c_int),
         ("tile_n", C.c_int), ("split_k", C.c_int), ("m_sub", C.c_int), ("no_persistent", C.c_int), ("pad_hi_only", C.c_int),
         ("cta_pair", C.c_int), ("gn_partial", C.c_void_p), ("gn_groups", C.c_int), ("halo", C.c_int), ("wide_io", C.c_int),
-        ("col_partial", C.c_void_p), ("col_begin", C.c_int), ("upsample2x", C.c_int),
+        ("col_partial", C.c_void_p), ("col_begin", C.c_int), ("upsample2x", C.c_int), ("tma_store", C.c_int),
     ]
 
 
@@ -309,6 +309,7 @@ def _scratch(device, nbytes: int) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------------- wrappers
 _NARROW_IO = 1 if os.environ.get("IR_WIDE_IO", "1") == "0" else 0      # A-B switch: IR_WIDE_IO=0 -> 128-bit epilogue I/O
+_TMA_STORE = 1 if os.environ.get("IR_TMA_STORE", "1") == "0" else 0    # A-B switch: IR_TMA_STORE=0 -> per-thread row stores everywhere
 
 
 def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: int, c_in: int, ksize: int = 1,
@@ -316,7 +317,7 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
               act: int = IR_ACT_NONE, out: torch.Tensor | None = None, tile_n: int = 0, split_k: int = 0,
               a_row_stride: int | None = None, pad_hi_only: bool = False, no_persistent: int = 0, m_sub: int = 0, cta_pair: int = 0, halo: int = 0, gn_partial: torch.Tensor | None = None,
               gn_groups: int = 32, wide_io: int = 0, col_partial: torch.Tensor | None = None, col_begin: int = 0,
-              upsample2x: bool = False) -> torch.Tensor:
+              upsample2x: bool = False, tma_store: int = 0) -> torch.Tensor:
     """a: fp16 channel-last [batch*h_in*w_in, >=c_in]; w: fp16 [c_out, ksize*ksize*c_in].
     gn_partial: fp32 [batch * (h_out*w_out/32) * gn_groups * 2] (gn_partial_numel) to receive pass A of the next GroupNorm.
     col_partial: fp32 [M/32, c_out - col_begin, 2] to receive per-(32-row slab, column) (mean, M2) of the outputs (AdaIN).
@@ -340,7 +341,7 @@ def conv_gemm(a: torch.Tensor, w: torch.Tensor, *, batch: int, h_in: int, w_in: 
         residual=ptr(residual), res_row_stride=residual.stride(-2) if residual is not None else 0,
         act=act, out=ptr(out), out_row_stride=out.stride(-2), tile_n=tile_n, split_k=split_k,
         pad_hi_only=int(pad_hi_only), no_persistent=int(no_persistent), m_sub=m_sub, cta_pair=cta_pair, halo=halo, gn_partial=ptr(gn_partial), gn_groups=gn_groups, wide_io=wide_io or _NARROW_IO,
-        col_partial=ptr(col_partial), col_begin=col_begin)
+        col_partial=ptr(col_partial), col_begin=col_begin, tma_store=tma_store or _TMA_STORE)
     k_tot = ksize * ksize * c_in
     with on_device(a):
         _run("ir_conv_gemm", f"m{m}_k{k_tot}_n{c_out}_ks{ksize}s{stride}", 2.0 * m * k_tot * c_out,

@@ -39,6 +39,7 @@ constexpr int kABytes = kBM * kBK * 2;  // 16 KB
 struct GemmKParams {
   CUtensorMap tma_a[4];
   CUtensorMap tma_b;
+  CUtensorMap tma_out;   // TMA-store epilogue (persistent kernel, TSTORE): out as [M rows][N columns], 64-column x 128-row boxes
   int M, N, n_out;
   int kc_per_tap, taps;
   int tiles_w, tiles_h;
@@ -289,9 +290,10 @@ __device__ __forceinline__ void store_row64(__half* ptr, const uint4 (&r)[4], in
 // epilogue_store<32> with the residual already in registers (prefetched before the accumulator was ready)
 // `sbias`: optional shared-memory copy of the 32 bias values of this chunk (halo kernel: staged once per N tile; the
 // broadcast LDG.128s otherwise queue behind the thread-per-row residual loads and output stores in L1TEX).
+// everything of epilogue_store32_pre except the store: + bias, fp16 round, + residual, activation, statistics, pack
 template <bool COLS = false, bool UPOK = true>
-__device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4 (&res)[4], bool has_res, const GemmKParams& p,
-                                                     long grow, int gcol, const float* sbias = nullptr, int phase = 0) {
+__device__ __forceinline__ void epilogue_pack32(float (&v)[32], const uint4 (&res)[4], bool has_res, const GemmKParams& p,
+                                                long grow, int gcol, const float* sbias, int phase, uint4 (&packed)[4]) {
   if (p.bias) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -317,12 +319,18 @@ __device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4
   }
   if (p.gn_partial) gn_stats32<UPOK>(v, p, grow, gcol, phase);
   if (COLS && p.col_partial && gcol >= p.col_begin) col_stats32(v, p, grow, gcol);   // only instantiated without a residual
-  __half* op = p.out + (UPOK ? out_row(p, grow, phase) : grow) * p.out_stride + gcol;
-  uint4 packed[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
     packed[q] = make_uint4(pack_half2(v[q * 8], v[q * 8 + 1]), pack_half2(v[q * 8 + 2], v[q * 8 + 3]),
                            pack_half2(v[q * 8 + 4], v[q * 8 + 5]), pack_half2(v[q * 8 + 6], v[q * 8 + 7]));
+}
+
+template <bool COLS = false, bool UPOK = true>
+__device__ __forceinline__ void epilogue_store32_pre(float (&v)[32], const uint4 (&res)[4], bool has_res, const GemmKParams& p,
+                                                     long grow, int gcol, const float* sbias = nullptr, int phase = 0) {
+  uint4 packed[4];
+  epilogue_pack32<COLS, UPOK>(v, res, has_res, p, grow, gcol, sbias, phase, packed);
+  __half* op = p.out + (UPOK ? out_row(p, grow, phase) : grow) * p.out_stride + gcol;
   store_row64(op, packed, p.wide_io);
 }
 
@@ -641,10 +649,18 @@ __device__ __forceinline__ void geglu_store32(uint32_t taddr_v, const GemmKParam
 // MSUB = 2: a CTA tile is two stacked 128-row tiles (256 x BN) that share every weight box: the operand traffic per
 // MMA cycle drops from 128 to 96 B/clk for BN = 128, the width of the 128-channel VAE layers.
 // RESID: the launch carries a residual (and no GEGLU) — its values are prefetched into registers.
-template <int BN, int STAGES, int MSUB, bool RESID>
+// TSTORE (BN = 128, MSUB = 1, no residual): the epilogue warps write their packed fp16 rows into a shared-memory tile in
+// the 128-byte-swizzled box layout (16-byte pieces of 8 consecutive rows land in 8 different bank groups: conflict-free)
+// and one thread per 64-column half issues ONE TMA store per tile (cp.async.bulk.tensor...global.shared::cta) instead of
+// 128 threads x two 32-byte STG each to a different line: the thread-per-row stores are what keeps the L1TEX LSU pipe
+// the busiest unit of the short-K layers. Two staging buffers: tile t+1 is packed while the store
+// of tile t drains. Partial last M tiles are clipped by the tensor map.
+template <int BN, int STAGES, int MSUB, bool RESID, bool TSTORE = false>
 __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kernel(const __grid_constant__ GemmKParams p) {
+  static_assert(!TSTORE || (BN == 128 && MSUB == 1 && !RESID), "TMA-store epilogue: 128-wide tiles without residual");
   constexpr int B_BYTES = BN * kBK * 2;
   constexpr int STAGE_BYTES = MSUB * kABytes + B_BYTES;
+  constexpr int OUT_BYTES = TSTORE ? 2 * 2 * 16384 : 0;     // [buffer][column half] x (128 rows x 128 B)
   constexpr uint32_t ACC_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // columns per accumulator
   constexpr uint32_t TMEM_COLS = 2 * MSUB * ACC_COLS;                    // two stages x MSUB sub-tiles
   static_assert(TMEM_COLS <= 512, "accumulators do not fit in tensor memory");
@@ -654,7 +670,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                   // [STAGES][MSUB] x 16 KB
   uint8_t* sB = smem + STAGES * MSUB * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* sOut = smem + STAGES * STAGE_BYTES;          // 1024-aligned (STAGE_BYTES is a multiple of 16 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + OUT_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;    // accumulator stage ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;        // accumulator stage drained
@@ -670,6 +687,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tma_a[0]);
     tma_prefetch_desc(&p.tma_b);
+    if (TSTORE) tma_prefetch_desc(&p.tma_out);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -789,6 +807,44 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
       }
       mbar_wait(&tfull_bar[as], (local >> 1) & 1);
       tc_fence_after();
+      if constexpr (TSTORE) {
+        // (host guarantees: no GEGLU / residual / upsample mode, N % 128 == 0, 16-byte aligned bias)
+        const long grow = static_cast<long>(ms) * kBM + row;
+        const bool row_ok = grow < p.M;
+        uint8_t* stg = sOut + ((local & 1) * 2 + half) * 16384;
+        const uint32_t taddr = tmem_base + as * ACC_COLS + lane_addr;
+        const uint4 no_res[4] = {};
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c0 = half * 64 + ci * 32;
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            uint4 packed[4];
+            epilogue_pack32<true, false>(v, no_res, false, p, grow, nt * BN + c0, nullptr, 0, packed);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)     // 16-byte piece j = ci*4+q of this row, at its swizzled slot j ^ (row & 7)
+              *reinterpret_cast<uint4*>(stg + row * 128 + (((ci * 4 + q) ^ (row & 7)) << 4)) = packed[q];
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);               // the accumulator stage is drained: the next tile's MMAs may start
+        fence_proxy_async_smem();                   // my generic-proxy writes are visible to the TMA engine
+        const bool issuer = quarter == 0 && lane == 0;
+        // the previous tile's store (the OTHER buffer) has finished reading shared memory: after the barrier every
+        // thread of this half may overwrite it (the buffer written above was released one barrier earlier)
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(1 + half, 128);
+        if (issuer) {
+          tma_store_2d(&p.tma_out, stg, nt * BN + half * 64, ms * kBM);
+          tma_store_commit();
+        }
+        continue;
+      }
       if (p.act == IR_ACT_GEGLU) {
         if constexpr (BN % 128 == 0) {
 #pragma unroll 1
@@ -836,6 +892,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
+    if (TSTORE && quarter == 0 && lane == 0) tma_store_wait_read<0>();   // shared memory stays valid until the last store has read it
   }
 
   tc_fence_before();
@@ -1313,19 +1370,19 @@ static int launch_halo(const GemmKParams& kp, bool pair, cudaStream_t stream) {
   return resid ? launch_halo_r<128, false, true>(kp, stream) : launch_halo_r<128, false, false>(kp, stream);
 }
 
-template <int BN, int STAGES, int MSUB, bool RESID>
+template <int BN, int STAGES, int MSUB, bool RESID, bool TSTORE = false>
 static int launch_persistent_r(const GemmKParams& kp, cudaStream_t stream) {
-  constexpr int smem = STAGES * (MSUB * kABytes + BN * kBK * 2) + 1024 + 256;
+  constexpr int smem = STAGES * (MSUB * kABytes + BN * kBK * 2) + (TSTORE ? 65536 : 0) + 1024 + 256;
   static PerDeviceOnce attr_once;   // function attributes are per device
   bool& attr_done = attr_once.slot();
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, STAGES, MSUB, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, STAGES, MSUB, RESID, TSTORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(IR_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm_persistent<%d,%d>): %s", BN, MSUB, cudaGetErrorString(e));
     attr_done = true;
   }
   const long tiles = static_cast<long>((kp.m_tiles + MSUB - 1) / MSUB) * ((kp.N + BN - 1) / BN);
   const int grid = static_cast<int>(tiles < 148 ? tiles : 148);
-  IR_LAUNCH((conv_gemm_persistent_kernel<BN, STAGES, MSUB, RESID>), grid, kPersistThreads, smem, stream, kp);
+  IR_LAUNCH((conv_gemm_persistent_kernel<BN, STAGES, MSUB, RESID, TSTORE>), grid, kPersistThreads, smem, stream, kp);
   IR_CUDA_LAUNCH_CHECK("conv_gemm_persistent launch");
   return 0;
 }
@@ -1353,6 +1410,8 @@ static int launch(const GemmKParams& kp, int m_tiles, cudaStream_t stream) {
   IR_CUDA_LAUNCH_CHECK("conv_gemm launch");
   return 0;
 }
+
+constexpr int kTmaStoreMaxK = 4;   // auto mode: TMA-store epilogue up to this many 64-wide K blocks (tools/misc_bench.py)
 
 static int pow2_floor(int x) {
   int p = 1;
@@ -1675,6 +1734,20 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
     // 256 x 128 CTA tiles (two stacked M tiles sharing the weight boxes) when there are plenty of M tiles
     const bool tall = bn_tile == 128 && !geglu && m_tiles >= 2 * 148 && num_k >= 16 && p->m_sub != 1 && !up;
     *stats_fused = kp.gn_partial != nullptr;
+    // TMA-store epilogue: 128-wide full tiles without residual / GEGLU. Auto mode: the short-K launches whose epilogue
+    // is the bottleneck (the variant keeps 4 operand stages instead of 6 to make room for the staging tiles)
+    if (p->tma_store < 0 || p->tma_store > 2) return set_error(IR_ERR_ARG, "ir_conv_gemm: tma_store=%d (0 = auto, 1 = off, 2 = force)", p->tma_store);
+    const bool ts_ok = bn_tile == 128 && !tall && !geglu && !p->residual && !up && p->c_out % 128 == 0 && fast_epilogue &&
+                       p->out_row_stride % 8 == 0;
+    if (p->tma_store == 2 && !ts_ok)
+      return set_error(IR_ERR_SHAPE, "ir_conv_gemm: tma_store needs the persistent kernel with 128-wide full tiles, no residual / GEGLU / upsample2x");
+    if (ts_ok && (p->tma_store == 2 || (p->tma_store == 0 && num_k <= kTmaStoreMaxK))) {
+      uint64_t odims[2] = {static_cast<uint64_t>(p->c_out), static_cast<uint64_t>(kp.M)};
+      uint64_t ostr[1] = {static_cast<uint64_t>(p->out_row_stride) * 2};
+      uint32_t obox[2] = {64, 128};
+      if (int rc = make_tmap_f16(&kp.tma_out, p->out, 2, odims, ostr, obox)) return rc;
+      return launch_persistent_r<128, 4, 1, false, true>(kp, stream);
+    }
     switch (bn_tile) {
       case 64: return launch_persistent<64, 8, 1>(kp, stream);
       case 128: return tall ? launch_persistent<128, 4, 2>(kp, stream) : launch_persistent<128, 6, 1>(kp, stream);

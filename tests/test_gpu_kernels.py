@@ -192,6 +192,41 @@ def test_conv3x3_halo(L, B, H, W, Ci, Co, use_res):
         assert rel_l2(out, L.conv_gemm(a, wk, halo=1, **kw)) <= 3e-4      # same products, different fp32 summation order
 
 
+@pytest.mark.parametrize("M,K,N,kw", [
+    (4096, 64, 128, {}), (1000, 64, 128, {}), (16384, 320, 640, {}), (77, 128, 256, {}), (262144, 64, 128, dict(stats=True)),
+    (8192, 320, 1280, dict(cols=True)), (4096, 640, 384, dict(act=True)), (128 * 149 + 5, 64, 128, {}),
+])
+def test_tma_store_epilogue_is_bit_identical(L, M, K, N, kw):
+    """tma_store=2 (output tile packed into a swizzled shared-memory box, one cp.async.bulk.tensor store per half tile)
+    against tma_store=1 (per-thread row stores) on the same persistent kernel family: bit-identical outputs and statistics,
+    partial last M tiles clipped by the tensor map, nothing written past the tensor."""
+    g = _gen(51)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    args = dict(batch=1, h_in=1, w_in=M, c_in=K, bias=bias, tile_n=128, no_persistent=2, split_k=1, cta_pair=1)
+    if kw.get("act"):
+        args["act"] = L.IR_ACT_SILU
+    outs, parts = [], []
+    for mode in (1, 2):
+        extra = {}
+        if kw.get("stats"):
+            extra = dict(gn_partial=torch.full((L.gn_partial_numel(1, M),), float("nan"), device="cuda"))
+        if kw.get("cols"):
+            extra = dict(col_partial=torch.full((M // 32, N - 2 * N // 4, 2), float("nan"), device="cuda"), col_begin=2 * N // 4)
+        buf = torch.full((M + 64, N), 7.0, device="cuda", dtype=torch.float16)      # guard rows behind the tensor
+        outs.append(L.conv_gemm(a, w, out=buf[:M], tma_store=mode, **args, **extra))
+        parts.append(next(iter(extra.values())) if extra else None)
+        assert (buf[M:] == 7.0).all()
+    assert torch.equal(outs[0], outs[1])
+    if parts[0] is not None:
+        assert torch.isfinite(parts[1]).all() and torch.equal(parts[0], parts[1])
+    ref = a.float() @ w.float().T + bias
+    if kw.get("act"):
+        ref = F.silu(ref.half().float())
+    assert rel_l2(outs[1], ref) <= TOL
+
+
 UP_CASES = [  # B, H, W, Ci, Co, kw
     (1, 8, 8, 64, 64, {}),                                  # one half-empty tile per phase, one tile per CTA
     (2, 8, 8, 128, 192, {}),                                # c_out not a multiple of the tile: the last N tile of a phase is clipped

@@ -49,5 +49,27 @@ def main():
         print(f"image-in + conv_in B={B}: padded 3x3 conv {t1:7.1f} us (layout {t3:6.1f}) | patches + K=64 GEMM {t2:7.1f} us (patches {t4:6.1f}) | rel-L2 {err:.2e}", flush=True)
 
 
+def tma_store_bench():
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for M, K, N, stats in [(262144, 64, 128, True), (1048576, 64, 128, True), (2097152, 64, 128, True), (16384, 320, 640, False), (16384, 320, 1280, False),
+                           (65536, 320, 640, False), (131072, 320, 1280, False), (16384, 640, 640, False), (65536, 128, 128, False), (262144, 128, 256, False),
+                           (65536, 1280, 1280, False)]:
+        a = torch.randn(M, K, device="cuda", generator=g).half()
+        w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).half()
+        bias = torch.randn(N, device="cuda", generator=g)
+        part = torch.empty(L.gn_partial_numel(1, M), device="cuda") if stats else None
+        out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        args = dict(batch=1, h_in=1, w_in=M, c_in=K, bias=bias, out=out, gn_partial=part)
+        t0 = timeit(lambda: L.conv_gemm(a, w, tma_store=1, **args))
+        t1 = timeit(lambda: L.conv_gemm(a, w, tma_store=1, tile_n=128, no_persistent=2, split_k=1, cta_pair=1, **args))
+        t2 = timeit(lambda: L.conv_gemm(a, w, tma_store=2, tile_n=128, no_persistent=2, split_k=1, cta_pair=1, **args))
+        gb = 2.0 * (M * K + N * K + M * N) / 1e3
+        print(f"gemm m{M}_k{K}_n{N}{' +stats' if stats else ''}: auto (row stores) {t0:7.1f} us | persistent 128 row stores {t1:7.1f} us ({gb / t1:6.0f} GB/s) | "
+              f"TMA store {t2:7.1f} us ({gb / t2:6.0f} GB/s, {2.0 * M * K * N / t2 / 1e6:6.0f} TF/s)", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tma":
+        tma_store_bench()
+        sys.exit(0)
     main()
