@@ -79,4 +79,3 @@ def test_tma_store_epilogue_is_a_bulk_tensor_store(sass):
     for name, lines in found.items():
         text = "\n".join(lines)
         assert "UTMASTG.2D" in text, f"{name}: no TMA store"
-        assert "UTMACMDFLUSH" in text or "UTMACCTL" in text or "DEPBAR" in text or True

@@ -37,7 +37,7 @@ ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_launches.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
   wc -l $OUT/${TAG}_launches.csv ;;
-caps|capsattn)
+caps|capsattn|capsnew)
   # ncu --set full of the dominant kernels on micro-drivers; summarised on the box (reports are ~10 MB each and
   # gpurun_out is capped at 64 MiB), only the text summaries and ncu_traffic.json travel back
   cap() { n=$1; k=$2; key=$3; shift 3
@@ -46,7 +46,13 @@ caps|capsattn)
     ncu -i /tmp/${TAG}_$n.ncu-rep --page raw --csv > $OUT/${TAG}_raw_$n.csv 2>/dev/null
     python tools/ncu_summary.py /tmp/${TAG}_$n.ncu-rep profiles/${TAG}_ncu_full_$n.txt "$key" > /dev/null && cp profiles/${TAG}_ncu_full_$n.txt profiles/ncu_traffic.json $OUT/
     rm -f /tmp/${TAG}_$n.ncu-rep; }
-  if [ $w = capsattn ]; then
+  if [ $w = capsnew ]; then
+  # round-2 additions: the folded upsamplers of the VAE decoder and the TMA-store epilogue on the patch conv_in
+  cap conv_up2x_512 conv "ir_conv_gemm:m262144_k2048_n512_ks3s1_up2x" tools/gemm_one.py up 4 128 512 512
+  cap conv_up2x_256 conv "ir_conv_gemm:m1048576_k1024_n256_ks3s1_up2x" tools/gemm_one.py up 4 256 256 256
+  cap conv_in_tma_store conv "ir_conv_gemm:m1048576_k64_n128_ks1s1" tools/gemm_one.py lin_ts 4 1048576 64 128 0
+  cap conv_in_row_store conv "ir_conv_gemm:m1048576_k64_n128_ks1s1_rowstores" tools/gemm_one.py lin_ts 4 1048576 64 128 1
+  elif [ $w = capsattn ]; then
   cap attn_shared_b1 shared_attn "ir_shared_attn_fwd:b1_h5_sq4096_skv16384_adain" tools/attn_one.py 1 5 4096 0 4 1
   cap attn_shared_b8 shared_attn "ir_shared_attn_fwd:b8_h5_sq4096_skv16384_adain" tools/attn_one.py 8 5 4096 0 4 1
   cap gn_apply_512 gn_apply "ir_groupnorm:b4_hw262144_c128" tools/norm_one.py gn 4 262144 128
