@@ -2,7 +2,7 @@
 # compute-sanitizer over the kernel-level parity tests: memcheck on every kernel family at small
 # shapes, racecheck (shared-memory hazards) and synccheck on the kernels that synchronise through shared memory /
 # clusters without the async proxy (norms, AdaIN statistics, concat, layout kernels). Summaries -> gpurun_out/<tag>_san_*.txt
-# usage: tools/sanitize.sh <tag>
+# usage: tools/sanitize.sh <tag> [new]
 TAG=${1:-r02}; OUT=gpurun_out; mkdir -p $OUT
 SAN=/usr/local/cuda/bin/compute-sanitizer
 SMALL='groupnorm or layernorm or adain or concat or upsample or latent_in or softmax'
@@ -14,6 +14,12 @@ run() {  # name tool timeout pytest-args...
     grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|Invalid|hazard|error" $OUT/${TAG}_san_$n.log | sort | uniq -c | sort -rn | head -15; } > $OUT/${TAG}_san_$n.txt
   cat $OUT/${TAG}_san_$n.txt
 }
+if [ "${2:-all}" = new ]; then   # the kernels added last: folded upsamplers, TMA-store epilogue, one-launch FreeU, image patches
+  run new_memcheck memcheck 1200 tests/test_gpu_kernels.py -k "upsample2x or tma_store or concat_freeu or image_patches"
+  run new_racecheck racecheck 600 tests/test_gpu_kernels.py -k "concat_freeu or image_patches"
+  run faceid_memcheck memcheck 900 tests/test_gpu_pipeline.py -k "faceid and eager"
+  exit 0
+fi
 run norms_memcheck memcheck 900 tests/test_gpu_kernels.py -k "$SMALL"
 # racecheck does not model tcgen05.alloc's shared-memory write (it reports it against the read that follows the barrier +
 # tcgen05 fences), so the GEMM-launching tests are left out of this pass

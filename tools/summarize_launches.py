@@ -12,7 +12,7 @@ def main():
     with open(src) as f:
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
-    ii = [i for i, r in enumerate(rows) if "image_in_kernel" in r["Kernel Name"]]
+    ii = [i for i, r in enumerate(rows) if "image_in_kernel" in r["Kernel Name"] or "image_patches" in r["Kernel Name"]]
     if ii:      # image pipeline: a step = [image_in (refs), image_in (degraded), ...]
         starts = ii[0::2]
     else:       # latent pipeline: a step = [ref latent_in, main latent_in, ...]
