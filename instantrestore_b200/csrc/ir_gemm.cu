@@ -1651,8 +1651,38 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   if (geglu && bn_tile % 128 != 0) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: GEGLU needs tile_n 128 or 256");
   (void)pow2_floor;
 
-  // split-K over a cluster when the output tiles alone cannot fill the 148 SMs (see the header comment)
   const int num_k = taps * kp.kc_per_tap;
+  // CTA-pair kernel, automatic choice (made before the K split: a launch that pairs is never split). tools/pair_sweep.py
+  // times every (op, shape) of a step with the pair forced at 256 / 160 / 128-wide tiles against the previous choice
+  // (profiles/r02aj_pair_sweep_b{1,8}.txt). What it showed: the one-tile kernel's 128 x 128 tiles with a 2-way K split are
+  // bound by L2 -> SM operand traffic on the mid-size long-K layers (m4096_k4608_n512: 256 CTAs x 36 K-blocks x 32 KB =
+  // 295 MB per launch at the 11 TB/s the crossbar delivers); 256 x 128 pair tiles move 25 % less (each CTA loads HALF of
+  // the weight box) and need no exchange: 27.5 -> 19.2 us (18 launches per step), m1024_k5120_n1280 26.1 -> 19.2,
+  // m1024_k11520_n1280 41.9 -> 34.8. 160-wide pair tiles win on the 640 / 1280-channel linears from 64 pair tiles
+  // (m4096_k2560_n640 20.8 -> 15.8, m4096_k640_n640 11.2 -> 9.7; at 8 identities m2048_k11520_n1280 66.1 -> 43.6,
+  // m2048_k5120_n1280 34.0 -> 23.9) and are ahead of the 256-wide ones whenever both apply below 296 tiles.
+  int bn_pair_auto = 0;
+  // upsample mode: both CTAs of a pair must share the phase (even tiles per phase); with GroupNorm statistics in the
+  // epilogue the short-K folded convolutions (K = 4 c_in) are epilogue-bound and the single-CTA 128 x 256 persistent tiles
+  // are ahead of the pair's coupled epilogues (tools/up_bench.py: 512 -> 512 @128^2 -> 256^2 134.6 vs 149.7 us, 256 -> 256
+  // @256^2 -> 512^2 157.6 vs 164.0)
+  const bool up_no_pair = up && ((kp.mtp & 1) || (kp.gn_partial && p->cta_pair != 2));
+  if (p->cta_pair == 0 && p->tile_n == 0 && p->split_k == 0 && p->no_persistent != 1 && !geglu && m_tiles >= 2 && !up_no_pair) {
+    const long m_pairs = (m_tiles + 1) / 2;
+    const bool conv3 = p->ksize == 3;
+    const long pt256 = p->c_out % 256 == 0 ? m_pairs * (p->c_out / 256) : 0;
+    const long pt160 = p->c_out % 160 == 0 ? m_pairs * (p->c_out / 160) : 0;
+    const long pt128 = p->c_out % 128 == 0 ? m_pairs * (p->c_out / 128) : 0;
+    const bool ok256 = pt256 && ((conv3 && num_k >= 18 && pt256 >= 64) || (num_k >= 16 && pt256 >= 296));
+    const bool ok160 = pt160 && ((conv3 && num_k >= 18 && pt160 >= 64) || (num_k >= 16 && pt160 >= 296) ||
+                                 (!conv3 && pt160 >= 64 && pt160 <= 296 && (num_k >= 20 || (num_k >= 10 && pt160 <= 74))));
+    const bool ok128 = pt128 && num_k >= 40 && pt128 >= 40 && pt128 <= 148;
+    if (ok256 && !(ok160 && pt256 < 296)) bn_pair_auto = 256;
+    else if (ok160) bn_pair_auto = 160;
+    else if (ok128) bn_pair_auto = 128;
+  }
+
+  // split-K over a cluster when the output tiles alone cannot fill the 148 SMs (see the header comment)
   int split = 1;
   if (p->split_k < 0 || p->split_k > 8 || (p->split_k & (p->split_k - 1)))
     return set_error(IR_ERR_ARG, "ir_conv_gemm: split_k=%d (0 = auto, 1, 2, 4 or 8)", p->split_k);
@@ -1661,11 +1691,11 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
     if (!can_split) return set_error(IR_ERR_SHAPE, "ir_conv_gemm: split_k needs c_out %% 64 == 0 and no GEGLU");
     split = p->split_k;
   }
-  if (can_split && !wide_persistent && (p->split_k == 0 || p->split_k > 1) && p->tile_n == 0) {
+  if (can_split && !wide_persistent && !bn_pair_auto && (p->split_k == 0 || p->split_k > 1) && p->tile_n == 0) {
     // narrower N tile first when even 8-way split of 128-wide tiles leaves most SMs idle
     if (static_cast<long>(m_tiles) * ((p->c_out + bn_tile - 1) / bn_tile) * 8 < 148 && bn_tile > 64) bn_tile = 64;
   }
-  if (can_split && !wide_persistent && p->split_k == 0 && p->c_out % bn_tile == 0 && (bn_tile == 64 || bn_tile == 128)) {
+  if (can_split && !wide_persistent && !bn_pair_auto && p->split_k == 0 && p->c_out % bn_tile == 0 && (bn_tile == 64 || bn_tile == 128)) {
     // K split only while every CTA of the cluster keeps >= 16 K-blocks: below that the cluster launch, the two cluster
     // barriers and the DSMEM exchange cost more than the idle SMs (tools/small_gemm_bench.py, device time per launch:
     // m1024_k1280_n1280 15.5 us with a 2-way split vs 9.3 without, m1024_k640_n640 12.0 vs 7.3, m256_k1280_n3840 14.5 vs 8.5;
@@ -1675,7 +1705,7 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   }
   // unsplit launches that fill less than half of the SMs: 64-wide tiles double the CTA count (m1024_k640_n640 7.3 -> 5.9 us,
   // m256_k1280_n1280 8.6 -> 7.0, m256_k1280_n3840 8.5 -> 7.4, m4096_k320_n320 7.5 -> 6.6)
-  if (split == 1 && p->split_k == 0 && p->tile_n == 0 && !geglu && !wide_persistent && bn_tile > 64 && p->c_out % 64 == 0 &&
+  if (split == 1 && !bn_pair_auto && p->split_k == 0 && p->tile_n == 0 && !geglu && !wide_persistent && bn_tile > 64 && p->c_out % 64 == 0 &&
       static_cast<long>(m_tiles) * ((p->c_out + bn_tile - 1) / bn_tile) < 74)
     bn_tile = 64;
   if (split > 1 && (p->c_out % bn_tile != 0 || (bn_tile / split) % 8 != 0 || num_k < split))
@@ -1690,29 +1720,16 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
   // CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 or 256 x 128 tiles over the two SMs of a TPC). Measured
   // (tools/pair_bench.py): ahead of the single-CTA kernels once there are >= 4 tiles per cluster and K >= 1024; behind
   // them on short-K / GEGLU launches (the accumulator hand-over couples the two epilogues), on few-tile launches and
-  // for 128-wide outputs (256 x 128 pair tiles: 798 vs 905 TFLOP/s of the stacked-M single-CTA kernel) — auto mode
-  // pairs only the 256-wide tiles.
+  // for 128-wide outputs with plenty of tiles (256 x 128 pair tiles: 798 vs 905 TFLOP/s of the stacked-M single-CTA
+  // kernel). The automatic choice (bn_pair_auto) is made above, before the K split.
   int bn_pair = 0;
   if (p->cta_pair < 0 || p->cta_pair > 2) return set_error(IR_ERR_ARG, "ir_conv_gemm: cta_pair=%d (0 = auto, 1 = off, 2 = force)", p->cta_pair);
-  // upsample mode: both CTAs of a pair must share the phase (even tiles per phase); with GroupNorm statistics in the
-  // epilogue the short-K folded convolutions (K = 4 c_in) are epilogue-bound and the single-CTA 128 x 256 persistent tiles
-  // are ahead of the pair's coupled epilogues (tools/up_bench.py: 512 -> 512 @128^2 -> 256^2 134.6 vs 149.7 us, 256 -> 256
-  // @256^2 -> 512^2 157.6 vs 164.0)
-  const bool up_no_pair = up && ((kp.mtp & 1) || (kp.gn_partial && p->cta_pair != 2));
-  if (p->cta_pair != 1 && split == 1 && m_tiles >= 2 && !up_no_pair) {
-    int cand = 0;
-    if (p->c_out % 256 == 0 && (p->tile_n == 0 || p->tile_n == 256)) cand = 256;
-    else if (p->c_out % 160 == 0 && !geglu && (p->tile_n == 0 || p->tile_n == 160)) cand = 160;
-    else if (p->c_out % 128 == 0 && (p->tile_n == 0 || p->tile_n == 128)) cand = 128;
-    if (cand) {
-      const long ptiles = static_cast<long>((m_tiles + 1) / 2) * (p->c_out / cand);
-      if (p->cta_pair == 2) bn_pair = cand;
-      // auto: 3x3 convolutions (K >= 1152) from 64 pair tiles, linears from 4 tiles per cluster; not the 128-wide
-      // tiles (the stacked-M single-CTA kernel and the halo kernel are ahead there)
-      else if (!geglu && p->no_persistent != 1 && cand != 128 && p->split_k == 0 &&
-               ((p->ksize == 3 && num_k >= 18 && ptiles >= 64) || (num_k >= 16 && ptiles >= 296)))
-        bn_pair = cand;
-    }
+  if (p->cta_pair == 2 && split == 1 && m_tiles >= 2 && !up_no_pair) {       // forced: the widest tile the arguments allow
+    if (p->c_out % 256 == 0 && (p->tile_n == 0 || p->tile_n == 256)) bn_pair = 256;
+    else if (p->c_out % 160 == 0 && !geglu && (p->tile_n == 0 || p->tile_n == 160)) bn_pair = 160;
+    else if (p->c_out % 128 == 0 && (p->tile_n == 0 || p->tile_n == 128)) bn_pair = 128;
+  } else if (split == 1) {
+    bn_pair = bn_pair_auto;
   }
   if (p->cta_pair == 2 && !bn_pair)
     return set_error(IR_ERR_SHAPE, "ir_conv_gemm: cta_pair needs c_out %% 128 == 0 or %% 160 == 0, no K split, >= 2 M tiles (c_out=%d split=%d m_tiles=%d)", p->c_out, split, m_tiles);
