@@ -8,6 +8,11 @@
 //       128 B/clk shared-memory port for the K/V operand reads. The two warpgroups run out of phase, so the MUFU pipe
 //       (the bound at d=64: 16 exp/clk/SM vs 8192 MMA FLOP/clk/SM) always has work while the tensor pipe runs the
 //       other tile's QK^T / PV.
+//   Score buffers ROTATE between the two query tiles: slot k = 2 * (KV tile) + (query tile) uses buffer k % NB. The
+//       AdaIN variant needs the TMEM for its second accumulator (NB = 2: every query tile owns one buffer); the plain
+//       variant has 128 free columns (NB = 3), so QK^T of slot k + 3 is issued right after PV of slot k -- one slot
+//       (half a period) EARLIER than with two buffers -- and the round trip softmax -> P -> PV -> QK^T -> scores (about
+//       800 clk of issue, MMA and commit latency, 21 % of the stall samples of the two-buffer kernel) is hidden.
 //   warp 8 (one lane): TMA producer — both Q tiles once, then K/V tiles straight out of the token-major projection
 //       outputs (the head split is just the TMA column coordinate), 128B-swizzled, 4-stage ring.
 //   warp 9 (one lane): tcgen05.mma issuer — S_i = Q_i K_j^T (TMEM, 128 columns per tile), O_i += P_i V_j (A = P from
@@ -36,7 +41,6 @@ constexpr int kKVStages = 4;
 constexpr int kMaxRef = 16;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8, exact in fp16 / fp32 accumulation
 constexpr int kAttnThreads = 320;
-constexpr bool kPingPong = false;         // strict alternation of the two warpgroups on the exp pass
 #ifndef IR_ATTN_POLY_OF8
 #define IR_ATTN_POLY_OF8 2
 #endif
@@ -69,8 +73,11 @@ constexpr int kOffAdain = kOffV + kKVStages * kTileBytes;   // [kMaxRef][2][64] 
 constexpr int kOffBar = kOffAdain + kMaxRef * 2 * 64 * 4;
 constexpr int kAttnSmem = kOffBar + 256 + 1024;
 
-// TMEM columns: S0 | S1 | O0 | O1 | ACC0 | ACC1   (P_i = packed fp16, aliases the first 64 columns of S_i)
-constexpr uint32_t kTmemS = 0, kTmemO = 256, kTmemAcc = 384;
+// TMEM columns: AdaIN  S(buf 0) | S(buf 1) | O0 | O1 | ACC0 | ACC1
+//               plain  S(buf 0) | S(buf 1) | S(buf 2) | O0 | O1        (P = packed fp16, aliases the first 64 columns of its S)
+constexpr uint32_t kTmemS = 0, kTmemAcc = 384;
+template <bool ADAIN> constexpr int kNBuf = ADAIN ? 2 : 3;
+template <bool ADAIN> constexpr uint32_t kTmemO = kNBuf<ADAIN> * kKT;
 
 struct TileRef {
   int chunk;   // 0 = own (when present), else 1 + reference index (or reference index when no own chunk)
@@ -202,10 +209,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
   uint64_t* q_full = bars;                   // 1
   uint64_t* kv_full = bars + 1;              // kKVStages
   uint64_t* kv_empty = kv_full + kKVStages;  // kKVStages
-  uint64_t* s_full = kv_empty + kKVStages;   // 2 (per query tile)
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_done = p_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  constexpr int NB = kNBuf<ADAIN>;
+  uint64_t* s_full = kv_empty + kKVStages;   // 3 (per score buffer)
+  uint64_t* p_full = s_full + 3;             // 3
+  uint64_t* o_done = p_full + 3;             // 2 (per query tile): one phase per PV
+  uint64_t* all_done = o_done + 2;           // 1: every MMA of the CTA has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -221,11 +230,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     if (p.n_ref) { tma_prefetch_desc(&p.tma_k_ref); tma_prefetch_desc(&p.tma_v_ref); }
     mbar_init(q_full, 1);
     for (int s = 0; s < kKVStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
-      mbar_init(&o_done[i], 1);
     }
+    for (int i = 0; i < 2; ++i) mbar_init(&o_done[i], 1);
+    mbar_init(all_done, 1);
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -279,43 +289,61 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
       // descriptors are (constant high word, low word = address >> 4 | LBO): stepping K or the stage is an integer add;
       // the issue loop has to stay far below the 512 clk of tensor work per (KV tile, query tile)
       const uint32_t q_lo0 = umma_desc_lo(smem_u32(sQ)), k_lo0 = umma_desc_lo(smem_u32(sK)), v_lo0 = umma_desc_lo_mn(smem_u32(sV));
-      auto issue_qk = [&](int jj, int i) {
-        const uint32_t k_lo = k_lo0 + (jj % kKVStages) * (kTileBytes >> 4);
-        const uint32_t q_lo = q_lo0 + i * (kTileBytes >> 4);
+      // slot k = 2 * (KV tile) + (query tile) lives in score buffer k % NB
+      auto issue_qk = [&](int k, int buf) {
+        const uint32_t k_lo = k_lo0 + ((k >> 1) % kKVStages) * (kTileBytes >> 4);
+        const uint32_t q_lo = q_lo0 + (k & 1) * (kTileBytes >> 4);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_f16_ss_lo(tmem_base + kTmemS + i * kKT, q_lo + 2 * k, k_lo + 2 * k, IDESC_QK, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[i]);
+        for (int kk = 0; kk < kD / 16; ++kk)
+          umma_f16_ss_lo(tmem_base + kTmemS + buf * kKT, q_lo + 2 * kk, k_lo + 2 * kk, IDESC_QK, kk != 0 ? 1u : 0u);
+        umma_commit(&s_full[buf]);
       };
+      int kv_ready = -1;          // highest KV tile whose arrival has been waited for
+      auto need_kv = [&](int jj) {
+        if (jj > kv_ready) {
+          mbar_wait(&kv_full[jj % kKVStages], (jj / kKVStages) & 1);
+          tc_fence_after();
+          kv_ready = jj;
+        }
+      };
+      const int n_slots = 2 * n_tiles;
       mbar_wait(q_full, 0);
-      if (n_tiles > 0) {
-        mbar_wait(&kv_full[0], 0);
-        tc_fence_after();
-        issue_qk(0, 0);
-        issue_qk(0, 1);
+      for (int k = 0; k < NB && k < n_slots; ++k) {
+        need_kv(k >> 1);
+        issue_qk(k, k);
       }
       TileRef mt = locate_tile(p, g_begin);
+      int kb_run = 0;             // buffer and barrier phase of the current slot (NB = 2: compile-time, = query tile)
+      uint32_t kp_run = 0;
       for (int jj = 0; jj < n_tiles; ++jj) {
         const int s = jj % kKVStages;
         // a segment (AdaIN: one chunk; otherwise the whole range) starts with a fresh accumulator
         const bool fresh = (jj == 0) || (ADAIN && mt.t == 0);
         if (++mt.t == (mt.ref < 0 ? p.own_tiles : p.ref_tiles)) { mt.t = 0; ++mt.ref; }
         const uint32_t v_lo = v_lo0 + s * (kTileBytes >> 4);
-        if (jj + 1 < n_tiles) mbar_wait(&kv_full[(jj + 1) % kKVStages], ((jj + 1) / kKVStages) & 1);
+        // K tiles of the QK^Ts issued below: waited for here, off the chain P published -> PV -> QK^T -> scores
+        if (2 * jj + NB < n_slots) need_kv((2 * jj + NB) >> 1);
+        if (2 * jj + 1 + NB < n_slots) need_kv((2 * jj + 1 + NB) >> 1);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          mbar_wait(&p_full[i], jj & 1);
+          const int kb = NB == 2 ? i : kb_run;
+          const uint32_t kp = NB == 2 ? static_cast<uint32_t>(jj & 1) : kp_run;
+          mbar_wait(&p_full[kb], kp);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < kKT / 16; ++kk)
-            umma_f16_ts_lo(tmem_base + kTmemO + i * kD, tmem_base + kTmemS + i * kKT + kk * 8, v_lo + kk * (2048 >> 4), IDESC_PV,
+            umma_f16_ts_lo(tmem_base + kTmemO<ADAIN> + i * kD, tmem_base + kTmemS + kb * kKT + kk * 8, v_lo + kk * (2048 >> 4), IDESC_PV,
                            (kk != 0 || !fresh) ? 1u : 0u);
           umma_commit(&o_done[i]);
-          // tcgen05.mma executes in issue order: the next QK^T refills S_i only after this PV has read P_i out of it
-          if (jj + 1 < n_tiles) issue_qk(jj + 1, i);
+          // tcgen05.mma executes in issue order: QK^T of slot k + NB refills this buffer only after this PV has read P
+          // out of it
+          const int k2 = 2 * jj + i + NB;
+          if (k2 < n_slots) issue_qk(k2, kb);
+          if (i == 1) umma_commit(&kv_empty[s]);   // both query tiles have consumed K (QK^T issued earlier) and V of this tile
+          if (NB != 2 && ++kb_run == NB) { kb_run = 0; kp_run ^= 1; }
         }
-        umma_commit(&kv_empty[s]);
       }
+      umma_commit(all_done);
     }
     __syncwarp();
   } else {
@@ -323,18 +351,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     const int i = warp >> 2;                         // query tile of this warpgroup
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t t_S = tmem_base + kTmemS + i * kKT + lane_addr;
-    const uint32_t t_O = tmem_base + kTmemO + i * kD + lane_addr;
+    const uint32_t t_S0 = tmem_base + kTmemS + lane_addr;
+    const uint32_t t_O = tmem_base + kTmemO<ADAIN> + i * kD + lane_addr;
     const uint32_t t_A = tmem_base + kTmemAcc + i * kD + lane_addr;
     const float c = p.scale_log2;
 
-    // The two warpgroups take turns on the MUFU-bound exp pass (named barriers 1 and 2): while one exponentiates, the
-    // other waits for / reads its next scores and the tensor pipe runs its PV and QK^T.
-    if (kPingPong && i == 1) named_bar_arrive(1, 256);
     float m_ref = -INFINITY;     // reference max (log2 units) every stored exponential is relative to
     float l_seg = 0.f;           // row sum of the current segment
     float l_tot = 0.f;           // row sum of the finished segments (AdaIN path)
     bool acc_valid = false;      // the second accumulator holds finished segments
+    int buf_run = i;             // score buffer of slot 2 * jj + i and the phase of its barriers (NB = 2: buffer = query tile)
+    uint32_t sp = 0;
 
     // Tile bookkeeping is carried across the loop: ONE division at the start instead of three per tile and thread (the
     // AdaIN variant executed 8100 warp instructions per CTA and KV tile against 7020 for the plain one, all of the
@@ -346,8 +373,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
       const bool seg_last = (jj == n_tiles - 1) || (ADAIN && tr.t == chunk_tiles - 1);
       const int len = tr.ref < 0 ? p.s_own : p.s_ref;
       const int valid = min(kKT, len - tr.t * kKT);   // keys of this tile that exist
+      const int buf = NB == 2 ? i : buf_run;
+      const uint32_t t_S = t_S0 + buf * kKT;
 
-      mbar_wait(&s_full[i], jj & 1);
+      mbar_wait(&s_full[buf], sp);
       tc_fence_after();
       // pass 1: row max (TMEM reads are cheap; keeping all 128 scores live across both passes would spill)
       const float m_new = (valid < kKT ? row_max128<true>(t_S, valid) : row_max128<false>(t_S, valid)) * c;
@@ -357,7 +386,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
       } else {
         const bool need = m_new > m_ref + kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {          // TMEM ld/st are warp-collective: the warp rescales together
-          // s_full(jj) was committed after PV(jj-1): the accumulators are stable until we publish P(jj)
+          // PV(jj - 1) of this query tile is the last one issued (the next waits for the P published below). With two
+          // score buffers these scores were committed after it; with three it may still be accumulating into O.
+          if (NB > 2) {
+            mbar_wait(&o_done[i], (jj - 1) & 1);
+            tc_fence_after();
+          }
           const float f = need ? fast_exp2(m_ref - m_new) : 1.0f;
           if (need) m_ref = m_new;
           if (!seg_first) tmem_scale64(t_O, f);
@@ -370,12 +404,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
       }
 
       // pass 2: exponentials -> P (TMEM), row sum
-      if (kPingPong) named_bar_sync(1 + i, 256);            // my turn on the MUFU pipe
       l_seg += valid < kKT ? exp_pass128<true>(t_S, c, -m_ref, valid) : exp_pass128<false>(t_S, c, -m_ref, valid);
-      if (kPingPong && !(i == 1 && jj == n_tiles - 1)) named_bar_arrive(1 + (i ^ 1), 256);   // hand the MUFU pipe over
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_full[i]);
+      mbar_arrive(&p_full[buf]);
+      if (NB == 2) {
+        sp ^= 1;
+      } else {
+        buf_run += 2;
+        if (buf_run >= NB) { buf_run -= NB; sp ^= 1; }
+      }
 
       if (ADAIN && seg_last) {
         // fold the finished segment into the second accumulator: acc += a * O_seg + b * rowsum(P_seg)
@@ -426,7 +464,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) shared_attn_kernel(const __gr
     const int qrow = (2 * pair + i) * kQT + row;
     if (n_tiles > 0) {
       if (!ADAIN) {
-        mbar_wait(&o_done[i], (n_tiles - 1) & 1);
+        mbar_wait(all_done, 0);      // not o_done: with three score buffers its phase may be two PVs behind
         tc_fence_after();
       }
       const uint32_t t_src = ADAIN ? t_A : t_O;
