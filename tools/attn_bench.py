@@ -9,6 +9,7 @@ SHAPES = [  # (B, H, S, own, n_ref, adain)
     (32, 5, 4096, True, 0, False), (8, 5, 4096, False, 4, True), (8, 5, 4096, True, 4, True), (32, 10, 1024, True, 0, False),
     (8, 10, 1024, False, 4, True), (4, 5, 4096, True, 0, False), (1, 5, 4096, False, 4, True), (1, 10, 1024, False, 4, True),
     (1, 20, 256, False, 4, True), (64, 5, 4096, False, 1, True), (4, 5, 4096, False, 8, True),
+    (8, 5, 4096, False, 4, False), (64, 5, 4096, False, 1, False),   # the reference chunks through the plain variant
 ]
 
 
