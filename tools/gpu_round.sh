@@ -37,7 +37,7 @@ ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_launches.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
   wc -l $OUT/${TAG}_launches.csv ;;
-caps|capsattn|capsnew)
+caps|capsattn|capsnew|capsplain)
   # ncu --set full of the dominant kernels on micro-drivers; summarised on the box (reports are ~10 MB each and
   # gpurun_out is capped at 64 MiB), only the text summaries and ncu_traffic.json travel back
   cap() { n=$1; k=$2; key=$3; shift 3
@@ -52,6 +52,11 @@ caps|capsattn|capsnew)
   cap conv_up2x_256 conv "ir_conv_gemm:m1048576_k1024_n256_ks3s1_up2x" tools/gemm_one.py up 4 256 256 256
   cap conv_in_tma_store conv "ir_conv_gemm:m1048576_k64_n128_ks1s1" tools/gemm_one.py lin_ts 4 1048576 64 128 0
   cap conv_in_row_store conv "ir_conv_gemm:m1048576_k64_n128_ks1s1_rowstores" tools/gemm_one.py lin_ts 4 1048576 64 128 1
+  elif [ $w = capsplain ]; then
+  # the plain variant on three rotating score buffers, next to the (unchanged) shared-image variant
+  cap attn_b32 shared_attn "ir_shared_attn_fwd:b32_h5_sq4096_skv4096" tools/attn_one.py 32 5 4096 1 0 0
+  cap attn_b4 shared_attn "ir_shared_attn_fwd:b4_h5_sq4096_skv4096" tools/attn_one.py 4 5 4096 1 0 0
+  cap attn_shared_b1 shared_attn "ir_shared_attn_fwd:b1_h5_sq4096_skv16384_adain" tools/attn_one.py 1 5 4096 0 4 1
   elif [ $w = capsattn ]; then
   cap attn_shared_b1 shared_attn "ir_shared_attn_fwd:b1_h5_sq4096_skv16384_adain" tools/attn_one.py 1 5 4096 0 4 1
   cap attn_shared_b8 shared_attn "ir_shared_attn_fwd:b8_h5_sq4096_skv16384_adain" tools/attn_one.py 8 5 4096 0 4 1
