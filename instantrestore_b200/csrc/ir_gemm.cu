@@ -39,7 +39,9 @@ constexpr int kABytes = kBM * kBK * 2;  // 16 KB
 struct GemmKParams {
   CUtensorMap tma_a[4];
   CUtensorMap tma_b;
-  CUtensorMap tma_out;   // TMA-store epilogue (persistent kernel, TSTORE): out as [M rows][N columns], 64-column x 128-row boxes
+  CUtensorMap tma_out;   // TMA-store epilogue: out as [M rows][N columns]; persistent kernel (TSTORE) 64-column x 128-row boxes,
+                         // 128-wide halo pair 64-column x 32-row boxes (one per epilogue warp)
+  CUtensorMap tma_res;   // 128-wide halo pair: the residual, same boxes (TMA load into the warp's staging tile)
   int M, N, n_out;
   int kc_per_tap, taps;
   int tiles_w, tiles_h;
@@ -1140,20 +1142,23 @@ static int launch_pair(const GemmKParams& kp, int bn_pair, cudaStream_t stream) 
 // K order: channel slice, then tap (the kernels above run tap, then slice): same products, different fp32 summation
 // order.
 constexpr int kHaloW = 130;
+// weight-ring depth: 16 KB slots on the single CTA (5) and the 256-wide pair (7), 8 KB slots on the 128-wide pair (10)
+constexpr int halo_b_slots(int bn, bool pair) { return pair ? (bn == 256 ? 7 : 10) : 5; }
 
 template <int BN, bool PAIR, bool RESID>
 __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __grid_constant__ GemmKParams p) {
-  static_assert((BN == 128 && !PAIR) || (BN == 256 && PAIR), "halo kernel: 128-wide single CTA or 256-wide CTA pair");
+  static_assert(BN == 128 || (BN == 256 && PAIR), "halo kernel: 128-wide single CTA, 128- or 256-wide CTA pair");
   constexpr int MSUB = PAIR ? 1 : 2;                       // output image rows per CTA
   constexpr int HROWS = MSUB + 2;
   constexpr uint32_t HALO_BYTES = HROWS * kHaloW * 128;    // one 64-channel halo box
   constexpr int HALO_SLOT = (HALO_BYTES + 1023) / 1024 * 1024;
   constexpr int NA = 2;
-  constexpr int NB = PAIR ? 7 : 5;
-  constexpr int B_BYTES = 128 * kBK * 2;                   // 128 weight rows of one tap (pair: this CTA's half)
-  constexpr uint32_t STAGE_COLS = 256;                     // accumulator columns per stage (2 x 128 or 1 x 256)
+  constexpr int NB = halo_b_slots(BN, PAIR);
+  constexpr int B_ROWS = PAIR ? BN / 2 : BN;               // weight rows of one tap in this CTA (pair: its half of the N tile)
+  constexpr int B_BYTES = B_ROWS * kBK * 2;
+  constexpr uint32_t STAGE_COLS = 256;                     // accumulator columns per stage (2 x 128, 1 x 256, or 128 of them)
   constexpr uint32_t TMEM_COLS = 512;
-  constexpr uint32_t IDESC = PAIR ? umma_idesc_f16(256, 256, 0, 0) : umma_idesc_f16(128, 128, 0, 0);
+  constexpr uint32_t IDESC = PAIR ? umma_idesc_f16(256, BN, 0, 0) : umma_idesc_f16(128, 128, 0, 0);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1165,8 +1170,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
   uint64_t* b_empty = b_full + NB;
   uint64_t* tfull_bar = b_empty + NB;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // TIO (128-wide pair: the shared memory the 8 KB weight slots leave free): every epilogue warp owns a 32-row x 64-column
+  // staging tile in the tensor map's 128-byte-swizzled box layout. The residual box is TMA-LOADED into it while the tile's
+  // MMAs run, the thread (= pixel row) adds its accumulator in place, and ONE elected lane TMA-STORES the box: no
+  // thread-per-row global access is left in the epilogue (ncu on the single-CTA kernel: L1TEX LSU pipe 68 %, the busiest
+  // unit of the 128-channel layers, 32 sectors per warp-wide 256-bit access).
+  constexpr bool TIO = PAIR && BN == 128;
+  uint64_t* r_full = tempty_bar + 2;                          // TIO: 8 (per epilogue warp): residual box landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + (TIO ? 8 : 0));
   float* sBias = reinterpret_cast<float*>(tmem_slot + 4);     // BN bias values of the current N tile (16-byte aligned)
+  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sBias + BN) + 1023) & ~uintptr_t(1023));   // TIO: 8 x 4 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1195,6 +1208,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], PAIR ? 512 : 256);
+    }
+    if (TIO) {
+      for (int w = 0; w < 8; ++w) mbar_init(&r_full[w], 1);
+      tma_prefetch_desc(&p.tma_out);
+      if (RESID) tma_prefetch_desc(&p.tma_res);
     }
     fence_mbar_init();
   }
@@ -1236,7 +1254,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
             if (PAIR) {
               if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], 2 * B_BYTES);
               tma_load_2d_pair(sB + sb * B_BYTES, &p.tma_b, dsmem_addr(smem_u32(&b_full[sb]), 0), tap * c_in + c * kBK,
-                               nt * BN + static_cast<int>(rank) * 128);
+                               nt * BN + static_cast<int>(rank) * B_ROWS);
             } else {
               mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
               tma_load_2d(sB + sb * B_BYTES, &p.tma_b, &b_full[sb], tap * c_in + c * kBK, nt * BN);
@@ -1311,6 +1329,56 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
         bias_nt = nt;
       }
       const long grow0 = (static_cast<long>(img) * p.img_h + h0) * p.img_w + w0 + row;
+      if constexpr (TIO) {
+        uint8_t* stg = sStage + (warp - 2) * 4096;
+        uint64_t* rbar = &r_full[warp - 2];
+        const int orow0 = static_cast<int>(grow0) - lane, ocol0 = nt * BN + c_begin;
+        // the previous tile's store has finished reading the staging tile; the residual box of this tile lands in it while
+        // the MMAs of the tile run (this point is reached right after the previous tile's epilogue)
+        if (elect_one()) {
+          tma_store_wait_read<0>();
+          if (RESID) {
+            mbar_arrive_expect_tx(rbar, 4096);
+            tma_load_2d(stg, &p.tma_res, rbar, ocol0, orow0);
+          }
+        }
+        __syncwarp();
+        mbar_wait(&tfull_bar[as], (local >> 1) & 1);
+        tc_fence_after();
+        if (RESID) mbar_wait(rbar, local & 1);
+        const uint32_t taddr = tmem_base + as * STAGE_COLS + lane_addr;
+#pragma unroll
+        for (int ci = 0; ci < kChunks; ++ci) {
+          const int c0 = c_begin + ci * 32;
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          uint4 res[4] = {};
+          if (RESID) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)     // 16-byte piece j = ci*4+q of this row, at its swizzled slot j ^ (row & 7)
+              res[q] = *reinterpret_cast<const uint4*>(stg + lane * 128 + (((ci * 4 + q) ^ (lane & 7)) << 4));
+          }
+          uint4 packed[4];
+          epilogue_pack32<false, false>(v, res, RESID, p, grow0, nt * BN + c0, p.bias ? sBias + c0 : nullptr, 0, packed);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((ci * 4 + q) ^ (lane & 7)) << 4)) = packed[q];
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(dsmem_addr(smem_u32(&tempty_bar[as]), 0));   // the accumulator stage is drained
+        fence_proxy_async_smem();                   // my generic-proxy writes are visible to the TMA engine
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_2d(&p.tma_out, stg, ocol0, orow0);
+          tma_store_commit();
+        }
+        __syncwarp();
+        continue;
+      }
       uint4 resid[RESID ? MSUB : 1][RESID ? kChunks : 1][4];
       if (RESID) {
 #pragma unroll
@@ -1343,6 +1411,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv3_halo_kernel(const __
       if (PAIR) mbar_arrive_cluster(dsmem_addr(smem_u32(&tempty_bar[as]), 0));
       else mbar_arrive(&tempty_bar[as]);
     }
+    if (TIO) {                         // shared memory stays valid until the last store has read it
+      if (elect_one()) tma_store_wait_read<0>();
+      __syncwarp();
+    }
   }
 
   tc_fence_before();
@@ -1357,7 +1429,8 @@ template <int BN, bool PAIR, bool RESID>
 static int launch_halo_r(const GemmKParams& kp, cudaStream_t stream) {
   constexpr int msub = PAIR ? 1 : 2;
   constexpr int halo_slot = ((msub + 2) * kHaloW * 128 + 1023) / 1024 * 1024;
-  constexpr int smem = 2 * halo_slot + (PAIR ? 7 : 5) * 128 * kBK * 2 + 1024 + 256 + 1024;   // + the staged bias tile
+  constexpr int smem = 2 * halo_slot + halo_b_slots(BN, PAIR) * (PAIR ? BN / 2 : BN) * kBK * 2 + 1024 + 256 + 1024 +   // + the staged bias tile
+                       (PAIR && BN == 128 ? 1024 + 8 * 4096 : 0);                                                      // + the epilogue warps' staging tiles
   static PerDeviceOnce attr_once;   // function attributes are per device
   bool& attr_done = attr_once.slot();
   if (!attr_done) {
@@ -1374,9 +1447,10 @@ static int launch_halo_r(const GemmKParams& kp, cudaStream_t stream) {
   return 0;
 }
 
-static int launch_halo(const GemmKParams& kp, bool pair, cudaStream_t stream) {
+static int launch_halo(const GemmKParams& kp, int pair_bn, cudaStream_t stream) {
   const bool resid = kp.residual != nullptr;
-  if (pair) return resid ? launch_halo_r<256, true, true>(kp, stream) : launch_halo_r<256, true, false>(kp, stream);
+  if (pair_bn == 256) return resid ? launch_halo_r<256, true, true>(kp, stream) : launch_halo_r<256, true, false>(kp, stream);
+  if (pair_bn == 128) return resid ? launch_halo_r<128, true, true>(kp, stream) : launch_halo_r<128, true, false>(kp, stream);
   return resid ? launch_halo_r<128, false, true>(kp, stream) : launch_halo_r<128, false, false>(kp, stream);
 }
 
@@ -1531,8 +1605,15 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
     if (p->halo == 2 && !eligible)
       return set_error(IR_ERR_SHAPE, "ir_conv_gemm: halo needs a 3x3 stride-1 conv, w %% 128 == 0, even h, c_out %% 128 == 0, no K split / tile_n");
     if (eligible && p->halo != 1) {
-      const bool pair = p->c_out % 256 == 0 && p->cta_pair != 1;
-      const long tiles = static_cast<long>(p->batch) * (p->h_in / 2) * (p->w_in / 128) * (p->c_out / (pair ? 256 : 128));
+      // CTA pair: 256-wide N tiles, or 128-wide ones for the 128-channel layers (each CTA loads one image row and HALF of the
+      // weight tile: 96 B/clk of shared-memory operand reads per SM instead of the 128 B/clk -- the port limit -- of the
+      // single-CTA 128 x 128 MMA). cta_pair = 1 keeps the single-CTA kernel (A/B).
+      // The 128-wide pair moves its outputs / residual with TMA: rows must be 16-byte multiples from a 16-byte-aligned base.
+      const bool tio_ok = (reinterpret_cast<uintptr_t>(p->out) & 15) == 0 &&
+                          (!p->residual || ((reinterpret_cast<uintptr_t>(p->residual) & 15) == 0 && p->res_row_stride % 8 == 0));
+      const int pair_bn = p->cta_pair == 1 ? 0 : (p->c_out % 256 == 0 ? 256 : (tio_ok ? 128 : 0));
+      const bool pair = pair_bn != 0;
+      const long tiles = static_cast<long>(p->batch) * (p->h_in / 2) * (p->w_in / 128) * (p->c_out / (pair_bn == 256 ? 256 : 128));
       if (p->halo == 2 || (p->no_persistent != 1 && tiles >= (pair ? 74 : 148))) {
         kp.img_h = p->h_in;
         kp.img_w = p->w_in;
@@ -1544,10 +1625,20 @@ static int conv_gemm_dispatch(const ir_conv_gemm_params* p, ir_stream_t stream_,
         if (int rc = make_tmap_f16(&kp.tma_a[0], p->a, 4, dims, str, box)) return rc;
         uint64_t wdims[2] = {static_cast<uint64_t>(taps) * p->c_in, static_cast<uint64_t>(p->c_out)};
         uint64_t wstr[1] = {static_cast<uint64_t>(taps) * p->c_in * 2};
-        uint32_t wbox[2] = {64, 128};
+        uint32_t wbox[2] = {64, pair_bn == 128 ? 64u : 128u};
         if (int rc = make_tmap_f16(&kp.tma_b, p->w, 2, wdims, wstr, wbox)) return rc;
+        if (pair_bn == 128) {
+          uint64_t odims[2] = {static_cast<uint64_t>(p->c_out), static_cast<uint64_t>(kp.M)};
+          uint64_t ostr[1] = {static_cast<uint64_t>(p->out_row_stride) * 2};
+          uint32_t obox[2] = {64, 32};
+          if (int rc = make_tmap_f16(&kp.tma_out, p->out, 2, odims, ostr, obox)) return rc;
+          if (p->residual) {
+            uint64_t rstr[1] = {static_cast<uint64_t>(kp.res_stride) * 2};
+            if (int rc = make_tmap_f16(&kp.tma_res, p->residual, 2, odims, rstr, obox)) return rc;
+          }
+        }
         *stats_fused = kp.gn_partial != nullptr;
-        return launch_halo(kp, pair, stream);
+        return launch_halo(kp, pair_bn, stream);
       }
     }
   }

@@ -173,7 +173,8 @@ def test_conv3x3_cta_pair(L, B, H, Ci, Co, stride):
 ])
 def test_conv3x3_halo(L, B, H, W, Ci, Co, use_res):
     """Halo kernel (input slice staged once, nine shifted views): image borders (TMA zero fill), several 128-pixel tiles
-    per row, odd tile counts over the CTA pair, 128-wide (single CTA) and 256-wide (pair) N tiles."""
+    per row, odd tile counts over the CTA pair, 128-wide (CTA pair by default, single CTA with cta_pair=1) and 256-wide
+    (pair) N tiles."""
     g = _gen(33)
     x = torch.randn(B, Ci, H, W, device="cuda", generator=g).half()
     w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Ci)).half()
@@ -188,6 +189,10 @@ def test_conv3x3_halo(L, B, H, W, Ci, Co, use_res):
     out = L.conv_gemm(a, wk, halo=2, **kw)
     assert rel_l2(out, ref) <= TOL
     assert torch.equal(out, L.conv_gemm(a, wk, halo=2, **kw))
+    if Co % 256:                                       # 128-wide N tiles: the single-CTA kernel computes the same sums in the same order
+        single = L.conv_gemm(a, wk, halo=2, cta_pair=1, **kw)
+        assert rel_l2(single, ref) <= TOL
+        assert torch.equal(out, single)
     if (W & (W - 1)) == 0 and (H & (H - 1)) == 0:      # the tap-by-tap kernels need power-of-two images
         assert rel_l2(out, L.conv_gemm(a, wk, halo=1, **kw)) <= 3e-4      # same products, different fp32 summation order
 
@@ -310,7 +315,8 @@ def test_upsample2x_rejects_unsupported_combinations(L):
 
 
 @pytest.mark.parametrize("kind,B,H,W,Ci,Co,kw", [
-    ("conv", 2, 128, 128, 128, 128, {}),                    # halo kernel, single CTA
+    ("conv", 2, 128, 128, 128, 128, {}),                    # halo kernel, 128-wide CTA pair
+    ("conv", 2, 128, 128, 128, 128, dict(cta_pair=1)),      # halo kernel, single CTA
     ("conv", 1, 128, 128, 256, 256, {}),                    # halo kernel, CTA pair
     ("conv", 4, 64, 64, 512, 512, dict(halo=1)),            # CTA-pair kernel (tap by tap)
     ("conv", 2, 64, 64, 128, 256, dict(halo=1, cta_pair=1)),  # persistent single-CTA kernel

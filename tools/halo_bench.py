@@ -35,7 +35,7 @@ def main():
         w = (torch.randn(Co, 9 * Ci, device="cuda", generator=g) / math.sqrt(9 * Ci)).half()
         bias = torch.randn(Co, device="cuda", generator=g)
         res = torch.randn(B * H * H, Co, device="cuda", generator=g).half()
-        f = lambda h: L.conv_gemm(a, w, batch=B, h_in=H, w_in=H, c_in=Ci, ksize=3, bias=bias, residual=res, halo=h)
+        f = lambda h, cp=0: L.conv_gemm(a, w, batch=B, h_in=H, w_in=H, c_in=Ci, ksize=3, bias=bias, residual=res, halo=h, cta_pair=cp)
         flops = 2.0 * B * H * H * 9 * Ci * Co
         o1, o2 = f(1), f(2)
         torch.cuda.synchronize()
@@ -46,6 +46,12 @@ def main():
         if not check_only:
             t1, t2 = timeit(lambda: f(1)), timeit(lambda: f(2))
             line += f" | taps {t1:8.1f} us {flops / t1 / 1e6:7.1f} TF/s | halo {t2:8.1f} us {flops / t2 / 1e6:7.1f} TF/s"
+            if Co % 256:      # 128-wide outputs: the CTA pair (default) against the single-CTA kernel
+                o3 = f(2, 1)
+                torch.cuda.synchronize()
+                e3 = ((o3.float() - o2.float()).norm() / o2.float().norm()).item()
+                t3 = timeit(lambda: f(2, 1))
+                line += f" | single CTA {t3:8.1f} us {flops / t3 / 1e6:7.1f} TF/s (rel-L2 vs pair {e3:.1e})"
         print(line, flush=True)
     print("halo_bench:", "ALL OK" if bad == 0 else f"{bad} MISMATCHES")
     sys.exit(1 if bad else 0)
