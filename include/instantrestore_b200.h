@@ -97,7 +97,10 @@ typedef struct {
   int gn_groups;
   int halo; /* A-B measurement: 0 = auto, 1 = never, 2 = always the halo kernel (3x3 stride 1, w_in % 128 == 0, even
                h_in, c_out % 128 == 0): each 64-channel input slice is staged once per tile as a (rows+2) x 130 pixel box
-               and the nine taps read shifted views of it */
+               and the nine taps read shifted views of it. On the halo kernel cta_pair = 1 keeps 128-wide outputs
+               (c_out % 256 != 0) on the single-CTA kernel; the default is the 128-wide CTA pair, whose epilogue moves the
+               residual and the outputs with TMA (out / residual 16-byte aligned, res_row_stride % 8 == 0; otherwise the
+               single-CTA kernel runs) */
   int wide_io; /* A-B measurement: 0 = auto (256-bit residual loads / output stores in the epilogue whenever out and
                   residual rows are 32-byte aligned; results are bit-identical), 1 = always 128-bit */
   void* col_partial; /* optional fp32 [M / 32, c_out - col_begin, 2]: per (32-row slab, output column >= col_begin) the (mean, M2)

@@ -79,3 +79,15 @@ def test_tma_store_epilogue_is_a_bulk_tensor_store(sass):
     for name, lines in found.items():
         text = "\n".join(lines)
         assert "UTMASTG.2D" in text, f"{name}: no TMA store"
+
+
+def test_halo_pair128_epilogue_runs_on_tensor_maps(sass):
+    """The 128-wide CTA-pair halo kernel moves its residual in and its outputs out with TMA (UTMALDG / UTMASTG) and keeps
+    no vectorised per-thread global store of output rows (STG.E.ENL2.256 / STG.E.128); the statistics' 8-byte stores stay."""
+    found = _kernels(sass, "conv3_halo_kernelILi128ELb1E")
+    assert len(found) == 2, "expected the residual and the no-residual instantiation of conv3_halo_kernel<128, pair>"
+    for name, lines in found.items():
+        text = "\n".join(lines)
+        assert "UTMASTG.2D" in text, f"{name}: no TMA store"
+        assert not re.search(r"STG\.E(\.ENL2)?\.(128|256)", text), f"{name}: per-thread row stores left in the epilogue"
+        assert "UTCHMMA.2CTA" in text, f"{name}: not a cta_group::2 kernel"
