@@ -2,7 +2,7 @@
 # compute-sanitizer over the kernel-level parity tests: memcheck on every kernel family at small
 # shapes, racecheck (shared-memory hazards) and synccheck on the kernels that synchronise through shared memory /
 # clusters without the async proxy (norms, AdaIN statistics, concat, layout kernels). Summaries -> gpurun_out/<tag>_san_*.txt
-# usage: tools/sanitize.sh <tag> [new]
+# usage: tools/sanitize.sh <tag> [new|last]
 TAG=${1:-r02}; OUT=gpurun_out; mkdir -p $OUT
 SAN=/usr/local/cuda/bin/compute-sanitizer
 SMALL='groupnorm or layernorm or adain or concat or upsample or latent_in or softmax'
@@ -14,6 +14,11 @@ run() {  # name tool timeout pytest-args...
     grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|Invalid|hazard|error" $OUT/${TAG}_san_$n.log | sort | uniq -c | sort -rn | head -15; } > $OUT/${TAG}_san_$n.txt
   cat $OUT/${TAG}_san_$n.txt
 }
+if [ "${2:-all}" = last ]; then  # the kernels of the last session: three-buffer attention, 128-wide halo pair (TMA-in / TMA-out epilogue)
+  run attn3_memcheck memcheck 600 tests/test_gpu_kernels.py -k "attention"
+  run halo_pair128_memcheck memcheck 600 tests/test_gpu_kernels.py -k "halo or pass_a"
+  exit 0
+fi
 if [ "${2:-all}" = new ]; then   # the kernels added last: folded upsamplers, TMA-store epilogue, one-launch FreeU, image patches
   run new_memcheck memcheck 1200 tests/test_gpu_kernels.py -k "upsample2x or tma_store or concat_freeu or image_patches"
   run new_racecheck racecheck 600 tests/test_gpu_kernels.py -k "concat_freeu or image_patches"
