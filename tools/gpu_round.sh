@@ -37,7 +37,7 @@ ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/${TAG}_launches.csv \
      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-trace --no-graph > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu rc=$?"
   wc -l $OUT/${TAG}_launches.csv ;;
-caps|capsattn|capsnew|capsplain)
+caps|capsattn|capsnew|capsplain|capshalo)
   # ncu --set full of the dominant kernels on micro-drivers; summarised on the box (reports are ~10 MB each and
   # gpurun_out is capped at 64 MiB), only the text summaries and ncu_traffic.json travel back
   cap() { n=$1; k=$2; key=$3; shift 3
@@ -52,6 +52,10 @@ caps|capsattn|capsnew|capsplain)
   cap conv_up2x_256 conv "ir_conv_gemm:m1048576_k1024_n256_ks3s1_up2x" tools/gemm_one.py up 4 256 256 256
   cap conv_in_tma_store conv "ir_conv_gemm:m1048576_k64_n128_ks1s1" tools/gemm_one.py lin_ts 4 1048576 64 128 0
   cap conv_in_row_store conv "ir_conv_gemm:m1048576_k64_n128_ks1s1_rowstores" tools/gemm_one.py lin_ts 4 1048576 64 128 1
+  elif [ $w = capshalo ]; then
+  # 128-channel layer (128->128 @512^2, 4 images, residual): the 128-wide CTA pair with the TMA-in / TMA-out epilogue, and the single-CTA kernel
+  cap conv_halo_pair128 conv3_halo "ir_conv_gemm:m1048576_k1152_n128_ks3s1" tools/gemm_one.py conv3 4 512 128 128
+  cap conv_halo_128_single conv3_halo "ir_conv_gemm:m1048576_k1152_n128_ks3s1_single" tools/gemm_one.py conv3 4 512 128 128 1
   elif [ $w = capsplain ]; then
   # the plain variant on three rotating score buffers, next to the (unchanged) shared-image variant
   cap attn_b32 shared_attn "ir_shared_attn_fwd:b32_h5_sq4096_skv4096" tools/attn_one.py 32 5 4096 1 0 0
