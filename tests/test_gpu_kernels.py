@@ -197,6 +197,24 @@ def test_conv3x3_halo(L, B, H, W, Ci, Co, use_res):
         assert rel_l2(out, L.conv_gemm(a, wk, halo=1, **kw)) <= 3e-4      # same products, different fp32 summation order
 
 
+def test_conv3x3_halo_pair128_strided_views(L):
+    """The 128-wide halo pair moves residual and outputs through tensor maps: they may be column slices of wider buffers
+    (row strides and column offsets that are multiples of 8 elements, the alignment ir_conv_gemm asks of every call)."""
+    g = _gen(41)
+    B, H, W, Ci, Co = 1, 128, 128, 128, 128
+    a = torch.randn(B * H * W, Ci, device="cuda", generator=g).half()
+    wk = (torch.randn(Co, 9 * Ci, device="cuda", generator=g) / math.sqrt(9 * Ci)).half()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    res_wide = torch.randn(B * H * W, Co + 64, device="cuda", generator=g).half()
+    res = res_wide[:, 8:8 + Co]                                  # stride Co + 64, 16-byte aligned column offset
+    kw = dict(batch=B, h_in=H, w_in=W, c_in=Ci, ksize=3, bias=bias, split_k=1, halo=2)
+    ref = L.conv_gemm(a, wk, residual=res.contiguous(), cta_pair=1, **kw)      # single CTA, contiguous
+    out_wide = torch.full((B * H * W, 2 * Co), 7.0, device="cuda").half()
+    L.conv_gemm(a, wk, residual=res, out=out_wide[:, Co:], **kw)               # pair: strided residual in, strided out
+    assert torch.equal(out_wide[:, Co:], ref)
+    assert bool((out_wide[:, :Co] == 7.0).all())                               # the neighbouring columns are untouched
+
+
 @pytest.mark.parametrize("M,K,N,kw", [
     (4096, 64, 128, {}), (1000, 64, 128, {}), (16384, 320, 640, {}), (77, 128, 256, {}), (262144, 64, 128, dict(stats=True)),
     (8192, 320, 1280, dict(cols=True)), (4096, 640, 384, dict(act=True)), (128 * 149 + 5, 64, 128, {}),
