@@ -161,11 +161,14 @@ __global__ void __launch_bounds__(256) gn_merge_kernel(const float2* __restrict_
   }
 }
 
+constexpr int kGnApplyThreads = 256;
+
 // ---- GroupNorm pass B: y = a[c] * x + b[c] (+ SiLU) with a = rstd * gamma, b = beta - mean * a. Every thread owns
 // fixed 8-channel vectors (its 16 affine coefficients live in registers) and walks the rows of its CTA's row range
 // with 4 sixteen-byte loads in flight: no per-element index math, no shared-memory lookups.
 // grid = (row blocks, batch).
-__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __half* __restrict__ x, int x_stride, int hw, int channels,
+template <int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) gn_apply_kernel(const __half* __restrict__ x, int x_stride, int hw, int channels,
                                                        int groups, int rows_per_block, const float2* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int silu, __half* __restrict__ out, int out_stride) {
@@ -174,8 +177,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __half* __restri
   pdl_wait();
   const int cpg = channels / groups;
   const int vpr = channels >> 3;
-  const int lanes = vpr < 256 ? vpr : 256;
-  const int rgroups = 256 / lanes;
+  const int lanes = vpr < NT ? vpr : NT;
+  const int rgroups = NT / lanes;
   const int vec0 = threadIdx.x % lanes, rg = threadIdx.x / lanes;
   if (rg >= rgroups) return;
   const int r0 = blockIdx.x * rows_per_block;
@@ -564,7 +567,11 @@ extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
   float2* stats = partial + static_cast<size_t>(p->batch) * kGnMaxSlabs * p->groups;
   int slabs, rps;
   const int vpr = p->channels >> 3;
-  const int rgroups = vpr < 256 ? 256 / vpr : 1;
+  // Threads per apply CTA (64 registers each). 128: a CTA takes 8192 registers, so one fits NEXT TO a resident 320-thread x
+  // 168-register conv / attention CTA of another request (11776 registers free per SM) and the HBM-bound pass overlaps the
+  // tensor-bound one; 256-thread CTAs (16384 registers) have to wait for the SM. IR_GN_APPLY_THREADS=256|128 for the A/B.
+  static const int apply_nt = [] { const char* e = getenv("IR_GN_APPLY_THREADS"); const int v = e ? atoi(e) : 0; return v == 128 || v == 256 ? v : kGnApplyThreads; }();
+  const int rgroups = vpr < apply_nt ? apply_nt / vpr : 1;
   if (p->partial_in) {
     // pass A already ran in the epilogue of the convolution that produced x: 32-pixel slabs
     if (p->hw % 32 != 0) return set_error(IR_ERR_SHAPE, "ir_groupnorm: partial_in needs hw %% 32 == 0 (hw=%d)", p->hw);
@@ -579,14 +586,19 @@ extern "C" int ir_groupnorm(const ir_groupnorm_params* p, ir_stream_t stream_) {
   IR_CUDA_LAUNCH_CHECK("gn_merge launch");
   // apply: one wave of 4 resident CTAs per SM (64 registers: two sweeps of four 16-byte loads per thread in flight),
   // >= 4 * rgroups rows per CTA so the pipelined loop is used
-  int row_blocks = (148 * 4 + p->batch - 1) / p->batch;
+  int row_blocks = (148 * (1024 / apply_nt) + p->batch - 1) / p->batch;
   int min_rows = 4 * rgroups;
   int rpb = (p->hw + row_blocks - 1) / row_blocks;
   if (rpb < min_rows) rpb = min_rows;
   row_blocks = (p->hw + rpb - 1) / rpb;
-  IR_LAUNCH(gn_apply_kernel, dim3(row_blocks, p->batch), 256, 0, stream,
-            static_cast<const __half*>(p->x), p->x_row_stride, p->hw, p->channels, p->groups, rpb, stats, p->gamma, p->beta, p->silu,
-            static_cast<__half*>(p->out), p->out_row_stride);
+  if (apply_nt == 128)
+    IR_LAUNCH(gn_apply_kernel<128>, dim3(row_blocks, p->batch), 128, 0, stream,
+              static_cast<const __half*>(p->x), p->x_row_stride, p->hw, p->channels, p->groups, rpb, stats, p->gamma, p->beta, p->silu,
+              static_cast<__half*>(p->out), p->out_row_stride);
+  else
+    IR_LAUNCH(gn_apply_kernel<256>, dim3(row_blocks, p->batch), 256, 0, stream,
+              static_cast<const __half*>(p->x), p->x_row_stride, p->hw, p->channels, p->groups, rpb, stats, p->gamma, p->beta, p->silu,
+              static_cast<__half*>(p->out), p->out_row_stride);
   IR_CUDA_LAUNCH_CHECK("gn_apply launch");
   return 0;
 }
