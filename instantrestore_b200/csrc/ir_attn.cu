@@ -15,9 +15,12 @@
 //       800 clk of issue, MMA and commit latency, 21 % of the stall samples of the two-buffer kernel) is hidden.
 //   warp 8 (one lane): TMA producer — both Q tiles once, then K/V tiles straight out of the token-major projection
 //       outputs (the head split is just the TMA column coordinate), 128B-swizzled, 4-stage ring.
-//   warp 9 (one lane): tcgen05.mma issuer — S_i = Q_i K_j^T (TMEM, 128 columns per tile), O_i += P_i V_j (A = P from
-//       TMEM, B = V consumed MN-major, no transpose), issued as PV_i(j), QK_i(j+1) back to back so the score
-//       buffer is refilled as soon as its P has been consumed. O accumulates IN TMEM across the KV tiles of a segment; the running max is only
+//   warp 9 (one lane): tcgen05.mma issuer — S = Q_i K_j^T (TMEM, 128 columns per buffer), O_i += P_i V_j (A = P from
+//       TMEM, B = V consumed MN-major, no transpose), issued as PV of slot k, QK^T of slot k + NB back to back so a score
+//       buffer is refilled as soon as its P has been consumed; the K tiles of the QK^Ts to come are waited for at the top
+//       of the iteration, off the chain "P published -> PV -> QK^T -> scores" (every instruction between the P barrier and
+//       the QK^T issue is exposed on the two-buffer variant: hoisting that wait was worth 3 %).
+//       O accumulates IN TMEM across the KV tiles of a segment; the running max is only
 //       raised when it grows by more than 2^8 (lazy rescale, done in TMEM by the softmax warps), so the common tile
 //       costs no accumulator traffic at all.
 // AdaIN: sum_r P_r (a_r*V_r + b_r) = a_r*(P_r V_r) + b_r*rowsum(P_r) — a segment is one reference chunk; at its end
